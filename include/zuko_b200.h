@@ -1,0 +1,229 @@
+/*
+ * zuko_b200 — C ABI of the B200-native (sm_100a) engine for Zuko's flow hot path.
+ *
+ * The reference (probabilists/zuko @ 1063ae4) has NO FFI, plugin registry or
+ * native code: its seams are Python protocols.  The entry points below are the
+ * boundary a native replacement of the hot path binds at; each cites the
+ * reference interface (file:line in /root/reference) it replaces.  The Python
+ * host side in zuko_b200/ mirrors the reference's LazyTransform /
+ * LazyDistribution / Flow API on top of these calls (see INTEGRATION.md for the
+ * ctypes stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns a zk_status (0 = OK) and never throws;
+ *     zk_last_error() gives a thread-local message for the last failure;
+ *   - all tensor pointers are DEVICE pointers to fp32 row-major data unless the
+ *     parameter comment says "host"; `ld*` are row strides in ELEMENTS;
+ *     ldc == 0 broadcasts a single context row (zuko/utils.py:236-244,
+ *     zuko/flows/autoregressive.py:209);
+ *   - calls are asynchronous on the given CUDA stream (cudaStream_t passed as
+ *     void*); the caller owns every input / output / workspace buffer;
+ *   - handles (zk_mlp, zk_layer) own only packed copies of the weights and are
+ *     immutable after creation => re-entrant across streams when each call has
+ *     its own workspace;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns ZK_ECUDA.
+ */
+#ifndef ZUKO_B200_H
+#define ZUKO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ZK_OK = 0,
+    ZK_EINVAL = 1,       /* bad shape / pointer / alignment / workspace too small */
+    ZK_EUNSUPPORTED = 2, /* option the engine does not implement */
+    ZK_ECUDA = 3,        /* CUDA runtime error (message in zk_last_error) */
+    ZK_ENOMEM = 4
+} zk_status;
+
+typedef void* zk_stream; /* cudaStream_t */
+
+/* univariate bijector applied per (sample, dim) */
+#define ZK_UNI_AFFINE 1 /* MonotonicAffineTransform, zuko/transforms.py:412-446; phi = (shift, scale) */
+#define ZK_UNI_RQS 2    /* MonotonicRQSTransform,    zuko/transforms.py:449-567; phi = (w[K], h[K], d[K-1]) */
+
+/* layer kinds (elements of a ComposedTransform, zuko/transforms.py:59-160) */
+#define ZK_LAYER_AUTOREGRESSIVE 1 /* flows/autoregressive.py:24-218 + transforms.py:966-1007 */
+#define ZK_LAYER_COUPLING 2       /* flows/coupling.py:25-139 + transforms.py:1010-1073 */
+#define ZK_LAYER_ELEMENTWISE 3    /* flows/gaussianization.py:28-94 */
+#define ZK_LAYER_SOFTCLIP 4       /* transforms.py:286-316 */
+#define ZK_LAYER_PERMUTATION 5    /* transforms.py:1182-1214 */
+#define ZK_LAYER_ROTATION 6       /* transforms.py:1217-1244 */
+
+/* arithmetic of the conditioner GEMMs (zuko/nn.py:217-218) */
+#define ZK_GEMM_AUTO 0    /* tcgen05 split-bf16 when the shape allows it, else fp32 SIMT */
+#define ZK_GEMM_FP32 1    /* fp32 FMA on CUDA cores (exact-order reference path, any shape) */
+#define ZK_GEMM_BF16X3 2  /* tcgen05.mma kind::f16, bf16 hi/lo split (3 MMAs), fp32 accumulate in TMEM */
+#define ZK_GEMM_BF16X1 3  /* single bf16 MMA: fast, does NOT meet the 1e-5 parity bar */
+
+int zk_version(void);
+const char* zk_last_error(void);
+/* sm count / compute capability of the current device; ZK_ECUDA if none. */
+zk_status zk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------- *
+ * Stand-alone bijector kernels (one fused pass each: z and summed ladj).
+ * `ladj` is per SAMPLE: sum over D of log|dy/dx| — i.e. what
+ * DependentTransform.call_and_ladj returns (transforms.py:210-214); with
+ * accumulate != 0 it is added to the buffer (transforms.py:147).
+ * `phi_ld` is the row stride of phi in elements (D*P for per-sample parameters
+ * as produced by MaskedAutoregressiveTransform.meta, flows/autoregressive.py:
+ * 207-215; 0 for one shared (D, P) table, flows/gaussianization.py:74-77).
+ * y may alias x; y or ladj may be NULL when not needed.
+ * ------------------------------------------------------------------------- */
+
+/* MonotonicRQSTransform(*phi).call_and_ladj(x)   — transforms.py:469-490,554-567 */
+zk_status zk_rqs_forward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld, int64_t B,
+                         int D, int K, float bound, float slope, float* y, int64_t ldy,
+                         float* ladj, int accumulate, zk_stream stream);
+/* MonotonicRQSTransform(*phi)._inverse(y)        — transforms.py:534-548 */
+zk_status zk_rqs_inverse(const float* y, int64_t ldy, const float* phi, int64_t phi_ld, int64_t B,
+                         int D, int K, float bound, float slope, float* x, int64_t ldx,
+                         zk_stream stream);
+/* MonotonicAffineTransform(shift, scale)         — transforms.py:426-446 */
+zk_status zk_affine_forward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld,
+                            int64_t B, int D, float slope, float* y, int64_t ldy, float* ladj,
+                            int accumulate, zk_stream stream);
+zk_status zk_affine_inverse(const float* y, int64_t ldy, const float* phi, int64_t phi_ld,
+                            int64_t B, int D, float slope, float* x, int64_t ldx,
+                            zk_stream stream);
+/* SoftclipTransform(bound)                       — transforms.py:299-316 */
+zk_status zk_softclip_forward(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y,
+                              int64_t ldy, float* ladj, int accumulate, zk_stream stream);
+zk_status zk_softclip_inverse(const float* y, int64_t ldy, int64_t B, int D, float bound, float* x,
+                              int64_t ldx, zk_stream stream);
+/* PermutationTransform: y[:, j] = x[:, order[j]] (bit-exact) — transforms.py:1207-1211.
+ * `order` is a DEVICE int64 vector of length D.  x and y must not alias. */
+zk_status zk_permute(const float* x, int64_t ldx, const int64_t* order, int64_t B, int D, float* y,
+                     int64_t ldy, zk_stream stream);
+/* RotationTransform: y = R x (transpose = 0) or R^T x (1); R is DEVICE (D, D)
+ * row-major, = matrix_exp(A - A^T) built by the caller — transforms.py:1235-1241. */
+zk_status zk_rotate(const float* x, int64_t ldx, const float* R, int transpose, int64_t B, int D,
+                    float* y, int64_t ldy, zk_stream stream);
+/* DiagNormal(loc, scale).log_prob(z) + ladj — distributions.py:115-119,337-363;
+ * loc/scale DEVICE (D) or both NULL for the standard normal; ladj may be NULL. */
+zk_status zk_diag_normal_log_prob(const float* z, int64_t ldz, const float* loc, const float* scale,
+                                  const float* ladj, int64_t B, int D, float* out,
+                                  zk_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * Conditioner: MaskedMLP (zuko/nn.py:221-318) or MLP (zuko/nn.py:122-192) with
+ * ReLU between layers and none after the last.  Creation applies `mask * W`
+ * ONCE (the reference redoes it on every call, nn.py:217-218) and packs the
+ * weights for the selected GEMM path.
+ * ------------------------------------------------------------------------- */
+typedef struct zk_mlp zk_mlp;
+
+typedef struct {
+    int n_linear;                /* number of linear layers (>= 1) */
+    const int* dims;             /* host, n_linear + 1 widths: in, hidden..., out */
+    const float* const* weight;  /* host array of DEVICE ptrs, (dims[i+1], dims[i]) row-major */
+    const float* const* bias;    /* host array of DEVICE ptrs, (dims[i+1]); entries may be NULL */
+    const uint8_t* const* mask;  /* host array of DEVICE ptrs (bool bytes), or NULL / NULL entries = dense */
+    int gemm_mode;               /* ZK_GEMM_* */
+} zk_mlp_desc;
+
+zk_status zk_mlp_create(const zk_mlp_desc* desc, zk_mlp** out);
+zk_status zk_mlp_destroy(zk_mlp* mlp);
+size_t zk_mlp_workspace_bytes(const zk_mlp* mlp, int64_t B);
+/* out = mlp(cat(x, c)): x (B, dx), c (B, dc) or one row (ldc = 0) or NULL (dc = 0);
+ * dx + dc must equal dims[0]; out is (B, dims[n_linear]) with row stride ldo. */
+zk_status zk_mlp_forward(const zk_mlp* mlp, const float* x, int64_t ldx, int dx, const float* c,
+                         int64_t ldc, int dc, int64_t B, float* out, int64_t ldo, void* workspace,
+                         size_t workspace_bytes, zk_stream stream);
+/* which GEMM path the handle resolved to (ZK_GEMM_FP32 / BF16X3 / BF16X1) */
+int zk_mlp_gemm_mode(const zk_mlp* mlp);
+
+/* ------------------------------------------------------------------------- *
+ * Layers: one lazy transformation of the reference, packed.
+ * ------------------------------------------------------------------------- */
+typedef struct zk_layer zk_layer;
+
+typedef struct {
+    int kind;       /* ZK_LAYER_* */
+    int features;   /* D */
+    int context;    /* C (0 = unconditional) */
+    int univariate; /* ZK_UNI_* (autoregressive / coupling / elementwise) */
+    int bins;       /* K for ZK_UNI_RQS */
+    float bound;    /* spline bound B (5.0) or softclip bound */
+    float slope;    /* minimum slope (1e-3) */
+    int passes;     /* autoregressive: number of inverse sweeps (transforms.py:994-1000) */
+    const int64_t* order;         /* host (D): autoregressive order classes (MaskedAutoregressiveTransform.order,
+                                     flows/autoregressive.py:121-124; may be NULL) or the permutation order */
+    const uint8_t* coupling_mask; /* host (D) bool: 1 = constant split x_a (transforms.py:1037-1041) */
+    const zk_mlp_desc* hyper;     /* conditioner; NULL for parameter-free / shared-table layers */
+    const float* phi;             /* DEVICE (D, P) shared table: elementwise without context */
+    const float* rotation;        /* DEVICE (D, D) R for ZK_LAYER_ROTATION */
+} zk_layer_desc;
+
+zk_status zk_layer_create(const zk_layer_desc* desc, zk_layer** out);
+zk_status zk_layer_destroy(zk_layer* layer);
+size_t zk_layer_workspace_bytes(const zk_layer* layer, int64_t B);
+/* t(c).call_and_ladj(x): y (B, D), ladj (B) summed over the event dim; y must not alias x. */
+zk_status zk_layer_forward(const zk_layer* layer, const float* x, int64_t ldx, const float* c,
+                           int64_t ldc, int64_t B, float* y, int64_t ldy, float* ladj,
+                           int accumulate, void* workspace, size_t workspace_bytes,
+                           zk_stream stream);
+/* t(c).inv(y); x must not alias y. */
+zk_status zk_layer_inverse(const zk_layer* layer, const float* y, int64_t ldy, const float* c,
+                           int64_t ldc, int64_t B, float* x, int64_t ldx, void* workspace,
+                           size_t workspace_bytes, zk_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * Flow: NormalizingFlow(ComposedTransform(layers...), DiagNormal(loc, scale))
+ * — zuko/lazy.py:156-172, zuko/distributions.py:39-138.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int n_layers;
+    const zk_layer* const* layers; /* host array of handles, applied first to last in the forward direction */
+    int features;
+    int context;
+    const float* base_loc;   /* DEVICE (D) or NULL (0) */
+    const float* base_scale; /* DEVICE (D) or NULL (1) */
+} zk_flow_desc;
+
+/* bytes of workspace that let a batch of B rows run in a single chunk; any
+ * workspace >= zk_flow_min_workspace_bytes() is accepted (the batch is then
+ * processed in row chunks). */
+size_t zk_flow_workspace_bytes(const zk_flow_desc* flow, int64_t B);
+size_t zk_flow_min_workspace_bytes(const zk_flow_desc* flow);
+
+/* transform.call_and_ladj(x) — transforms.py:141-150: z (B, D), ladj (B). */
+zk_status zk_flow_forward(const zk_flow_desc* flow, const float* x, int64_t ldx, const float* c,
+                          int64_t ldc, int64_t B, float* z, int64_t ldz, float* ladj,
+                          void* workspace, size_t workspace_bytes, zk_stream stream);
+/* NormalizingFlow.log_prob(x) — distributions.py:115-119: log_prob (B).
+ * sum_log_prob: optional DEVICE double[1] receiving sum_b log_prob[b] by a
+ * fixed-order two-stage reduction (the per-device term of the mean NLL). */
+zk_status zk_flow_log_prob(const zk_flow_desc* flow, const float* x, int64_t ldx, const float* c,
+                           int64_t ldc, int64_t B, float* log_prob, double* sum_log_prob,
+                           void* workspace, size_t workspace_bytes, zk_stream stream);
+/* transform.inv(z) — distributions.py:121-127 (z supplied by the caller);
+ * with log_prob != NULL also NormalizingFlow.rsample_and_log_prob's second
+ * output for that z — distributions.py:129-138. */
+zk_status zk_flow_inverse(const zk_flow_desc* flow, const float* z, int64_t ldz, const float* c,
+                          int64_t ldc, int64_t B, float* x, int64_t ldx, float* log_prob,
+                          void* workspace, size_t workspace_bytes, zk_stream stream);
+
+/* Host-buffer entry point (end-to-end path): x_host (B, D), c_host (B, C) or
+ * one row (ldc = 0) or NULL, log_prob_host (B) are HOST pointers (pinned for
+ * overlap); rows are streamed through the device in chunks with the copies
+ * overlapped with compute.  `workspace` is a DEVICE buffer. */
+zk_status zk_flow_log_prob_host(const zk_flow_desc* flow, const float* x_host, int64_t ldx,
+                                const float* c_host, int64_t ldc, int64_t B, float* log_prob_host,
+                                double* sum_log_prob_host, void* workspace, size_t workspace_bytes,
+                                zk_stream stream);
+
+/* number of kernel launches issued by this library since load (bench evidence) */
+int64_t zk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZUKO_B200_H */

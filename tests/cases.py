@@ -1,0 +1,122 @@
+"""Shared test helpers: golden loading and construction of the zuko_b200 counterparts of
+the flows that tests/golden/make_golden.py built with the reference."""
+
+from __future__ import annotations
+
+import zlib
+from functools import partial
+from pathlib import Path
+
+import numpy as np
+import torch
+
+import zuko_b200 as zuko
+from zuko_b200.flows import MAF, NICE, NSF, ElementWiseTransform, GeneralCouplingTransform, MaskedAutoregressiveTransform
+from zuko_b200.lazy import Flow, UnconditionalDistribution, UnconditionalTransform
+from zuko_b200.transforms import MonotonicRQSTransform, PermutationTransform, RotationTransform, SoftclipTransform
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# name -> (seed, constructor) — must mirror tests/golden/make_golden.py:main()
+FLOW_CASES = {
+    "cfg1_maf": (0, lambda: MAF(4, 0, transforms=2, hidden_features=[32, 32])),
+    "cfg2_nsf": (0, lambda: NSF(16, 8, transforms=4, bins=8, hidden_features=[256] * 3)),
+    "cfg3_maf": (0, lambda: MAF(32, 0, transforms=8, hidden_features=[512] * 4)),
+    "cfg4_nsf": (0, lambda: NSF(64, 0, transforms=8, bins=16)),
+    "cfg5_nsf": (0, lambda: NSF(64, 16, transforms=8, bins=16, hidden_features=[512] * 3)),
+    "nsf35_row": (0, lambda: NSF(3, 5)),
+    "maf35_batch": (0, lambda: MAF(3, 5)),
+    "nice35": (0, lambda: NICE(3, 5)),
+    "nsf5_passes2": (0, lambda: NSF(5, 0, passes=2, hidden_features=[32, 32])),
+    "maf5_randperm": (7, lambda: MAF(5, 2, randperm=True, hidden_features=[24])),
+    "nsf1_elementwise": (0, lambda: NSF(1, 3, hidden_features=[16])),
+    "nsf6_stress": (0, lambda: NSF(6, 3, transforms=3, hidden_features=[64, 64])),
+}
+SMALL_CASES = [k for k in FLOW_CASES if not k.startswith(("cfg2", "cfg3", "cfg4", "cfg5"))]
+BIG_CASES = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
+
+
+def load(name: str) -> dict:
+    with np.load(GOLDEN / f"{name}.npz", allow_pickle=False) as f:
+        return {k: f[k] for k in f.files}
+
+
+def crc(t: torch.Tensor) -> int:
+    return zlib.crc32(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes())
+
+
+def _composed():
+    D, C = 5, 3
+    torch.manual_seed(3)
+    order = torch.randperm(D)
+    A = torch.randn(D, D)
+    layers = [
+        MaskedAutoregressiveTransform(D, C, hidden_features=[32, 32]),
+        UnconditionalTransform(SoftclipTransform, bound=11.0),
+        UnconditionalTransform(PermutationTransform, order, buffer=True),
+        MaskedAutoregressiveTransform(D, C, univariate=partial(MonotonicRQSTransform, slope=1e-3),
+                                      shapes=[(8,), (8,), (7,)], hidden_features=[32, 32]),  # fmt: skip
+        UnconditionalTransform(RotationTransform, A, buffer=True),
+        GeneralCouplingTransform(D, C, hidden_features=[32]),
+        ElementWiseTransform(D, C, hidden_features=[16]),
+    ]
+    base = UnconditionalDistribution(zuko.distributions.DiagNormal, torch.zeros(D) + 0.25, torch.ones(D) * 1.5, buffer=True)
+    return Flow(layers, base)
+
+
+def _composed_uncond():
+    D = 5
+    torch.manual_seed(4)
+    layers = [
+        ElementWiseTransform(D, 0, univariate=partial(MonotonicRQSTransform, slope=1e-3), shapes=[(4,), (4,), (3,)]),
+        MaskedAutoregressiveTransform(D, 0, hidden_features=[32, 32]),
+        UnconditionalTransform(SoftclipTransform, bound=11.0),
+        ElementWiseTransform(D, 0),
+    ]
+    base = UnconditionalDistribution(zuko.distributions.DiagNormal, torch.zeros(D), torch.ones(D), buffer=True)
+    return Flow(layers, base)
+
+
+FLOW_CASES["composed"] = (None, _composed)
+FLOW_CASES["composed_uncond"] = (None, _composed_uncond)
+SMALL_CASES += ["composed", "composed_uncond"]
+
+
+def build_flow(name: str, golden: dict | None = None):
+    """Builds the zuko_b200 flow for a golden case under the same seed as the reference,
+    then (when the case stores them) loads the reference's own tensors, and applies the
+    case's weight scaling.  Returns the flow in eval mode on the CPU."""
+    golden = golden if golden is not None else load(f"flow_{name}")
+    seed, ctor = FLOW_CASES[name]
+    if seed is not None:
+        torch.manual_seed(seed)
+    flow = ctor().eval()
+    stored = {k[3:]: torch.from_numpy(v) for k, v in golden.items() if k.startswith("sd/")}
+    if stored:
+        flow.load_state_dict(stored, strict=True)
+    if "w_scale" in golden:
+        with torch.no_grad():
+            for p in flow.parameters():
+                p.mul_(float(golden["w_scale"]))
+    return flow
+
+
+def rel_err(ours: np.ndarray, ref: np.ndarray) -> float:
+    ours, ref = np.asarray(ours, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(ours - ref) / np.maximum(np.abs(ref), 1.0))) if ours.size else 0.0
+
+
+def assert_log_prob_parity(ours, g: dict, rtol: float = 1e-5):
+    """The parity bar of BASELINE.json / SURVEY §7.4-1b:
+    |ours - ref64| <= max(rtol * |ref64|, 2 * |ref32 - ref64|) per sample (the second term
+    only matters for sharp splines where the reference's own fp32 answer drifts), with an
+    absolute floor rtol * 1 for log-densities that happen to be ~0."""
+    ours = np.asarray(ours, dtype=np.float64)
+    ref64, ref32 = g["log_prob64"].astype(np.float64), g["log_prob32"].astype(np.float64)
+    tol = np.maximum(rtol * np.maximum(np.abs(ref64), 1.0), 2.0 * np.abs(ref32 - ref64))
+    err = np.abs(ours - ref64)
+    worst = int(np.argmax(err - tol))
+    assert np.all(err <= tol), (
+        f"log_prob parity: sample {worst}: ours={ours[worst]!r} ref64={ref64[worst]!r} ref32={ref32[worst]!r} "
+        f"err={err[worst]:.3e} tol={tol[worst]:.3e}"
+    )

@@ -1,0 +1,181 @@
+"""Distributions of the flow hot path: ``NormalizingFlow`` and ``DiagNormal``.
+
+Host-side mirror of zuko/distributions.py:39-138 (NormalizingFlow) and :337-363
+(DiagNormal).  Densities and inverse passes run in the B200 engine; torch provides the
+random numbers (``torch.randn`` on the device) and owns all memory.
+"""
+
+from __future__ import annotations
+
+__all__ = ["DiagNormal", "NormalizingFlow"]
+
+from textwrap import indent
+
+import torch
+from torch import Size, Tensor
+from torch.distributions import Distribution, Transform, constraints
+
+from . import _engine as E
+from . import _ops
+from .transforms import ComposedTransform
+
+Distribution.set_default_validate_args(False)  # like zuko/distributions.py:35
+
+
+class DiagNormal(Distribution):
+    """Multivariate normal with diagonal covariance, ``loc`` / ``scale`` of shape ``(D,)``
+    (zuko/distributions.py:337-363 = Independent(Normal(loc, scale), 1)).
+
+    ``log_prob`` is evaluated by ``zk_diag_normal_log_prob`` (the arithmetic of
+    torch/distributions/normal.py:87-102 summed over the event dimension)."""
+
+    has_rsample = True
+    arg_constraints = {}
+
+    def __init__(self, loc: Tensor, scale: Tensor, ndims: int = 1) -> None:
+        loc, scale = torch.as_tensor(loc), torch.as_tensor(scale)
+        if ndims != 1 or loc.dim() != 1 or scale.shape != loc.shape:
+            raise NotImplementedError("zuko_b200: DiagNormal supports 1-d loc/scale and ndims=1 only")
+        self.loc, self.scale = loc, scale
+        super().__init__(batch_shape=Size(), event_shape=loc.shape, validate_args=False)
+
+    def __repr__(self) -> str:
+        return f"DiagNormal(loc: {self.loc.shape}, scale: {self.scale.shape})"
+
+    @property
+    def support(self) -> constraints.Constraint:
+        return constraints.real_vector
+
+    @property
+    def mean(self) -> Tensor:
+        return self.loc.expand(self.batch_shape + self.event_shape)
+
+    @property
+    def stddev(self) -> Tensor:
+        return self.scale.expand(self.batch_shape + self.event_shape)
+
+    def expand(self, batch_shape: Size, new: Distribution | None = None) -> Distribution:
+        new = self._get_checked_instance(DiagNormal, new)
+        new.loc, new.scale = self.loc, self.scale
+        Distribution.__init__(new, batch_shape=Size(batch_shape), event_shape=self.event_shape, validate_args=False)
+        return new
+
+    def rsample(self, shape: Size = ()) -> Tensor:
+        full = Size(shape) + self.batch_shape + self.event_shape
+        eps = torch.randn(full, device=self.loc.device, dtype=self.loc.dtype)  # torch RNG (normal.py:82-85)
+        return self.loc + eps * self.scale
+
+    def sample(self, shape: Size = ()) -> Tensor:
+        with torch.no_grad():
+            return self.rsample(shape)
+
+    def log_prob(self, z: Tensor) -> Tensor:
+        E.require_cuda(z, "input")
+        D = self.loc.shape[0]
+        lead = torch.broadcast_shapes(z.shape[:-1], self.batch_shape)
+        z2 = z.expand(*lead, D).reshape(-1, D).contiguous()
+        out = torch.empty(z2.shape[0], device=z.device, dtype=torch.float32)
+        loc, scale = self.loc.detach().contiguous(), self.scale.detach().contiguous()
+        E.require_cuda(loc, "base loc")
+        with torch.cuda.device(z.device):
+            E.check(E.lib().zk_diag_normal_log_prob(z2.data_ptr(), D, loc.data_ptr(), scale.data_ptr(), None,
+                                                    z2.shape[0], D, out.data_ptr(), E.stream_ptr(z.device)))  # fmt: skip
+        return out.reshape(lead)
+
+
+class NormalizingFlow(Distribution):
+    """Normalizing flow ``p(x) = p_Z(f(x)) |det df/dx|`` (zuko/distributions.py:39-138).
+
+    With a composed stack of engine layers and a ``DiagNormal`` base, ``log_prob``,
+    ``rsample`` and ``rsample_and_log_prob`` are each ONE engine call
+    (``zk_flow_log_prob`` / ``zk_flow_inverse``)."""
+
+    has_rsample = True
+    arg_constraints = {}
+
+    def __init__(self, transform: Transform, base: Distribution) -> None:
+        super().__init__(validate_args=False)
+        reinterpreted = transform.codomain.event_dim - len(base.event_shape)
+        if reinterpreted > 0:
+            raise NotImplementedError("zuko_b200: base distributions with fewer event dims than the transform are not supported")
+        self.transform = transform
+        self.base = base
+        self.reinterpreted = max(-reinterpreted, 0)
+
+    def __repr__(self) -> str:
+        lines = indent(f"(transform): {self.transform}\n(base): {self.base}", "  ")
+        return f"{type(self).__name__}(\n{lines}\n)"
+
+    @property
+    def batch_shape(self) -> Size:
+        return self.base.batch_shape
+
+    @property
+    def event_shape(self) -> Size:
+        return self.transform.inverse_shape(self.base.event_shape)
+
+    def expand(self, batch_shape: Size, new: Distribution | None = None) -> Distribution:
+        new = self._get_checked_instance(NormalizingFlow, new)
+        new.transform = self.transform
+        new.base = self.base.expand(batch_shape)
+        new.reinterpreted = self.reinterpreted
+        Distribution.__init__(new, validate_args=False)
+        return new
+
+    # -- fused engine path -----------------------------------------------------
+    def _flow_call(self):
+        if "_fc" in self.__dict__:
+            return self.__dict__["_fc"]
+        fc = None
+        t, base = self.transform, self.base
+        if isinstance(t, ComposedTransform) and isinstance(base, DiagNormal) and self.reinterpreted == 0:
+            fused = t._fused(base.loc.shape[0])
+            if fused is not None:
+                call, ctx = fused
+                fc = (_ops.FlowCall(call._handles, call.D, call.C, base.loc, base.scale), ctx)
+        self.__dict__["_fc"] = fc
+        return fc
+
+    def log_prob(self, x: Tensor) -> Tensor:
+        fc = self._flow_call()
+        if fc is not None:
+            call, ctx = fc
+            lp = call.log_prob(x, ctx)
+            return lp.expand(torch.broadcast_shapes(lp.shape, self.batch_shape)) if self.batch_shape else lp
+        z, ladj = self.transform.call_and_ladj(x)
+        if self.reinterpreted:
+            ladj = ladj.sum(dim=tuple(range(-self.reinterpreted, 0)))
+        return self.base.log_prob(z) + ladj
+
+    def log_prob_and_sum(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        """``(log_prob(x), sum(log_prob(x)) as a device double[1])`` — the per-rank term of
+        the mean NLL, produced by a fixed-order reduction inside the same engine call."""
+        fc = self._flow_call()
+        if fc is None:
+            lp = self.log_prob(x)
+            return lp, lp.double().sum().reshape(1)
+        call, ctx = fc
+        return call.log_prob(x, ctx, with_sum=True)
+
+    def rsample(self, shape: Size = ()) -> Tensor:
+        z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
+        fc = self._flow_call()
+        if fc is not None:
+            call, ctx = fc
+            return call.inverse(z, ctx)
+        return self.transform.inv(z)
+
+    def sample(self, shape: Size = ()) -> Tensor:
+        with torch.no_grad():
+            return self.rsample(shape)
+
+    def rsample_and_log_prob(self, shape: Size = ()) -> tuple[Tensor, Tensor]:
+        z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
+        fc = self._flow_call()
+        if fc is not None:
+            call, ctx = fc
+            return call.inverse(z, ctx, with_log_prob=True)
+        x, ladj = self.transform.inv.call_and_ladj(z)
+        if self.reinterpreted:
+            ladj = ladj.sum(dim=tuple(range(-self.reinterpreted, 0)))
+        return x, self.base.log_prob(z) - ladj

@@ -1,0 +1,112 @@
+"""Shared plumbing of the lazy layers: resolving the ``univariate`` / ``shapes`` hooks to an
+engine bijector and packing the layer into a ``zk_layer`` handle."""
+
+from __future__ import annotations
+
+import ctypes
+from collections.abc import Callable, Sequence
+from functools import partial
+from math import prod
+
+import torch
+from torch import Size
+
+from .. import _engine as E
+from ..transforms import MonotonicAffineTransform, MonotonicRQSTransform
+
+
+def resolve_univariate(univariate: Callable, shapes: Sequence[Size]) -> dict:
+    """Maps the reference's ``univariate=`` / ``shapes=`` constructor hooks
+    (zuko/flows/autoregressive.py:95-104, flows/coupling.py:84-93,
+    flows/gaussianization.py:64-72) onto an engine bijector."""
+    kwargs = {}
+    f = univariate
+    while isinstance(f, partial):
+        if f.args:
+            raise NotImplementedError("zuko_b200: positional arguments bound to `univariate` are not supported")
+        kwargs = {**f.keywords, **kwargs}
+        f = f.func
+    shapes = [tuple(s) for s in shapes]
+    if f is MonotonicAffineTransform:
+        if shapes != [(), ()]:
+            raise ValueError(f"MonotonicAffineTransform expects shapes [(), ()], got {shapes}")
+        extra = set(kwargs) - {"slope"}
+        if extra:
+            raise NotImplementedError(f"zuko_b200: unsupported MonotonicAffineTransform arguments {sorted(extra)}")
+        return dict(kind=E.ZK_UNI_AFFINE, bins=0, bound=5.0, slope=float(kwargs.get("slope", 1e-3)), total=2)
+    if f is MonotonicRQSTransform:
+        if len(shapes) != 3 or shapes[0] != shapes[1] or len(shapes[0]) != 1 or shapes[2] != (shapes[0][0] - 1,):
+            raise ValueError(f"MonotonicRQSTransform expects shapes [(K,), (K,), (K-1,)], got {shapes}")
+        extra = set(kwargs) - {"slope", "bound"}
+        if extra:
+            raise NotImplementedError(f"zuko_b200: unsupported MonotonicRQSTransform arguments {sorted(extra)}")
+        K = shapes[0][0]
+        return dict(kind=E.ZK_UNI_RQS, bins=K, bound=float(kwargs.get("bound", 5.0)),
+                    slope=float(kwargs.get("slope", 1e-3)), total=3 * K - 1)  # fmt: skip
+    raise NotImplementedError(
+        f"zuko_b200: univariate transformation {getattr(f, '__name__', f)!r} is not implemented by the engine "
+        "(supported: MonotonicAffineTransform, MonotonicRQSTransform)"
+    )
+
+
+class PackedLayerMixin:
+    """Gives a lazy layer a cached ``zk_layer`` handle, rebuilt when any tensor it was
+    packed from changes (data pointer / version / device) — optimizer steps,
+    ``load_state_dict``, ``.to()``, Bayesian re-parameterisation (zuko/bayesian.py:161-166)."""
+
+    def _layer_tensors(self) -> list:
+        ts = []
+        hyper = getattr(self, "hyper", None)
+        if hyper is not None:
+            ts.append(hyper.gemm_mode)
+            for m in hyper._linears():
+                ts += [m.weight, m.bias, getattr(m, "mask", None)]
+        for p in getattr(self, "phi", []) or []:
+            ts.append(p)
+        return ts
+
+    def _layer_signature(self) -> tuple:
+        return tuple(
+            (t.data_ptr(), t._version, t.device, t.dtype) if torch.is_tensor(t) else t for t in self._layer_tensors()
+        )
+
+    def _zk_layer(self) -> ctypes.c_void_p:
+        sig = self._layer_signature()
+        cached = self.__dict__.get("_zk_cache")
+        if cached is not None and cached[0] == sig:
+            return cached[1]
+        self._zk_release()
+        desc, keep = self._layer_desc()
+        h = ctypes.c_void_p()
+        E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
+        del keep
+        self.__dict__["_zk_cache"] = (sig, h)
+        return h
+
+    def _zk_release(self) -> None:
+        cached = self.__dict__.pop("_zk_cache", None)
+        if cached is not None:
+            E.lib().zk_layer_destroy(cached[1])
+
+    def __del__(self) -> None:
+        try:
+            self._zk_release()
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_zk_cache", None)
+        return state
+
+    def _base_desc(self, kind: int) -> E.LayerDesc:
+        u = self._uni
+        return E.LayerDesc(kind=kind, features=self.features, context=self.context, univariate=u["kind"],
+                           bins=u["bins"], bound=u["bound"], slope=u["slope"], passes=getattr(self, "passes", 0))  # fmt: skip
+
+    def _describe_base(self) -> str:
+        return "MonotonicRQSTransform(bins=%d)" % self._uni["bins"] if self._uni["kind"] == E.ZK_UNI_RQS else "MonotonicAffineTransform()"
+
+
+def total_of(shapes: Sequence[Size]) -> int:
+    return sum(prod(s) for s in shapes)

@@ -1,0 +1,238 @@
+"""Conditioner networks of the flow hot path: ``MaskedMLP`` and ``MLP``.
+
+Host-side mirror of zuko/nn.py:122-192 (MLP), :202-218 (MaskedLinear) and :221-318
+(MaskedMLP).  The modules own the same parameters / buffers under the same state-dict
+keys as the reference (``{2j}.weight``, ``{2j}.bias``, ``{2j}.mask``) and are initialised
+by the same torch initialisers in the same order, so a reference checkpoint loads
+unchanged and ``torch.manual_seed(s)`` yields bit-identical weights.
+
+``forward`` does not run torch ops: it hands the weights to the B200 engine
+(``zk_mlp_forward`` — pre-masked, packed once per parameter version).
+"""
+
+from __future__ import annotations
+
+__all__ = ["MLP", "Linear", "MaskedLinear", "MaskedMLP"]
+
+import ctypes
+from collections.abc import Callable, Sequence
+
+import torch
+import torch.nn as nn
+from torch import BoolTensor, Tensor
+
+from . import _engine as E
+
+
+class Linear(nn.Module):
+    """Dense affine layer ``y = x W^T + b`` with U(-1/sqrt(in), 1/sqrt(in)) initialisation
+    (zuko/nn.py:51-119, ``stack`` is not supported by the engine)."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, stack: int | None = None) -> None:
+        super().__init__()
+        if stack is not None:
+            raise NotImplementedError("zuko_b200: stacked Linear operators are outside the accelerated path")
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.in_features, self.out_features = in_features, out_features
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        k = self.weight.shape[-1] ** -0.5
+        nn.init.uniform_(self.weight, -k, k)
+        if self.bias is not None:
+            nn.init.uniform_(self.bias, -k, k)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+
+class MaskedLinear(nn.Linear):
+    """``y = x (W * A)^T + b`` for a boolean adjacency ``A`` (out, in) — zuko/nn.py:202-218.
+    The product ``mask * weight`` is formed once, when the engine packs the layer."""
+
+    def __init__(self, adjacency: BoolTensor, **kwargs) -> None:
+        out_features, in_features = adjacency.shape
+        super().__init__(in_features, out_features, **kwargs)
+        self.register_buffer("mask", adjacency)
+
+
+def _relu_only(activation: Callable[[], nn.Module] | None) -> type:
+    if activation is None or activation is nn.ReLU:
+        return nn.ReLU
+    raise NotImplementedError(
+        f"zuko_b200: activation {activation!r} is not implemented by the engine (ReLU only); "
+        "the reference supports arbitrary activations (zuko/nn.py:264-265)"
+    )
+
+
+class _EngineMLP(nn.Sequential):
+    """Shared engine plumbing for MLP / MaskedMLP: packs the linear layers into a
+    ``zk_mlp`` handle, re-packing whenever a parameter / mask changes (optimizer step,
+    ``load_state_dict``, ``.to()``, re-parameterisation)."""
+
+    gemm_mode = "auto"  # "auto" | "fp32" | "bf16x3" | "bf16x1"
+
+    def _linears(self) -> list[nn.Module]:
+        return [m for m in self if hasattr(m, "weight")]
+
+    def _signature(self) -> tuple:
+        sig = [self.gemm_mode]
+        for m in self._linears():
+            for t in (m.weight, m.bias, getattr(m, "mask", None)):
+                sig.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
+        return tuple(sig)
+
+    def mlp_desc(self) -> tuple[E.MlpDesc, list]:
+        """Builds the ``zk_mlp_desc`` for the current parameters. Returns (desc, keepalive)."""
+        lins = self._linears()
+        n = len(lins)
+        keep: list = []
+        dims = (ctypes.c_int * (n + 1))(lins[0].weight.shape[1], *[m.weight.shape[0] for m in lins])
+        W = (ctypes.c_void_p * n)()
+        Bv = (ctypes.c_void_p * n)()
+        M = (ctypes.c_void_p * n)()
+        for i, m in enumerate(lins):
+            E.require_cuda(m.weight, "conditioner weight")
+            w = m.weight.detach().contiguous()
+            keep.append(w)
+            W[i] = w.data_ptr()
+            if m.bias is not None:
+                b = m.bias.detach().contiguous()
+                keep.append(b)
+                Bv[i] = b.data_ptr()
+            mask = getattr(m, "mask", None)
+            if mask is not None:
+                mk = mask.detach().to(torch.uint8).contiguous()
+                keep.append(mk)
+                M[i] = mk.data_ptr()
+        desc = E.MlpDesc(n, dims, W, Bv, M, E.GEMM_MODES[self.gemm_mode])
+        keep += [dims, W, Bv, M]
+        return desc, keep
+
+    def _handle(self) -> ctypes.c_void_p:
+        sig = self._signature()
+        cached = self.__dict__.get("_zk_cache")
+        if cached is not None and cached[0] == sig:
+            return cached[1]
+        self._release()
+        desc, keep = self.mlp_desc()
+        h = ctypes.c_void_p()
+        E.check(E.lib().zk_mlp_create(ctypes.byref(desc), ctypes.byref(h)))
+        del keep
+        self.__dict__["_zk_cache"] = (sig, h)
+        return h
+
+    def _release(self) -> None:
+        cached = self.__dict__.pop("_zk_cache", None)
+        if cached is not None:
+            E.lib().zk_mlp_destroy(cached[1])
+
+    def __del__(self) -> None:
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def __getstate__(self):  # handles are not picklable (torch.save of the whole module)
+        state = self.__dict__.copy()
+        state.pop("_zk_cache", None)
+        return state
+
+    def forward(self, x: Tensor) -> Tensor:
+        E.require_cuda(x, "conditioner input")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        B = x2.shape[0]
+        out = torch.empty(B, self.out_features, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            h = self._handle()
+            need = E.lib().zk_mlp_workspace_bytes(h, B)
+            ws = E.Workspace.get(x.device, need, need) if need else None
+            E.check(
+                E.lib().zk_mlp_forward(
+                    h, x2.data_ptr(), x2.shape[1], x2.shape[1], None, 0, 0, B, out.data_ptr(),
+                    self.out_features, ws.data_ptr() if ws is not None else None,
+                    ws.numel() if ws is not None else 0, E.stream_ptr(x.device),
+                )
+            )  # fmt: skip
+        return out.reshape(*lead, self.out_features)
+
+
+class MLP(_EngineMLP):
+    """Dense multi-layer perceptron ``in -> hidden... -> out`` with ReLU between layers
+    (zuko/nn.py:122-192; ``normalize`` / custom activations are not implemented)."""
+
+    def __init__(
+        self,
+        in_features: int,
+        out_features: int,
+        hidden_features: Sequence[int] = (64, 64),
+        activation: Callable[[], nn.Module] | None = None,
+        normalize: bool = False,
+        **kwargs,
+    ) -> None:
+        act = _relu_only(activation)
+        if normalize:
+            raise NotImplementedError("zuko_b200: LayerNorm between MLP layers is outside the accelerated path")
+        widths = [in_features, *hidden_features, out_features]
+        layers: list[nn.Module] = []
+        for fan_in, fan_out in zip(widths[:-1], widths[1:], strict=True):
+            layers += [Linear(fan_in, fan_out, **kwargs), act()]
+        super().__init__(*layers[:-1])
+        self.in_features, self.out_features = in_features, out_features
+
+
+def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> list[BoolTensor]:
+    """Masks of the masked MLP realising ``adjacency`` (out, in): every output may only
+    depend on the inputs its adjacency row allows.  Restates zuko/nn.py:270-293.
+
+    Outputs with identical dependency sets are merged into *classes* (unique rows).  Class
+    ``j`` precedes class ``i`` when ``deps(j) ⊆ deps(i)``.  Hidden unit ``u`` of every hidden
+    layer is assigned the class ``reachable[u mod #reachable]`` — cyclically over the classes
+    with a non-empty dependency set; it listens to the units of the previous layer whose
+    class precedes its own.  The output layer restores the original row multiplicity.
+    """
+    adjacency = torch.as_tensor(adjacency, dtype=torch.bool)
+    classes, inverse = torch.unique(adjacency, dim=0, return_inverse=True)
+    as_f64 = classes.to(torch.float64)
+    overlap = as_f64 @ as_f64.T  # |deps(i) ∩ deps(j)|
+    precedes = overlap == classes.sum(dim=-1)  # [i, j]: deps(j) ⊆ deps(i)
+
+    masks: list[BoolTensor] = []
+    unit_class = None
+    widths = [*hidden_features, adjacency.shape[0]]
+    for depth, width in enumerate(widths):
+        table = classes if depth == 0 else precedes[:, unit_class]
+        if not table.any():
+            raise ValueError("The adjacency matrix leads to a null Jacobian.")
+        if depth < len(hidden_features):
+            reachable = table.any(dim=-1).nonzero().squeeze(-1)
+            unit_class = reachable[torch.arange(width) % len(reachable)]
+            masks.append(table[unit_class])
+        else:
+            masks.append(table[inverse])
+    return masks
+
+
+class MaskedMLP(_EngineMLP):
+    """Masked multi-layer perceptron whose Jacobian ``dy_i/dx_j`` is null wherever
+    ``adjacency[i, j]`` is False (zuko/nn.py:221-318).  ``residual=True`` and non-ReLU
+    activations are not implemented by the engine."""
+
+    def __init__(
+        self,
+        adjacency: BoolTensor,
+        hidden_features: Sequence[int] = (64, 64),
+        activation: Callable[[], nn.Module] | None = None,
+        residual: bool = False,
+    ) -> None:
+        act = _relu_only(activation)
+        if residual:
+            raise NotImplementedError("zuko_b200: residual MaskedMLP blocks are outside the accelerated path (zuko/nn.py:297-309)")
+        out_features, in_features = adjacency.shape
+        layers: list[nn.Module] = []
+        for mask in masked_mlp_masks(adjacency, hidden_features):
+            layers += [MaskedLinear(adjacency=mask), act()]
+        super().__init__(*layers[:-1])
+        self.in_features, self.out_features = in_features, out_features

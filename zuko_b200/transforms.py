@@ -1,0 +1,510 @@
+"""Engine-backed transformations of the flow hot path.
+
+Host-side mirror of the ``Transform`` protocol the reference's hot path uses
+(zuko/transforms.py): ``__call__``, ``.inv``, ``log_abs_det_jacobian(x, y)`` and Zuko's
+``call_and_ladj(x) -> (y, ladj)`` (transforms.py:46-56).  Every method forwards to the
+C ABI of the B200 engine; no torch arithmetic runs here.
+
+* univariate bijectors built from explicit parameters:
+  ``MonotonicRQSTransform`` (transforms.py:449-567), ``MonotonicAffineTransform``
+  (:412-446), ``SoftclipTransform`` (:286-316);
+* linear maps: ``PermutationTransform`` (:1182-1214), ``RotationTransform`` (:1217-1244);
+* packed conditional layers produced by the lazy modules in ``zuko_b200.flows``:
+  ``AutoregressiveTransform`` (:966-1007), ``CouplingTransform`` (:1010-1073),
+  ``DependentTransform`` (:163-220, the element-wise case);
+* ``ComposedTransform`` (:59-160), which hands a whole stack of packed layers to one
+  flow-level engine call when it can.
+"""
+
+from __future__ import annotations
+
+__all__ = [
+    "AutoregressiveTransform",
+    "ComposedTransform",
+    "CouplingTransform",
+    "DependentTransform",
+    "MonotonicAffineTransform",
+    "MonotonicRQSTransform",
+    "PermutationTransform",
+    "RotationTransform",
+    "SoftclipTransform",
+]
+
+import ctypes
+import math
+from textwrap import indent
+
+import torch
+from torch import LongTensor, Size, Tensor
+from torch.distributions import Transform, constraints
+from torch.distributions.utils import _sum_rightmost
+
+from . import _engine as E
+from . import _ops
+
+
+def _call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:  # noqa: ANN001
+    y = self.__call__(x)
+    return y, self.log_abs_det_jacobian(x, y)
+
+
+# same extension of the torch protocol as zuko/transforms.py:46-56
+Transform.call_and_ladj = _call_and_ladj
+
+
+class _InverseOf(Transform):
+    """``t.inv`` for engine transforms: swaps the two directions and negates the ladj
+    (torch/distributions/transforms.py:217-283)."""
+
+    def __init__(self, t: Transform) -> None:
+        super().__init__()
+        self._t = t
+
+    domain = property(lambda self: self._t.codomain)
+    codomain = property(lambda self: self._t.domain)
+    bijective = True
+
+    @property
+    def inv(self) -> Transform:
+        return self._t
+
+    def __repr__(self) -> str:
+        return f"Inverse({self._t})"
+
+    def __call__(self, y: Tensor) -> Tensor:
+        return self._t._inverse(y)
+
+    def _inverse(self, x: Tensor) -> Tensor:
+        return self._t(x)
+
+    def log_abs_det_jacobian(self, y: Tensor, x: Tensor) -> Tensor:
+        return -self._t.log_abs_det_jacobian(x, y)
+
+    def call_and_ladj(self, y: Tensor) -> tuple[Tensor, Tensor]:
+        x = self._t._inverse(y)
+        return x, -self._t.log_abs_det_jacobian(x, y)
+
+    def forward_shape(self, shape: Size) -> Size:
+        return self._t.inverse_shape(shape)
+
+    def inverse_shape(self, shape: Size) -> Size:
+        return self._t.forward_shape(shape)
+
+
+class EngineTransform(Transform):
+    """Base class: subclasses implement ``call_and_ladj`` and ``_inverse``."""
+
+    bijective = True
+    sign = +1
+
+    def __init__(self) -> None:
+        super().__init__(cache_size=0)
+
+    @property
+    def inv(self) -> Transform:
+        return _InverseOf(self)
+
+    def __call__(self, x: Tensor) -> Tensor:
+        return self._call(x)
+
+    def _call(self, x: Tensor) -> Tensor:
+        return self.call_and_ladj(x)[0]
+
+    def log_abs_det_jacobian(self, x: Tensor, y: Tensor) -> Tensor:
+        return self.call_and_ladj(x)[1]
+
+    def __eq__(self, other: object) -> bool:
+        return self is other
+
+    __hash__ = object.__hash__
+
+
+# --------------------------------------------------------------------------- #
+# univariate bijectors with explicit parameters
+# --------------------------------------------------------------------------- #
+
+
+def _elementwise(phi: Tensor, x: Tensor, P: int):
+    """Maps an element-wise call (x of any shape, params with broadcastable batch shape)
+    onto the engine's (B, D=1) layout.  Returns (x2 (N,1), phi2, phi_ld, shape)."""
+    E.require_cuda(x, "input")
+    E.require_cuda(phi, "parameters")
+    if x.requires_grad or phi.requires_grad:
+        raise NotImplementedError("zuko_b200: the engine is forward-only (no autograd through the bijectors yet)")
+    batch = phi.shape[:-1]
+    shape = torch.broadcast_shapes(x.shape, batch)
+    x2 = x.expand(shape).reshape(-1, 1).contiguous()
+    if len(batch) == 0 or math.prod(batch) == 1:
+        return x2, phi.reshape(1, P).contiguous(), 0, shape
+    phi2 = phi.expand(*shape, P).reshape(-1, P).contiguous()
+    return x2, phi2, P, shape
+
+
+class MonotonicRQSTransform(EngineTransform):
+    """Monotonic rational-quadratic spline with unconstrained parameters
+    ``widths (*, K)``, ``heights (*, K)``, ``derivatives (*, K-1)`` — the constructor of
+    zuko/transforms.py:469-490; evaluated by ``zk_rqs_forward`` / ``zk_rqs_inverse``."""
+
+    domain = constraints.real
+    codomain = constraints.real
+
+    def __init__(self, widths: Tensor, heights: Tensor, derivatives: Tensor, bound: float = 5.0, slope: float = 1e-3) -> None:
+        super().__init__()
+        batch = torch.broadcast_shapes(widths.shape[:-1], heights.shape[:-1], derivatives.shape[:-1])
+        parts = [t.expand(*batch, t.shape[-1]) for t in (widths, heights, derivatives)]
+        self.phi = torch.cat(parts, dim=-1)  # (*, 3K-1): layout of flows/spline.py:57
+        self.bins = widths.shape[-1]
+        self.bound, self.slope = float(bound), float(slope)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(bins={self.bins})"
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        P = 3 * self.bins - 1
+        x2, phi, ld, shape = _elementwise(self.phi, x, P)
+        y = torch.empty_like(x2)
+        ladj = torch.empty(x2.shape[0], device=x2.device, dtype=torch.float32)
+        with torch.cuda.device(x2.device):
+            E.check(E.lib().zk_rqs_forward(x2.data_ptr(), 1, phi.data_ptr(), ld, x2.shape[0], 1, self.bins,
+                                           self.bound, self.slope, y.data_ptr(), 1, ladj.data_ptr(), 0,
+                                           E.stream_ptr(x2.device)))  # fmt: skip
+        return y.reshape(shape), ladj.reshape(shape)
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        P = 3 * self.bins - 1
+        y2, phi, ld, shape = _elementwise(self.phi, y, P)
+        x = torch.empty_like(y2)
+        with torch.cuda.device(y2.device):
+            E.check(E.lib().zk_rqs_inverse(y2.data_ptr(), 1, phi.data_ptr(), ld, y2.shape[0], 1, self.bins,
+                                           self.bound, self.slope, x.data_ptr(), 1, E.stream_ptr(y2.device)))  # fmt: skip
+        return x.reshape(shape)
+
+
+class MonotonicAffineTransform(EngineTransform):
+    """``f(x) = exp(a) x + b`` with soft-clipped log-scale (zuko/transforms.py:426-446)."""
+
+    domain = constraints.real
+    codomain = constraints.real
+
+    def __init__(self, shift: Tensor, scale: Tensor, slope: float = 1e-3) -> None:
+        super().__init__()
+        shift, scale = torch.broadcast_tensors(shift, scale)
+        self.phi = torch.stack((shift, scale), dim=-1)  # (*, 2): (shift, unconstrained log-scale)
+        self.slope = float(slope)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}()"
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        x2, phi, ld, shape = _elementwise(self.phi, x, 2)
+        y = torch.empty_like(x2)
+        ladj = torch.empty(x2.shape[0], device=x2.device, dtype=torch.float32)
+        with torch.cuda.device(x2.device):
+            E.check(E.lib().zk_affine_forward(x2.data_ptr(), 1, phi.data_ptr(), ld, x2.shape[0], 1, self.slope,
+                                              y.data_ptr(), 1, ladj.data_ptr(), 0, E.stream_ptr(x2.device)))  # fmt: skip
+        return y.reshape(shape), ladj.reshape(shape)
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        y2, phi, ld, shape = _elementwise(self.phi, y, 2)
+        x = torch.empty_like(y2)
+        with torch.cuda.device(y2.device):
+            E.check(E.lib().zk_affine_inverse(y2.data_ptr(), 1, phi.data_ptr(), ld, y2.shape[0], 1, self.slope,
+                                              x.data_ptr(), 1, E.stream_ptr(y2.device)))  # fmt: skip
+        return x.reshape(shape)
+
+
+class SoftclipTransform(EngineTransform):
+    """``f(x) = x / (1 + |x / B|)`` mapping R to (-B, B) (zuko/transforms.py:286-316)."""
+
+    def __init__(self, bound: float = 1.0) -> None:
+        super().__init__()
+        self.bound = float(bound)
+        self.domain = constraints.real
+        self.codomain = constraints.interval(-bound, bound)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(bound={self.bound})"
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        E.require_cuda(x, "input")
+        x2 = x.reshape(-1, 1).contiguous()
+        y = torch.empty_like(x2)
+        ladj = torch.empty(x2.shape[0], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            E.check(E.lib().zk_softclip_forward(x2.data_ptr(), 1, x2.shape[0], 1, self.bound, y.data_ptr(), 1,
+                                                ladj.data_ptr(), 0, E.stream_ptr(x.device)))  # fmt: skip
+        return y.reshape(x.shape), ladj.reshape(x.shape)
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        E.require_cuda(y, "input")
+        y2 = y.reshape(-1, 1).contiguous()
+        x = torch.empty_like(y2)
+        with torch.cuda.device(y.device):
+            E.check(E.lib().zk_softclip_inverse(y2.data_ptr(), 1, y2.shape[0], 1, self.bound, x.data_ptr(), 1,
+                                                E.stream_ptr(y.device)))  # fmt: skip
+        return x.reshape(y.shape)
+
+    def _layer_desc(self, D: int):
+        return E.LayerDesc(kind=E.ZK_LAYER_SOFTCLIP, features=D, bound=self.bound, slope=1e-3), []
+
+
+# --------------------------------------------------------------------------- #
+# linear maps
+# --------------------------------------------------------------------------- #
+
+
+class PermutationTransform(EngineTransform):
+    """``y = x[..., order]`` — a bit-exact gather (zuko/transforms.py:1182-1214)."""
+
+    domain = constraints.real_vector
+    codomain = constraints.real_vector
+
+    def __init__(self, order: LongTensor) -> None:
+        super().__init__()
+        if order.dim() != 1:
+            raise NotImplementedError("zuko_b200: batched permutation orders are not supported")
+        self.order = order
+
+    def __repr__(self) -> str:
+        order = self.order.tolist()
+        if len(order) > 10:
+            order = str(order[:5] + [...] + order[-5:]).replace("Ellipsis", "...")
+        return f"{type(self).__name__}({order})"
+
+    def _gather(self, x: Tensor, order: Tensor) -> Tensor:
+        E.require_cuda(x, "input")
+        D = order.shape[0]
+        x2 = x.reshape(-1, D).contiguous()
+        y = torch.empty_like(x2)
+        order = order.to(device=x.device, dtype=torch.int64).contiguous()
+        with torch.cuda.device(x.device):
+            E.check(E.lib().zk_permute(x2.data_ptr(), D, order.data_ptr(), x2.shape[0], D, y.data_ptr(), D,
+                                       E.stream_ptr(x.device)))  # fmt: skip
+        return y.reshape(x.shape)
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        return self._gather(x, self.order), torch.zeros_like(x[..., 0])
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        return self._gather(y, torch.argsort(self.order))
+
+    def _layer_desc(self, D: int):
+        host = self.order.detach().to("cpu", torch.int64).contiguous()
+        arr = (ctypes.c_int64 * D)(*host.tolist())
+        return E.LayerDesc(kind=E.ZK_LAYER_PERMUTATION, features=D, slope=1e-3, bound=1.0, order=arr), [arr]
+
+
+class RotationTransform(EngineTransform):
+    """``y = R x`` with ``R = exp(A - A^T)`` orthogonal (zuko/transforms.py:1217-1244).
+    ``matrix_exp`` of the (D, D) generator is one-time torch plumbing; the batched
+    product runs in ``zk_rotate``."""
+
+    domain = constraints.real_vector
+    codomain = constraints.real_vector
+
+    def __init__(self, A: Tensor) -> None:
+        super().__init__()
+        if A.dim() != 2:
+            raise NotImplementedError("zuko_b200: batched rotation generators are not supported")
+        A = A.detach()
+        self.R = torch.linalg.matrix_exp(A - A.mT).contiguous()
+
+    def _apply(self, x: Tensor, transpose: int) -> Tensor:
+        E.require_cuda(x, "input")
+        E.require_cuda(self.R, "rotation matrix")
+        D = self.R.shape[0]
+        x2 = x.reshape(-1, D).contiguous()
+        y = torch.empty_like(x2)
+        with torch.cuda.device(x.device):
+            E.check(E.lib().zk_rotate(x2.data_ptr(), D, self.R.data_ptr(), transpose, x2.shape[0], D,
+                                      y.data_ptr(), D, E.stream_ptr(x.device)))  # fmt: skip
+        return y.reshape(x.shape)
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        return self._apply(x, 0), torch.zeros_like(x[..., 0])
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        return self._apply(y, 1)
+
+    def _layer_desc(self, D: int):
+        return E.LayerDesc(kind=E.ZK_LAYER_ROTATION, features=D, slope=1e-3, bound=1.0, rotation=self.R.data_ptr()), [self.R]
+
+
+# --------------------------------------------------------------------------- #
+# packed conditional layers
+# --------------------------------------------------------------------------- #
+
+
+class _PackedLayerTransform(EngineTransform):
+    """A ``zk_layer`` handle (owned by a lazy module) bound to a context ``c``."""
+
+    domain = constraints.real_vector
+    codomain = constraints.real_vector
+
+    def __init__(self, owner, c: Tensor | None) -> None:  # noqa: ANN001
+        super().__init__()
+        self._owner = owner
+        self._c = c
+        self.features = owner.features
+
+    def _layer_handle(self, D: int | None = None):
+        return self._owner._zk_layer()
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        return _ops.layer_forward(self._layer_handle(), self.features, x, self._c)
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        return _ops.layer_inverse(self._layer_handle(), self.features, y, self._c)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}()"
+
+
+class AutoregressiveTransform(_PackedLayerTransform):
+    """``y_i = f(x_i | x_<i, c)`` with a masked conditioner (zuko/transforms.py:966-1007).
+    The inverse runs the reference's ``passes`` fixed-point sweeps (:994-1000)."""
+
+    @property
+    def passes(self) -> int:
+        return self._owner.passes
+
+
+class CouplingTransform(_PackedLayerTransform):
+    """``y_a = x_a, y_b = f(x_b | x_a, c)`` (zuko/transforms.py:1010-1073)."""
+
+
+class DependentTransform(_PackedLayerTransform):
+    """Element-wise univariate transformation whose ladj is summed over the feature
+    dimension (zuko/transforms.py:163-220 wrapping flows/gaussianization.py:86-94)."""
+
+
+# --------------------------------------------------------------------------- #
+# composition
+# --------------------------------------------------------------------------- #
+
+
+def _simple_layer_handle(t: Transform, D: int):
+    """Creates (and caches on the transform object) a zk_layer for a parameter-free /
+    explicit-parameter transform so that it can join a fused flow call."""
+    cache = t.__dict__.setdefault("_zk_layers", {})
+    key = D
+    if key not in cache:
+        desc, keep = t._layer_desc(D)
+        h = ctypes.c_void_p()
+        E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
+        cache[key] = _OwnedLayer(h)
+        del keep
+    return cache[key].handle
+
+
+class _OwnedLayer:
+    def __init__(self, handle) -> None:  # noqa: ANN001
+        self.handle = handle
+
+    def __del__(self) -> None:
+        try:
+            E.lib().zk_layer_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class ComposedTransform(EngineTransform):
+    """``f = f_n ∘ ... ∘ f_0`` (zuko/transforms.py:59-160).
+
+    When every member is an engine layer bound to the same context, the whole stack runs
+    as ONE flow-level engine call per direction (``zk_flow_forward`` / ``zk_flow_inverse``);
+    otherwise members are applied one after the other with the reference's event-dim
+    bookkeeping (transforms.py:141-150)."""
+
+    def __init__(self, *transforms: Transform) -> None:
+        super().__init__()
+        assert transforms, "'transforms' cannot be empty"
+        event_dim = 0
+        for t in reversed(transforms):
+            event_dim = t.domain.event_dim + max(event_dim - t.codomain.event_dim, 0)
+        self.domain_dim = event_dim
+        for t in transforms:
+            event_dim += t.codomain.event_dim - t.domain.event_dim
+        self.codomain_dim = event_dim
+        self.transforms = list(transforms)
+
+    def __repr__(self) -> str:
+        lines = "\n".join(f"({i}): {t}" for i, t in enumerate(self.transforms))
+        return f"{type(self).__name__}(\n" + indent(lines, "  ") + "\n)"
+
+    @property
+    def domain(self) -> constraints.Constraint:
+        dom = self.transforms[0].domain
+        extra = self.domain_dim - dom.event_dim
+        return constraints.independent(dom, extra) if extra > 0 else dom
+
+    @property
+    def codomain(self) -> constraints.Constraint:
+        cod = self.transforms[-1].codomain
+        extra = self.codomain_dim - cod.event_dim
+        return constraints.independent(cod, extra) if extra > 0 else cod
+
+    # -- fused path ----------------------------------------------------------
+    def _fused(self, D: int):
+        """Returns a FlowCall when all members can run inside one engine call."""
+        key = ("_fused", D)
+        if key in self.__dict__:
+            return self.__dict__[key]
+        call = None
+        ctx = None
+        handles = []
+        ok = self.domain_dim == 1 and self.codomain_dim == 1
+        C = 0
+        for t in self.transforms if ok else ():
+            if isinstance(t, _PackedLayerTransform):
+                if t.features != D:
+                    ok = False
+                    break
+                if t._owner.context:
+                    if ctx is not None and ctx is not t._c:
+                        ok = False
+                        break
+                    ctx = t._c
+                    C = t._owner.context
+                handles.append(t._layer_handle())
+            elif hasattr(t, "_layer_desc"):
+                handles.append(_simple_layer_handle(t, D))
+            else:
+                ok = False
+                break
+        if ok:
+            call = (_ops.FlowCall(handles, D, C, None, None), ctx)
+        self.__dict__[key] = call
+        return call
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        fused = self._fused(x.shape[-1]) if x.dim() >= 1 else None
+        if fused is not None:
+            call, ctx = fused
+            return call.forward(x, ctx)
+        event_dim = self.domain_dim
+        acc = 0
+        for t in self.transforms:
+            x, ladj = t.call_and_ladj(x)
+            acc = acc + _sum_rightmost(ladj, event_dim - t.domain.event_dim)
+            event_dim += t.codomain.event_dim - t.domain.event_dim
+        return x, acc
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        fused = self._fused(y.shape[-1]) if y.dim() >= 1 else None
+        if fused is not None:
+            call, ctx = fused
+            return call.inverse(y, ctx)
+        for t in reversed(self.transforms):
+            y = t.inv(y)
+        return y
+
+    def forward_shape(self, shape: Size) -> Size:
+        for t in self.transforms:
+            shape = t.forward_shape(shape)
+        return shape
+
+    def inverse_shape(self, shape: Size) -> Size:
+        for t in reversed(self.transforms):
+            shape = t.inverse_shape(shape)
+        return shape
