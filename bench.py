@@ -1,0 +1,364 @@
+"""bench.py — NSF log_prob throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, host cores)
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+``flow(c).log_prob(x)`` + the fixed-order sum of the log-densities (the per-device term of
+the mean NLL) for the workload BASELINE.json quotes the metric on —
+configs[1]: NSF(features=16, context=8, transforms=4, bins=8, hidden=[256]*3), batch 2^20 per
+GPU.  With N > 1 (torchrun, one rank per GPU) every rank processes its own 2^20 rows (weak
+scaling) and ONE NCCL all-reduce of {sum log p, count} closes the step.
+
+Printed JSON (one line, rank 0): see the contract in the task description; additionally
+``roofline`` (dominant kernel), ``kernels`` (every kernel class timed in isolation with CUDA
+events), ``cpu_baseline`` and ``parity``.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "nsf_log_prob_samples_per_sec"
+UNIT = "samples/s"
+WORKLOAD = "NSF(features=16, context=8, transforms=4, bins=8, hidden=[256]*3) log_prob"
+D, C, T, K, H = 16, 8, 4, 8, [256, 256, 256]
+P = 3 * K - 1
+
+
+def build_model():
+    import zuko_b200 as zuko
+
+    torch.manual_seed(0)
+    return zuko.flows.NSF(D, C, transforms=T, bins=K, hidden_features=H).eval()
+
+
+def measured_peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}  # fmt: skip
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}  # fmt: skip
+
+
+def cuda_time_ms(fn, iters: int, stream=None) -> float:
+    """Average device time of fn() over iters launches, CUDA events on the current stream."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the oracle port on the host cores
+# --------------------------------------------------------------------------- #
+
+
+def cpu_reference_rate(rows: int, repeats: int = 1):
+    """Times the oracle's fp32 CPU restatement of flow(c).log_prob(x) (all host threads, OpenMP)
+    on `rows` rows of the bench workload.  Returns (samples/s, seconds, threads)."""
+    from oracle import oracle
+
+    flow = build_model()
+    spec = oracle.flowspec_from_module(flow)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(rows, D, generator=g).numpy()
+    c = torch.randn(rows, C, generator=g).numpy()
+    spec.log_prob(x[:256], c[:256], dtype=np.float32)  # warm-up (library load, page-in)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        spec.log_prob(x, c, dtype=np.float32)
+        best = min(best, time.perf_counter() - t0)
+    return rows / best, best, os.cpu_count()
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_rate(min(rows, 1024))
+    times = []
+    for _ in range(args.steps):
+        rate, sec, threads = cpu_reference_rate(rows)
+        times.append(sec)
+    sec = float(np.mean(times))
+    rate = rows / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_step": rows, "note": "oracle port (plain C, OpenMP) of the reference's CPU path; bounded sample per step"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{rows} rows of the workload per step"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+
+
+def run_ours(args) -> None:
+    import torch.distributed as dist
+
+    import zuko_b200 as zuko  # noqa: F401
+    from zuko_b200 import _engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    peaks = measured_peaks()
+
+    flow = build_model().to(dev)
+    NBUF = 4  # inputs rotate over 4 buffers: 4 x 100 MB > 126 MB L2
+    g = torch.Generator().manual_seed(1234 + rank)
+    xs_host = [torch.randn(B, D, generator=g).pin_memory() for _ in range(NBUF)]
+    cs_host = [torch.randn(B, C, generator=g).pin_memory() for _ in range(NBUF)]
+    xs = [t.to(dev) for t in xs_host]
+    cs = [t.to(dev) for t in cs_host]
+    red = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def step(i: int):
+        d = flow(cs[i % NBUF])
+        lp, total = d.log_prob_and_sum(xs[i % NBUF])
+        red[0:1].copy_(total)
+        red[1] = float(B)
+        if world > 1:
+            dist.all_reduce(red)  # ONE collective: {sum log p, count} -> mean NLL
+        return lp
+
+    with torch.no_grad():
+        # ---- parity of the bench workload against the oracle (small slice, outside timing)
+        parity = None
+        if rank == 0:
+            from oracle import oracle
+
+            spec = oracle.flowspec_from_module(build_model())
+            n = 2048
+            ours = flow(cs[0][:n]).log_prob(xs[0][:n]).cpu().numpy().astype(np.float64)
+            ref = spec.log_prob(xs_host[0][:n].numpy(), cs_host[0][:n].numpy())
+            parity = {"rows": n, "max_rel_err_vs_fp64_oracle": float(np.max(np.abs(ours - ref) / np.maximum(np.abs(ref), 1.0)))}
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches0 = E.lib().zk_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        launches = E.lib().zk_launch_count() - launches0
+        ms_per_step = elapsed_ms.item() / args.steps
+        value = world * B / (ms_per_step * 1e-3)
+        mean_nll = -(red[0] / red[1]).item()
+
+        # ---- end to end through the public API with HOST buffers (H2D + compute + D2H per step)
+        fc = flow(cs[0])._flow_call()[0]
+        out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        e2e_steps = max(2, min(args.steps, 10))
+        for i in range(2):
+            fc.log_prob_host(xs_host[i % NBUF], cs_host[i % NBUF], dev, out_host)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            _, tot = fc.log_prob_host(xs_host[i % NBUF], cs_host[i % NBUF], dev, out_host)  # synchronous
+        e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = world * B / e2e_s.item()
+
+        # ---- per-kernel timing in isolation (CUDA events), rank 0
+        kernels, roofline = [], None
+        if rank == 0:
+            kernels = time_kernels(flow, xs[0], cs[0], dev, peaks, iters=max(3, min(args.steps, 10)))
+            dom = max(kernels, key=lambda k: k["ms_per_step"])
+            roofline = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+            roofline["kernel"] = dom["name"]
+            roofline["peak_source"] = peaks["source"]
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, threads = cpu_reference_rate(args.cpu_rows)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_rows} rows of the workload, oracle fp32 C port with OpenMP, {sec:.1f} s"}  # fmt: skip
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (conditioner GEMMs: %s)" % gemm_mode_name(flow), "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "l2": f"inputs rotate over {NBUF} buffers ({NBUF * B * (D + C) * 4 >> 20} MB > 126 MB L2); phi intermediates {B * D * P * 4 >> 20} MB per layer"},
+            "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4, "d2h_bytes_per_step": B * 4,
+                                             "steps": e2e_steps, "api": "FlowCall.log_prob_host -> zk_flow_log_prob_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "mean_nll": mean_nll, "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu, "parity": parity,
+        }  # fmt: skip
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_mode_name(flow) -> str:
+    from zuko_b200 import _engine as E
+
+    h = flow.transform.transforms[0].hyper._handle()
+    return {E.ZK_GEMM_FP32: "fp32 FMA", E.ZK_GEMM_BF16X3: "tcgen05 bf16x3, fp32 accumulate", E.ZK_GEMM_BF16X1: "tcgen05 bf16"}.get(E.lib().zk_mlp_gemm_mode(h), "?")
+
+
+def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
+    """Times each kernel class of one flow layer in isolation through the stand-alone C-ABI
+    entry points (CUDA events on the current stream) and converts to roofline terms.
+    Algorithmic bytes / FLOPs per SURVEY §8d; x4 layers per step."""
+    import ctypes
+
+    from zuko_b200 import _engine as E
+
+    L = E.lib()
+    B = x.shape[0]
+    layer = flow.transform.transforms[0]
+    hyper = layer.hyper
+    h = hyper._handle()
+    phi = torch.empty(B, D * P, device=dev)
+    y = torch.empty_like(x)
+    ladj = torch.zeros(B, device=dev)
+    need = L.zk_mlp_workspace_bytes(h, B)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    st = E.stream_ptr(dev)
+
+    def mlp():
+        E.check(L.zk_mlp_forward(h, x.data_ptr(), D, D, c.data_ptr(), C, C, B, phi.data_ptr(), D * P, ws.data_ptr(), ws.numel(), st))
+
+    def rqs():
+        E.check(L.zk_rqs_forward(x.data_ptr(), D, phi.data_ptr(), D * P, B, D, K, 5.0, 1e-3, y.data_ptr(), D, ladj.data_ptr(), 1, st))
+
+    for _ in range(2):
+        mlp()
+        rqs()
+    t_mlp = cuda_time_ms(mlp, iters)
+    t_rqs = cuda_time_ms(rqs, iters)
+    dims = [D + C, *H, D * P]
+    flops = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * B  # dense FLOPs nn.py:218 executes
+    rqs_bytes = 4.0 * (D + D * P + D + 1) * B  # x + phi + y + ladj
+    tf = flops / (t_mlp * 1e-3) / 1e12
+    gbs = rqs_bytes / (t_rqs * 1e-3) / 1e9
+    return [
+        {"name": "conditioner (MaskedMLP 24-256-256-256-368), one flow layer", "bound": "tensor", "achieved": tf,
+         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
+         "traffic": None, "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops},
+        {"name": "uni_kernel<RQS,8> fused RQS + ladj, one flow layer", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": t_rqs, "ms_per_step": t_rqs * T,
+         "algorithmic_bytes": rqs_bytes},
+    ]  # fmt: skip
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
+    ap.add_argument("--cpu-rows", type=int, default=1 << 15, help="rows of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

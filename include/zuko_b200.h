@@ -220,6 +220,11 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* flow, const float* x_host, i
                                 double* sum_log_prob_host, void* workspace, size_t workspace_bytes,
                                 zk_stream stream);
 
+/* Transcendental arithmetic of the bijector kernels: 1 (default) = MUFU rcp / ex2 / lg2
+ * approximations, 0 = IEEE division + expf / logf.  Process-wide; returns the previous
+ * value.  Both settings meet the 1e-5 parity bar on the BASELINE configs (tests/). */
+int zk_set_fast_math(int on);
+
 /* number of kernel launches issued by this library since load (bench evidence) */
 int64_t zk_launch_count(void);
 

@@ -1,12 +1,13 @@
 /*
  * ORACLE — TEST INFRASTRUCTURE ONLY (see zuko_oracle_impl.h for the contract).
  * Builds the fp32 (_f32) and fp64 (_f64) variants of the CPU restatement.
- *   gcc -O2 -fopenmp -shared -fPIC zuko_oracle.c -o libzuko_oracle.so -lm
+ *   gcc -O3 -mavx2 -mfma -fopenmp -shared -fPIC zuko_oracle.c -o libzuko_oracle.so -lm
  * No -ffast-math: the fp32 variant must round like the reference's eager ops.
  */
 #include <math.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #define ZO_MAX_BINS 256
 

@@ -37,22 +37,31 @@ void FN(zo_linear)(const REAL* x, int64_t ldx, int dx, const REAL* c, int64_t ld
                    int64_t B, const REAL* W, const uint8_t* mask, const REAL* bias, int out,
                    int relu, REAL* y, int64_t ldy) {
     const int in = dx + dc;
+    /* mask * W (nn.py:218), stored transposed (in, out) so that the inner loop runs over the
+     * contiguous outputs and vectorises; the sum over the inputs stays in index order. */
+    REAL* Wt = (REAL*)malloc((size_t)in * out * sizeof(REAL));
+    for (int o = 0; o < out; ++o)
+        for (int i = 0; i < in; ++i) {
+            const int64_t k = (int64_t)o * in + i;
+            Wt[(int64_t)i * out + o] = (mask && !mask[k]) ? (REAL)0 : W[k];
+        }
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < B; ++r) {
         const REAL* xr = x + r * ldx;
         const REAL* cr = c ? c + r * ldc : NULL;
+        REAL* __restrict__ yr = y + r * ldy;
+        for (int o = 0; o < out; ++o) yr[o] = 0;
+        for (int i = 0; i < in; ++i) {
+            const REAL xv = (i < dx) ? xr[i] : cr[i - dx];
+            const REAL* __restrict__ w = Wt + (int64_t)i * out;
+            for (int o = 0; o < out; ++o) yr[o] += xv * w[o];
+        }
         for (int o = 0; o < out; ++o) {
-            const REAL* w = W + (int64_t)o * in;
-            const uint8_t* m = mask ? mask + (int64_t)o * in : NULL;
-            REAL acc = 0;
-            for (int i = 0; i < dx; ++i) acc += xr[i] * ((m && !m[i]) ? (REAL)0 : w[i]);
-            for (int i = 0; i < dc; ++i)
-                acc += cr[i] * ((m && !m[dx + i]) ? (REAL)0 : w[dx + i]);
-            acc += bias ? bias[o] : (REAL)0;
-            if (relu && acc < 0) acc = 0;
-            y[r * ldy + o] = acc;
+            REAL v = yr[o] + (bias ? bias[o] : (REAL)0);
+            yr[o] = (relu && v < 0) ? (REAL)0 : v;
         }
     }
+    free(Wt);
 }
 
 /* ------------------------------------------------------------------------- */

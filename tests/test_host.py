@@ -1,0 +1,167 @@
+"""CPU tests of the host side: bit-exact mask / order construction, constructor parity
+with the reference (state-dict keys + CRC32 of every tensor), the C-ABI library
+(loads, exports every declared symbol), and the no-fallback behaviour."""
+
+import ctypes
+import io
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import zuko_b200 as zuko
+from cases import FLOW_CASES, build_flow, crc, load
+from zuko_b200 import _engine as E
+from zuko_b200.flows import MAF, NSF, MaskedAutoregressiveTransform
+from zuko_b200.nn import MaskedMLP, masked_mlp_masks
+from zuko_b200.transforms import MonotonicRQSTransform
+
+ROOT = Path(__file__).resolve().parent.parent
+M = load("masks")
+
+
+def _mat_specs():
+    adjacency = torch.from_numpy(M["adjacency"])
+    adj_ctx = torch.from_numpy(M["adjacency_ctx"])
+    rqs8 = dict(univariate=MonotonicRQSTransform, shapes=[(8,), (8,), (7,)])
+    rqs16 = dict(univariate=MonotonicRQSTransform, shapes=[(16,), (16,), (15,)])
+    return {
+        "maf4": dict(features=4, context=0, hidden_features=[32, 32]),
+        "nsf16c8": dict(features=16, context=8, hidden_features=[256] * 3, **rqs8),
+        "passes2": dict(features=5, context=7, passes=2, hidden_features=[16, 24]),
+        "order": dict(features=5, context=0, order=[3, 0, 4, 1, 2], hidden_features=[17]),
+        "rev64": dict(features=64, context=0, order=list(range(63, -1, -1)), hidden_features=[64, 64], **rqs16),
+        "adjacency": dict(features=5, context=0, adjacency=adjacency, hidden_features=[12, 12]),
+        "adjacency_ctx": dict(features=5, context=3, adjacency=adj_ctx, hidden_features=[12]),
+    }
+
+
+@pytest.mark.parametrize("name", list(_mat_specs()))
+def test_masks_bit_exact(name):
+    """Integer / boolean work must be bit-exact: masks, order classes and passes equal the
+    reference's (zuko/nn.py:258-318, flows/autoregressive.py:106-152)."""
+    t = MaskedAutoregressiveTransform(**_mat_specs()[name])
+    assert t.passes == int(M[f"{name}/passes"])
+    if f"{name}/order" in M:
+        assert np.array_equal(t.order.numpy(), M[f"{name}/order"])
+    else:
+        assert t.order is None
+    linears = [m for m in t.hyper if hasattr(m, "mask")]
+    for i, m in enumerate(linears):
+        shape = tuple(M[f"{name}/shape{i}"])
+        assert tuple(m.mask.shape) == shape
+        ref = np.unpackbits(M[f"{name}/mask{i}"])[: shape[0] * shape[1]].reshape(shape).astype(bool)
+        assert np.array_equal(m.mask.numpy(), ref), (name, i)
+    assert f"{name}/mask{len(linears)}" not in M
+
+
+def test_free_standing_masked_mlp():
+    adj = torch.from_numpy(M["free/adjacency"])
+    masks = masked_mlp_masks(adj, [16, 32])
+    for i, m in enumerate(masks):
+        assert np.array_equal(m.numpy(), M[f"free/mask{i}"])
+    with pytest.raises(ValueError):
+        masked_mlp_masks(torch.zeros(3, 3, dtype=torch.bool), [4])
+
+
+def test_adjacency_validation():
+    # reference: tests/test_flows.py:147-218
+    with pytest.raises(AssertionError, match="diagonal"):
+        MaskedAutoregressiveTransform(3, adjacency=torch.zeros(3, 3, dtype=torch.bool))
+    cyc = torch.eye(3, dtype=torch.bool)
+    cyc[0, 1] = cyc[1, 2] = cyc[2, 0] = True
+    with pytest.raises(AssertionError, match="cycles"):
+        MaskedAutoregressiveTransform(3, adjacency=cyc)
+    with pytest.raises(AssertionError, match="columns"):
+        MaskedAutoregressiveTransform(3, 2, adjacency=torch.eye(3, 4, dtype=torch.bool))
+
+
+@pytest.mark.parametrize("name", list(FLOW_CASES))
+def test_constructor_parity(name):
+    """Same seed => same state-dict keys and bit-identical tensors as the reference."""
+    g = load(f"flow_{name}")
+    seed, ctor = FLOW_CASES[name]
+    if seed is not None:
+        torch.manual_seed(seed)
+    sd = ctor().state_dict()
+    assert list(sd.keys()) == list(g["sd_keys"])
+    ours = np.array([crc(v) for v in sd.values()], dtype=np.int64)
+    bad = [k for k, a, b in zip(sd.keys(), ours, g["sd_crc"]) if a != b]
+    assert not bad, f"tensors differ from the reference initialisation: {bad[:5]}"
+
+
+def test_reference_checkpoint_loads():
+    g = load("flow_cfg1_maf")
+    flow = MAF(4, 0, transforms=2, hidden_features=[32, 32])
+    stored = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
+    flow.load_state_dict(stored, strict=True)
+    buf = io.BytesIO()
+    torch.save(flow, buf)  # tests/test_flows.py:77-91 saves the whole module
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert all(torch.equal(a, b) for a, b in zip(flow.state_dict().values(), again.state_dict().values()))
+    assert "MaskedAutoregressiveTransform" in repr(again)
+
+
+def test_features_one_falls_back_to_elementwise():
+    # flows/autoregressive.py:73-86
+    t = MaskedAutoregressiveTransform(1, 3)
+    assert type(t).__name__ == "ElementWiseTransform"
+
+
+def test_unsupported_options_raise():
+    with pytest.raises(NotImplementedError):
+        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), residual=True)
+    with pytest.raises(NotImplementedError):
+        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), activation=torch.nn.ELU)
+    with pytest.raises(NotImplementedError):
+        MaskedAutoregressiveTransform(3, univariate=torch.distributions.ExpTransform, shapes=[])
+
+
+# --------------------------------------------------------------------------- #
+# the C-ABI library
+# --------------------------------------------------------------------------- #
+
+
+def _declared_symbols():
+    header = (ROOT / "include" / "zuko_b200.h").read_text()
+    pat = r"^(?:zk_status|int|int64_t|size_t|const char\*)\s+(zk_[a-z0-9_]+)\s*\("
+    return sorted(set(re.findall(pat, header, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = E.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/zuko_b200.h but not exported"
+    assert set(E.EXPORTED_SYMBOLS) == set(declared), set(E.EXPORTED_SYMBOLS) ^ set(declared)
+    assert lib.zk_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly; nothing silently routes through torch or the oracle."""
+    flow = build_flow("nsf35_row")
+    x, c = torch.randn(8, 3), torch.randn(5)
+    with pytest.raises(E.EngineError, match="no CPU fallback"):
+        flow(c).log_prob(x)
+    with pytest.raises(E.EngineError, match="no CPU fallback"):
+        _ = zuko.transforms.SoftclipTransform()(torch.randn(3))
+
+
+def test_compute_without_device_is_an_error():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    lib = E.lib()
+    st = lib.zk_softclip_forward(None, 1, 0, 1, ctypes.c_float(1.0), None, 1, None, 0, None)
+    assert st in (E.ZK_EINVAL, E.ZK_ECUDA)
+    sm = ctypes.c_int()
+    assert lib.zk_device_info(ctypes.byref(sm), None, None) == E.ZK_ECUDA
+
+
+def test_product_does_not_import_oracle():
+    for path in (ROOT / "zuko_b200").rglob("*.py"):
+        src = path.read_text()
+        assert "oracle" not in src.replace("no CPU", ""), f"{path} mentions the oracle"

@@ -17,6 +17,7 @@ namespace zk {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_fast_math{1};
 
 zk_status fail(zk_status code, const char* fmt, ...) {
     char buf[1024];
@@ -92,7 +93,6 @@ struct zk_layer {
     int* idx_a = nullptr;          // device: constant-split columns (coupling), owned
     int* idx_b = nullptr;          // device: transformed columns (coupling), owned
     int n_a = 0, n_b = 0;
-    bool fast_math = true;
 };
 
 extern "C" {
@@ -100,6 +100,7 @@ extern "C" {
 int zk_version(void) { return 100; }
 const char* zk_last_error(void) { return g_last_error.c_str(); }
 int64_t zk_launch_count(void) { return g_launches.load(); }
+int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 
 zk_status zk_device_info(int* sm, int* major, int* minor) {
     int dev = 0;
@@ -122,6 +123,7 @@ zk_status zk_rqs_forward(const float* x, int64_t ldx, const float* phi, int64_t 
     a.univariate = ZK_UNI_RQS; a.x = x; a.ldx = ldx; a.phi = phi; a.phi_ld = phi_ld; a.B = B; a.D = D;
     a.K = K; a.bound = bound; a.slope = slope; a.y = y; a.ldy = ldy; a.ladj = ladj;
     a.accumulate = accumulate;
+    a.fast_math = g_fast_math.load() != 0;
     return launch_univariate(a, (cudaStream_t)stream);
 }
 
@@ -131,6 +133,7 @@ zk_status zk_rqs_inverse(const float* y, int64_t ldy, const float* phi, int64_t 
     UniArgs a;
     a.univariate = ZK_UNI_RQS; a.inverse = true; a.x = y; a.ldx = ldy; a.phi = phi; a.phi_ld = phi_ld;
     a.B = B; a.D = D; a.K = K; a.bound = bound; a.slope = slope; a.y = x; a.ldy = ldx;
+    a.fast_math = g_fast_math.load() != 0;
     return launch_univariate(a, (cudaStream_t)stream);
 }
 
@@ -140,6 +143,7 @@ zk_status zk_affine_forward(const float* x, int64_t ldx, const float* phi, int64
     UniArgs a;
     a.univariate = ZK_UNI_AFFINE; a.x = x; a.ldx = ldx; a.phi = phi; a.phi_ld = phi_ld; a.B = B;
     a.D = D; a.slope = slope; a.y = y; a.ldy = ldy; a.ladj = ladj; a.accumulate = accumulate;
+    a.fast_math = g_fast_math.load() != 0;
     return launch_univariate(a, (cudaStream_t)stream);
 }
 
@@ -148,6 +152,7 @@ zk_status zk_affine_inverse(const float* y, int64_t ldy, const float* phi, int64
     UniArgs a;
     a.univariate = ZK_UNI_AFFINE; a.inverse = true; a.x = y; a.ldx = ldy; a.phi = phi;
     a.phi_ld = phi_ld; a.B = B; a.D = D; a.slope = slope; a.y = x; a.ldy = ldx;
+    a.fast_math = g_fast_math.load() != 0;
     return launch_univariate(a, (cudaStream_t)stream);
 }
 
@@ -449,7 +454,7 @@ zk_status layer_forward_impl(const zk_layer* l, const float* x, int64_t ldx, con
     UniArgs a;
     a.univariate = l->uni; a.B = B; a.K = l->K; a.bound = l->bound; a.slope = l->slope;
     a.ladj = ladj; a.accumulate = accumulate; a.log_prob = log_prob; a.base_loc = loc;
-    a.base_scale = scale; a.fast_math = l->fast_math;
+    a.base_scale = scale; a.fast_math = g_fast_math.load() != 0;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:1005-1007 + flows/autoregressive.py:207-215
@@ -514,7 +519,7 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
     Arena ar(ws, ws_bytes);
     UniArgs a;
     a.univariate = l->uni; a.inverse = true; a.B = B; a.K = l->K; a.bound = l->bound;
-    a.slope = l->slope; a.fast_math = l->fast_math;
+    a.slope = l->slope; a.fast_math = g_fast_math.load() != 0;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:994-1000: x = zeros_like(y); for _ in range(passes): x = meta(x).inv(y)

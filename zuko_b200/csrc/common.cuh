@@ -17,6 +17,7 @@ namespace zk {
 // ---------------------------------------------------------------------------
 extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int> g_fast_math;
 
 zk_status fail(zk_status code, const char* fmt, ...);
 
