@@ -54,6 +54,8 @@ def layer_forward(handle, D: int, x: Tensor, c: Tensor | None) -> tuple[Tensor, 
     B = x2.shape[0]
     y = torch.empty_like(x2)
     ladj = torch.empty(B, device=x2.device, dtype=torch.float32)
+    if B == 0:
+        return y.reshape(*lead, D), ladj.reshape(lead)
     L = E.lib()
     with torch.cuda.device(x2.device):
         need = L.zk_layer_workspace_bytes(handle, B)
@@ -72,6 +74,8 @@ def layer_inverse(handle, D: int, y: Tensor, c: Tensor | None) -> Tensor:
     y2, c2, ldc, lead = _flatten(y, c, D)
     B = y2.shape[0]
     x = torch.empty_like(y2)
+    if B == 0:
+        return x.reshape(*lead, D)
     L = E.lib()
     with torch.cuda.device(y2.device):
         need = L.zk_layer_workspace_bytes(handle, B)
@@ -132,6 +136,9 @@ class FlowCall:
         B = x2.shape[0]
         lp = torch.empty(B, device=x2.device, dtype=torch.float32)
         total = torch.zeros(1, device=x2.device, dtype=torch.float64) if with_sum else None
+        if B == 0:
+            lp = lp.reshape(lead)
+            return (lp, total) if with_sum else lp
         with torch.cuda.device(x2.device):
             ws = self._ws(x2.device, max(B, 1))
             E.check(

@@ -64,7 +64,12 @@ __device__ __forceinline__ float softclip(float v, float a) {
 // true the vertical ones (inverse, transforms.py:535).
 // ---------------------------------------------------------------------------
 struct Bin {
-    float x0, x1, y0, y1, d0, d1;
+    float x0, y0;  // left knot of the selected bin
+    float dx, dy;  // bin width / height, formed directly from the softmax numerators:
+                   // bound * 2 * softmax_k, i.e. WITHOUT the cancellation of knot_{k+1} - knot_k
+                   // (transforms.py:505-509 subtracts two rounded knots; for a sharp spline
+                   // that costs up to ulp(5)/width in the slope s — here it costs ~1 ulp)
+    float d0, d1;
     bool inside;
 };
 
@@ -96,7 +101,7 @@ __device__ __forceinline__ Bin rqs_select(const float* __restrict__ p, int Krt, 
     float cw = 0.f, ch = 0.f;
     float xl = -bound, yl = -bound, rl = 0.f;  // left knot of the current bin, raw derivative
     Bin b;
-    b.x0 = xl; b.x1 = xl; b.y0 = yl; b.y1 = yl;
+    b.x0 = xl; b.y0 = yl; b.dx = 0.f; b.dy = 0.f;
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -117,9 +122,9 @@ __device__ __forceinline__ Bin rqs_select(const float* __restrict__ p, int Krt, 
         // sum_j [knot_j < v] - 1 of transforms.py:521-523 (strict <)
         const bool take = (j == 0) || ((SEARCH_Y ? yl : xl) < v);
         b.x0 = take ? xl : b.x0;
-        b.x1 = take ? xr : b.x1;
         b.y0 = take ? yl : b.y0;
-        b.y1 = take ? yr : b.y1;
+        b.dx = take ? e0 : b.dx;
+        b.dy = take ? e1 : b.dy;
         r0 = take ? rl : r0;
         r1 = take ? rr : r1;
         xl = xr;
@@ -128,6 +133,8 @@ __device__ __forceinline__ Bin rqs_select(const float* __restrict__ p, int Krt, 
     }
     // mask = 0 <= k < K (transforms.py:500): first knot (-bound) < v and NOT last knot < v
     b.inside = (-bound < v) && !((SEARCH_Y ? yl : xl) < v);
+    b.dx *= gx;
+    b.dy *= gy;
     b.d0 = zexp<FAST>(softclip<FAST>(r0, ad));  // transforms.py:482,490 (exp(0) = 1 at the ends)
     b.d1 = zexp<FAST>(softclip<FAST>(r1, ad));
     return b;
@@ -136,7 +143,7 @@ __device__ __forceinline__ Bin rqs_select(const float* __restrict__ p, int Krt, 
 // forward spline + log-derivative, transforms.py:554-567
 template <bool FAST>
 __device__ __forceinline__ void rqs_forward_eval(const Bin& b, float x, float& y, float& ladj) {
-    const float dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+    const float dx = b.dx, dy = b.dy;
     const float s = zdiv<FAST>(dy, dx);
     const float z = zdiv<FAST>(x - b.x0, dx);
     const float omz = 1.f - z;
@@ -155,7 +162,7 @@ __device__ __forceinline__ void rqs_forward_eval(const Bin& b, float x, float& y
 // inverse spline, transforms.py:534-548
 template <bool FAST>
 __device__ __forceinline__ float rqs_inverse_eval(const Bin& b, float y) {
-    const float dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+    const float dx = b.dx, dy = b.dy;
     const float s = zdiv<FAST>(dy, dx);
     const float y_ = y - b.y0;
     const float t = b.d0 + b.d1 - 2.f * s;
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(kUniThreads) uni_kernel(const UniParams a) {
 template <int UNI, int KT, bool INVERSE>
 zk_status launch_uni_t(const UniParams& p, bool fast, int grid, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> zk_status {
-        if (smem > 48 * 1024)
+        if (smem + 2048 > 48 * 1024)  // static smem (barrier) counts against the 48 KB default
             ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kUniThreads, smem, st>>>(p);
         return check_launch("uni_kernel");
