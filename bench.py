@@ -121,6 +121,16 @@ def cuda_time_ms(fn, iters: int, stream=None) -> float:
 # --------------------------------------------------------------------------- #
 
 
+def cpu_reference_adaptive(target_s: float, rows0: int = 1 << 15, max_rows: int = 1 << 22):
+    """Sizes the bounded CPU sample so that it takes about target_s seconds on this host."""
+    rate0, _, _ = cpu_reference_rate(rows0)
+    rows = int(min(max_rows, max(rows0, rate0 * target_s)))
+    rows = 1 << max(10, rows.bit_length() - 1)  # power of two
+    if rows <= rows0:
+        return cpu_reference_rate(rows0) + (rows0,)
+    return cpu_reference_rate(rows) + (rows,)
+
+
 def cpu_reference_rate(rows: int, repeats: int = 1):
     """Times the oracle's fp32 CPU restatement of flow(c).log_prob(x) (all host threads, OpenMP)
     on `rows` rows of the bench workload.  Returns (samples/s, seconds, threads)."""
@@ -144,9 +154,10 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = args.cpu_rows
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_rate(min(rows, 1024))
+    # one step = a bounded sample of the workload, sized for ~4 s per step on this host
+    rate0, _, threads = cpu_reference_rate(1 << 15)  # also the warm-up
+    rows = args.cpu_rows or (1 << max(15, int(rate0 * 4.0).bit_length() - 1))
+    rows = min(rows, 1 << 22)
     times = []
     for _ in range(args.steps):
         rate, sec, threads = cpu_reference_rate(rows)
@@ -272,9 +283,13 @@ def run_ours(args) -> None:
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec, threads = cpu_reference_rate(args.cpu_rows)
+            if args.cpu_rows:
+                rate, sec, threads = cpu_reference_rate(args.cpu_rows)
+                rows = args.cpu_rows
+            else:
+                rate, sec, threads, rows = cpu_reference_adaptive(12.0)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_rows} rows of the workload, oracle fp32 C port with OpenMP, {sec:.1f} s"}  # fmt: skip
+                   "sample": f"{rows} rows of the workload, oracle fp32 C port with OpenMP, {sec:.1f} s"}  # fmt: skip
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -351,7 +366,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
-    ap.add_argument("--cpu-rows", type=int, default=1 << 15, help="rows of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = size it to ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
