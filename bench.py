@@ -209,13 +209,12 @@ def run_ours(args) -> None:
     cs = [t.to(dev) for t in cs_host]
     red = torch.zeros(2, dtype=torch.float64, device=dev)
 
+    from zuko_b200.dist import mean_nll
+
     def step(i: int):
         d = flow(cs[i % NBUF])
         lp, total = d.log_prob_and_sum(xs[i % NBUF])
-        red[0:1].copy_(total)
-        red[1] = float(B)
-        if world > 1:
-            dist.all_reduce(red)  # ONE collective: {sum log p, count} -> mean NLL
+        red[0] = mean_nll(total, B)  # ONE collective over {sum log p, count} when world > 1
         return lp
 
     with torch.no_grad():
@@ -252,7 +251,7 @@ def run_ours(args) -> None:
         launches = E.lib().zk_launch_count() - launches0
         ms_per_step = elapsed_ms.item() / args.steps
         value = world * B / (ms_per_step * 1e-3)
-        mean_nll = -(red[0] / red[1]).item()
+        nll_value = red[0].item()
 
         # ---- end to end through the public API with HOST buffers (H2D + compute + D2H per step)
         fc = flow(cs[0])._flow_call()[0]
@@ -298,7 +297,7 @@ def run_ours(args) -> None:
                        "parallelism": f"dp{world}", "l2": f"inputs rotate over {NBUF} buffers ({NBUF * B * (D + C) * 4 >> 20} MB > 126 MB L2); phi intermediates {B * D * P * 4 >> 20} MB per layer"},
             "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4, "d2h_bytes_per_step": B * 4,
                                              "steps": e2e_steps, "api": "FlowCall.log_prob_host -> zk_flow_log_prob_host (pinned host buffers)"},
-            "gpu_launches": int(launches), "mean_nll": mean_nll, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "mean_nll": nll_value, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu, "parity": parity,
         }  # fmt: skip
         print(json.dumps(line))

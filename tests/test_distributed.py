@@ -1,0 +1,67 @@
+"""CPU tests of the N > 1 host logic with the gloo backend (world_size 2): row sharding and
+the single mean-NLL all-reduce.  The per-rank log-densities come from the oracle here (no GPU
+in this container); on the GPU box bench.py exercises the same helpers over NCCL."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cases import build_flow, load
+from zuko_b200.dist import mean_nll, shard_rows
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 8, 1000, 1 << 20):
+        for w in (1, 2, 3, 8):
+            spans = [shard_rows(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_rows(10, 2, 2)
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, out):
+    from oracle import oracle as O
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load("flow_nsf35_row")
+        spec = O.flowspec_from_module(build_flow("nsf35_row", g))
+        lo, hi = shard_rows(g["x"].shape[0], rank, world)
+        lp = spec.log_prob(g["x"][lo:hi], g["c"])
+        local = torch.tensor([lp.sum()], dtype=torch.float64)
+        nll = mean_nll(local, hi - lo)
+        out[rank] = float(nll)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mean_nll_allreduce_gloo_world2():
+    g = load("flow_nsf35_row")
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+        got = dict(out)
+    expect = -float(np.mean(g["log_prob64"]))
+    assert got[0] == got[1]  # every rank holds the same reduced scalar
+    assert abs(got[0] - expect) < 1e-9 * abs(expect)
+
+
+def test_mean_nll_without_process_group():
+    v = mean_nll(torch.tensor([-30.0], dtype=torch.float64), 10)
+    assert v.item() == 3.0
