@@ -224,6 +224,12 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* flow, const float* x_host, i
  * approximations, 0 = IEEE division + expf / logf.  Process-wide; returns the previous
  * value.  Both settings meet the 1e-5 parity bar on the BASELINE configs (tests/). */
 int zk_set_fast_math(int on);
+/* 1 (default): an autoregressive layer whose conditioner fits the fused kernel (hidden widths
+ * equal, multiple of 64, <= 256; D + C <= 256; RQS with 8 / 16 bins or affine; tensor-core GEMM
+ * mode) runs as ONE kernel — conditioner + bijector + ladj, activations and phi stay on chip.
+ * 0: always one GEMM kernel per linear layer + the stand-alone bijector kernel.  Returns the
+ * previous value. */
+int zk_set_fused_layers(int on);
 
 /* number of kernel launches issued by this library since load (bench evidence) */
 int64_t zk_launch_count(void);

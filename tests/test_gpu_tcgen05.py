@@ -87,3 +87,73 @@ def test_auto_mode_picks_tensor_cores_for_wide_layers(device):
     tiny = _masked((8, 4), [32, 32]).to(device)
     assert E.lib().zk_mlp_gemm_mode(wide._handle()) == E.ZK_GEMM_BF16X3
     assert E.lib().zk_mlp_gemm_mode(tiny._handle()) == E.ZK_GEMM_FP32
+
+
+# --------------------------------------------------------------------------- #
+# fully fused layer kernel (conditioner + bijector + ladj in one launch)
+# --------------------------------------------------------------------------- #
+
+FUSED_FLOWS = {
+    "nsf16c8_h256": lambda: zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 3),   # cfg2 shape
+    "nsf64_k16_h64": lambda: zuko.flows.NSF(64, 0, transforms=2, bins=16),                             # cfg4 shape
+    "nsf5c3_h192": lambda: zuko.flows.NSF(5, 3, transforms=3, bins=8, hidden_features=[192, 192]),     # 64-wide chunks, D % 4 != 0
+    "nsf7_k16_h128": lambda: zuko.flows.NSF(7, 0, transforms=2, bins=16, hidden_features=[128, 128]),  # odd D with DPC = 2
+    "maf32_h256": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[256] * 2),              # affine, 64 dims / chunk
+    "maf70c100_h128": lambda: zuko.flows.MAF(70, 100, transforms=2, hidden_features=[128] * 2),        # K0 = 170 -> 3 K blocks, 2 affine chunks
+}
+
+
+@pytest.fixture
+def unfused():
+    def run(fn):
+        prev = E.lib().zk_set_fused_layers(0)
+        try:
+            return fn()
+        finally:
+            E.lib().zk_set_fused_layers(prev)
+
+    return run
+
+
+@pytest.mark.parametrize("name", list(FUSED_FLOWS))
+@pytest.mark.parametrize("B", [1, 100, 128, 777, 20000])
+def test_fused_layer_matches_unfused_and_oracle(device, unfused, name, B):
+    torch.manual_seed(11)
+    flow_cpu = FUSED_FLOWS[name]().eval()
+    spec = O.flowspec_from_module(flow_cpu)
+    D = flow_cpu.base.loc.shape[0]
+    C = flow_cpu.transform.transforms[0].context
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, D, generator=g)
+    c = torch.randn(B, C, generator=g) if C else None
+    flow = FUSED_FLOWS[name]()
+    flow.load_state_dict(flow_cpu.state_dict())
+    flow = flow.to(device)
+    xd, cd = x.to(device), (None if c is None else c.to(device))
+    from zuko_b200.flows._packed import PackedLayerMixin  # noqa: F401
+
+    dist = flow(cd)
+    lp_f = dist.log_prob(xd)
+    z_f, ladj_f = dist.transform.call_and_ladj(xd)
+    lp_u = unfused(lambda: flow(cd).log_prob(xd))
+    z_u, ladj_u = unfused(lambda: flow(cd).transform.call_and_ladj(xd))
+    ref = spec.log_prob(x.numpy(), None if c is None else c.numpy())
+    assert rel_err(lp_f.cpu().numpy(), ref) < 1e-5
+    assert rel_err(lp_u.cpu().numpy(), ref) < 1e-5
+    # same arithmetic (split-bf16 GEMMs, same bijector math): fused and unfused agree to rounding
+    assert torch.allclose(lp_f, lp_u, rtol=2e-6, atol=2e-5)
+    assert torch.allclose(z_f, z_u, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(ladj_f, ladj_u, rtol=2e-6, atol=2e-5)
+
+
+def test_fused_layer_broadcast_context_and_launch_count(device):
+    torch.manual_seed(3)
+    flow = zuko.flows.NSF(16, 8, transforms=4, bins=8, hidden_features=[256] * 3).to(device)
+    x = torch.randn(4096, 16, device=device)
+    c_row = torch.randn(8, device=device)
+    lp_row = flow(c_row).log_prob(x)
+    lp_full = flow(c_row.expand(4096, 8).contiguous()).log_prob(x)
+    assert torch.equal(lp_row, lp_full)
+    n0 = E.lib().zk_launch_count()
+    flow(c_row).log_prob(x)
+    assert E.lib().zk_launch_count() - n0 == 4  # ONE kernel per flow layer, base log-prob fused into the last

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "bijectors.cuh"
+#include "fused_layer.cuh"
 #include "mlp.cuh"
 #include "mlp_tcgen05.cuh"
 
@@ -18,6 +19,7 @@ namespace zk {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_fast_math{1};
+std::atomic<int> g_fused{1};
 
 zk_status fail(zk_status code, const char* fmt, ...) {
     char buf[1024];
@@ -101,6 +103,7 @@ int zk_version(void) { return 100; }
 const char* zk_last_error(void) { return g_last_error.c_str(); }
 int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
+int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
 
 zk_status zk_device_info(int* sm, int* major, int* minor) {
     int dev = 0;
@@ -458,6 +461,16 @@ zk_status layer_forward_impl(const zk_layer* l, const float* x, int64_t ldx, con
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:1005-1007 + flows/autoregressive.py:207-215
+            if (g_fused.load() && fused_layer_supported(l->hyper, l->uni, l->K, l->D, l->C)) {
+                // ONE kernel: conditioner GEMMs + bijector + ladj; neither the hidden
+                // activations nor phi touch HBM
+                FusedLayerArgs f;
+                f.univariate = l->uni; f.bins = l->K; f.D = l->D; f.C = l->C; f.bound = l->bound;
+                f.slope = l->slope; f.x = x; f.ldx = ldx; f.c = c; f.ldc = ldc; f.B = B; f.y = y; f.ldy = ldy;
+                f.ladj = ladj; f.accumulate = accumulate; f.log_prob = log_prob; f.base_loc = loc;
+                f.base_scale = scale; f.fast_math = g_fast_math.load() != 0;
+                return launch_fused_layer(l->hyper, f, st);
+            }
             float* phi = ar.take<float>((size_t)B * l->D * l->P);
             ZK_REQUIRE(ar.ok, "layer_forward: workspace too small");
             ZK_TRY(zk_mlp_forward(l->hyper, x, ldx, l->D, c, ldc, l->C, B, phi, (int64_t)l->D * l->P,

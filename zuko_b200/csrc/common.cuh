@@ -18,6 +18,7 @@ namespace zk {
 extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
 extern std::atomic<int> g_fast_math;
+extern std::atomic<int> g_fused;
 
 zk_status fail(zk_status code, const char* fmt, ...);
 

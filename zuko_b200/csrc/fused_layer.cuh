@@ -1,0 +1,28 @@
+// zuko_b200 — fully fused flow-layer kernel (conditioner + bijector + ladj): interface.
+#pragma once
+
+#include "mlp.cuh"
+
+#define ZK_FUSED_MAX_LINEAR 6
+
+namespace zk {
+
+struct FusedLayerArgs {
+    int univariate = ZK_UNI_RQS;
+    int bins = 8;
+    int D = 0, C = 0;
+    float bound = 5.f, slope = 1e-3f;
+    const float* x = nullptr; int64_t ldx = 0;
+    const float* c = nullptr; int64_t ldc = 0;
+    int64_t B = 0;
+    float* y = nullptr; int64_t ldy = 0;  // may be null (log_prob only)
+    float* ladj = nullptr; int accumulate = 0;
+    float* log_prob = nullptr; const float* base_loc = nullptr; const float* base_scale = nullptr;
+    bool fast_math = true;
+};
+
+// true when the autoregressive layer (conditioner `m`, univariate, D, C) can run as ONE kernel
+bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C);
+zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
+
+}  // namespace zk
