@@ -274,7 +274,7 @@ def run_ours(args) -> None:
         kernels, roofline = [], None
         if rank == 0:
             kernels = time_kernels(flow, xs[0], cs[0], dev, peaks, iters=max(3, min(args.steps, 10)))
-            dom = max(kernels, key=lambda k: k["ms_per_step"])
+            dom = max((k for k in kernels if k["in_step"]), key=lambda k: k["ms_per_step"])
             roofline = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             roofline["kernel"] = dom["name"]
             roofline["peak_source"] = peaks["source"]
@@ -313,11 +313,9 @@ def gemm_mode_name(flow) -> str:
 
 
 def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
-    """Times each kernel class of one flow layer in isolation through the stand-alone C-ABI
-    entry points (CUDA events on the current stream) and converts to roofline terms.
-    Algorithmic bytes / FLOPs per SURVEY §8d; x4 layers per step."""
-    import ctypes
-
+    """Times each kernel class of one flow layer in isolation through the C-ABI entry points
+    (CUDA events on the current stream) and converts to roofline terms.  Algorithmic bytes /
+    FLOPs per SURVEY §8d; a step launches each of them T = 4 times (once per flow layer)."""
     from zuko_b200 import _engine as E
 
     L = E.lib()
@@ -325,11 +323,12 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     layer = flow.transform.transforms[0]
     hyper = layer.hyper
     h = hyper._handle()
+    hl = layer._zk_layer()
     phi = torch.empty(B, D * P, device=dev)
     y = torch.empty_like(x)
     ladj = torch.zeros(B, device=dev)
-    need = L.zk_mlp_workspace_bytes(h, B)
-    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    need = max(L.zk_mlp_workspace_bytes(h, B), L.zk_layer_workspace_bytes(hl, B), 1)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
     st = E.stream_ptr(dev)
 
     def mlp():
@@ -338,24 +337,46 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     def rqs():
         E.check(L.zk_rqs_forward(x.data_ptr(), D, phi.data_ptr(), D * P, B, D, K, 5.0, 1e-3, y.data_ptr(), D, ladj.data_ptr(), 1, st))
 
-    for _ in range(2):
-        mlp()
-        rqs()
-    t_mlp = cuda_time_ms(mlp, iters)
-    t_rqs = cuda_time_ms(rqs, iters)
+    def fused():
+        E.check(L.zk_layer_forward(hl, x.data_ptr(), D, c.data_ptr(), C, B, y.data_ptr(), D, ladj.data_ptr(), 1, ws.data_ptr(), ws.numel(), st))
+
     dims = [D + C, *H, D * P]
     flops = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * B  # dense FLOPs nn.py:218 executes
     rqs_bytes = 4.0 * (D + D * P + D + 1) * B  # x + phi + y + ladj
+    fused_bytes = 4.0 * (D + C + D + 1) * B    # fused layer: x, c in; y, ladj out
+    out = []
+    n0 = L.zk_launch_count()
+    fused()
+    is_fused = (L.zk_launch_count() - n0) == 1
+    if is_fused:
+        fused()
+        t = cuda_time_ms(fused, iters)
+        tf = flops / (t * 1e-3) / 1e12
+        out.append({"name": "fused_layer_kernel<RQS,8> (conditioner 24-256-256-256-368 on tcgen05 + RQS + ladj), one flow layer",
+                    "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "ms_per_launch": t, "ms_per_step": t * T,
+                    "algorithmic_flops": flops, "issued_flops": 3 * flops, "frac_issued": 3 * tf / peaks["bf16_tflops_sustained"],
+                    "algorithmic_hbm_bytes": fused_bytes, "in_step": True})  # fmt: skip
+    prev = L.zk_set_fused_layers(0)
+    try:
+        for _ in range(2):
+            mlp()
+            rqs()
+        t_mlp = cuda_time_ms(mlp, iters)
+        t_rqs = cuda_time_ms(rqs, iters)
+    finally:
+        L.zk_set_fused_layers(prev)
     tf = flops / (t_mlp * 1e-3) / 1e12
     gbs = rqs_bytes / (t_rqs * 1e-3) / 1e9
-    return [
-        {"name": "conditioner (MaskedMLP 24-256-256-256-368), one flow layer", "bound": "tensor", "achieved": tf,
-         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
-         "traffic": None, "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops},
-        {"name": "uni_kernel<RQS,8> fused RQS + ladj, one flow layer", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": t_rqs, "ms_per_step": t_rqs * T,
-         "algorithmic_bytes": rqs_bytes},
+    out += [
+        {"name": "unfused conditioner: split_input + 4 x linear_tc_kernel (24-256-256-256-368), one flow layer", "bound": "tensor",
+         "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
+         "traffic": None, "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops, "in_step": not is_fused},
+        {"name": "uni_kernel<RQS,8> stand-alone fused RQS + ladj (phi in HBM), one flow layer", "bound": "hbm", "achieved": gbs,
+         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": t_rqs,
+         "ms_per_step": t_rqs * T, "algorithmic_bytes": rqs_bytes, "in_step": not is_fused},
     ]  # fmt: skip
+    return out
 
 
 def main() -> None:
