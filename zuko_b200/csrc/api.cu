@@ -212,7 +212,7 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
         const int64_t n = (int64_t)m->dims[i + 1] * m->dims[i];
         float *w = nullptr, *b = nullptr;
         if (!d->weight[i]) { st = fail(ZK_EINVAL, "mlp_create: weight[%d] is null", i); break; }
-        if (cudaMalloc((void**)&w, n * 4) != cudaSuccess || cudaMalloc((void**)&b, (size_t)m->dims[i + 1] * 4) != cudaSuccess) {
+        if (cudaMalloc((void**)&w, n * 4) != cudaSuccess || cudaMalloc((void**)&b, ((size_t)m->dims[i + 1] + 4) * 4) != cudaSuccess /* +4: vector loads may touch one pad element */) {
             cudaFree(w);
             st = fail(ZK_ENOMEM, "mlp_create: cudaMalloc failed");
             break;
@@ -222,11 +222,10 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
         const uint8_t* mk = (d->mask ? d->mask[i] : nullptr);
         st = launch_apply_mask(d->weight[i], mk, n, w, 0);
         if (st != ZK_OK) break;
+        if (cudaMemsetAsync(b, 0, ((size_t)m->dims[i + 1] + 4) * 4, 0) != cudaSuccess) st = fail(ZK_ECUDA, "mlp_create: bias memset failed");
         if (d->bias && d->bias[i]) {
             if (cudaMemcpyAsync(b, d->bias[i], (size_t)m->dims[i + 1] * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess)
                 st = fail(ZK_ECUDA, "mlp_create: bias copy failed");
-        } else if (cudaMemsetAsync(b, 0, (size_t)m->dims[i + 1] * 4, 0) != cudaSuccess) {
-            st = fail(ZK_ECUDA, "mlp_create: bias memset failed");
         }
         if (i < d->n_linear - 1) m->max_hidden = std::max(m->max_hidden, m->dims[i + 1]);
     }

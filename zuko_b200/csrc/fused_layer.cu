@@ -251,18 +251,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                     mbar_arrive(&d_empty[buf]);  // accumulator buffer is free again
                     uint32_t ph[32], pl[32];
                     const int nbase = ch * p.CW + col0;
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + nbase);  // 128-byte aligned
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float v0 = fmaxf(__uint_as_float(ra[j]) + __ldg(bias + nbase + j), 0.f);
-                        const float v1 = fmaxf(__uint_as_float(ra[j + 1]) + __ldg(bias + nbase + j + 1), 0.f);
-                        split2_bf16(v0, v1, ph[j >> 1], pl[j >> 1]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bb = __ldg(b4 + (j >> 2));  // one broadcast 16-byte load per 4 columns
+                        split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
+                                    ph[j >> 1], pl[j >> 1]);
+                        split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
+                                    ph[(j >> 1) + 1], pl[(j >> 1) + 1]);
                     }
                     if (ncols == 64) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float v0 = fmaxf(__uint_as_float(rb[j]) + __ldg(bias + nbase + 32 + j), 0.f);
-                            const float v1 = fmaxf(__uint_as_float(rb[j + 1]) + __ldg(bias + nbase + 32 + j + 1), 0.f);
-                            split2_bf16(v0, v1, ph[16 + (j >> 1)], pl[16 + (j >> 1)]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = __ldg(b4 + 8 + (j >> 2));
+                            split2_bf16(fmaxf(__uint_as_float(rb[j]) + bb.x, 0.f), fmaxf(__uint_as_float(rb[j + 1]) + bb.y, 0.f),
+                                        ph[16 + (j >> 1)], pl[16 + (j >> 1)]);
+                            split2_bf16(fmaxf(__uint_as_float(rb[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(rb[j + 3]) + bb.w, 0.f),
+                                        ph[17 + (j >> 1)], pl[17 + (j >> 1)]);
                         }
                     }
                     if (ch == 0) {  // the A operand may be overwritten once ALL MMAs of this layer are done
@@ -313,10 +318,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                 float v[64];
                 const int nbase = ch * DPC * P + base;  // global output column of v[0]
                 const int n_total = p.D * P;
+                const float2* b2 = reinterpret_cast<const float2*>(bias + nbase);  // nbase is even
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(ra[j]) + ((nbase + j < n_total) ? __ldg(bias + nbase + j) : 0.f);
-                    v[32 + j] = __uint_as_float(rb[j]) + ((nbase + 32 + j < n_total) ? __ldg(bias + nbase + 32 + j) : 0.f);
+                for (int j = 0; j < 32; j += 2) {
+                    // float2 pairs are entirely inside or outside [0, n_total): both bounds are even
+                    const float2 ba = (nbase + j < n_total) ? __ldg(b2 + (j >> 1)) : make_float2(0.f, 0.f);
+                    const float2 bb = (nbase + 32 + j < n_total) ? __ldg(b2 + 16 + (j >> 1)) : make_float2(0.f, 0.f);
+                    v[j] = __uint_as_float(ra[j]) + ba.x;
+                    v[j + 1] = __uint_as_float(ra[j + 1]) + ba.y;
+                    v[32 + j] = __uint_as_float(rb[j]) + bb.x;
+                    v[33 + j] = __uint_as_float(rb[j + 1]) + bb.y;
                 }
                 auto do_dim = [&](const float* pp, int dloc) {
                     const int d = ch * DPC + dloc;

@@ -101,13 +101,14 @@ inline int pad64(int v) { return (v + 63) / 64 * 64; }
 // tensor map over bf16 planes [2][rows][Kp]; box = (64 x box_rows x 1), 128B swizzle
 zk_status make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows);
 
-// bf16 hi / lo split of two fp32 values, packed as (lo16 = first, hi16 = second)
+// bf16 hi / lo split of two fp32 values, packed as (low 16 bits = first, high 16 = second).
+// hi = rn_bf16(v) (one cvt.rn.bf16x2.f32 for the pair), lo = rn_bf16(v - hi): 6 instructions / pair.
 __device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+    lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
 }  // namespace zk
