@@ -230,6 +230,9 @@ int zk_set_fast_math(int on);
  * 0: always one GEMM kernel per linear layer + the stand-alone bijector kernel.  Returns the
  * previous value. */
 int zk_set_fused_layers(int on);
+/* Profiling hook: a DEVICE buffer of >= 256 int64 that the fused layer kernel fills with clock64()
+ * stamps of its pipeline events (CTA 0, third tile); NULL (default) disables it. */
+void zk_debug_timeline(long long* device_buffer);
 
 /* number of kernel launches issued by this library since load (bench evidence) */
 int64_t zk_launch_count(void);

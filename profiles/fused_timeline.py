@@ -1,0 +1,27 @@
+import sys, torch, numpy as np
+sys.path.insert(0, '/root/repo')
+import zuko_b200 as zuko
+from zuko_b200 import _engine as E
+torch.manual_seed(0)
+dev = torch.device('cuda:0')
+flow = zuko.flows.NSF(16, 8, transforms=1, bins=8, hidden_features=[256]*3).to(dev)
+B = 1 << 20
+x = torch.randn(B, 16, device=dev); c = torch.randn(B, 8, device=dev)
+flow(c).log_prob(x); torch.cuda.synchronize()
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
+E.lib().zk_debug_timeline(buf.data_ptr())
+flow(c).log_prob(x); torch.cuda.synchronize()
+E.lib().zk_debug_timeline(None)
+t = buf.cpu().numpy()
+t0 = t[48]
+names = {48: 'epi: tile start', 49: 'epi: input staged', 50: 'epi: tile end'}
+for l in range(4):
+    names[8*l+0] = f'mma L{l}: a_ready[0] seen'; names[8*l+1] = f'mma L{l}: a_ready[last] seen'; names[8*l+2] = f'mma L{l}: first W stage full'; names[8*l+3] = f'mma L{l}: all issued'
+for l in range(3):
+    for ch in range(2):
+        b = 64 + 16*l + 4*ch
+        names[b] = f'epi L{l}c{ch}: d_full seen'; names[b+1] = f'epi L{l}c{ch}: computed'; names[b+2] = f'epi L{l}c{ch}: layer_done seen'; names[b+3] = f'epi L{l}c{ch}: A written'
+for ch in range(8):
+    names[160+2*ch] = f'epi last c{ch}: d_full seen'; names[161+2*ch] = f'epi last c{ch}: dims done'
+ev = sorted((int(v - t0), names.get(i, str(i))) for i, v in enumerate(t) if v != 0)
+for dt, n in ev: print(f'{dt:8d}  {n}')

@@ -127,7 +127,7 @@ def test_unsupported_options_raise():
 
 def _declared_symbols():
     header = (ROOT / "include" / "zuko_b200.h").read_text()
-    pat = r"^(?:zk_status|int|int64_t|size_t|const char\*)\s+(zk_[a-z0-9_]+)\s*\("
+    pat = r"^(?:zk_status|int|int64_t|size_t|void|const char\*)\s+(zk_[a-z0-9_]+)\s*\("
     return sorted(set(re.findall(pat, header, flags=re.M)))
 
 

@@ -104,6 +104,7 @@ const char* zk_last_error(void) { return g_last_error.c_str(); }
 int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
+void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
 
 zk_status zk_device_info(int* sm, int* major, int* minor) {
     int dev = 0;

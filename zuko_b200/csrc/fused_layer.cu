@@ -62,6 +62,7 @@ struct FusedParams {
     float* ladj; int accumulate;
     float* log_prob; const float* base_loc; const float* base_scale;
     float bound, aw, ad;
+    long long* dbg;  // optional timeline buffer (clock64 stamps of CTA 0, third tile), see zk_debug_timeline
 };
 
 // 16 bytes into the canonical K-major SWIZZLE_128B tile: row r, 16-byte chunk c (8 bf16)
@@ -69,6 +70,11 @@ __device__ __forceinline__ void st_swizzled(uint8_t* tile, int r, int c, uint32_
     const uint32_t addr = smem_u32(tile) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(cc), "r"(d) : "memory");
 }
+
+#define ZK_STAMP(slot)                                                        \
+    do {                                                                      \
+        if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on) p.dbg[(slot)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -83,7 +89,7 @@ template <>
 struct LastCfg<ZK_UNI_AFFINE, 0> { static constexpr int P = 2, DPC = 64; };
 
 template <int UNI, int KT, bool FAST>
-__global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
     constexpr int P = Cfg::P, DPC = Cfg::DPC;
     constexpr int N_LAST = (DPC * P + 15) & ~15;       // MMA N of a last-layer chunk
@@ -104,24 +110,33 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
     uint64_t* layer_done = bars + 14;         // [1]  all MMAs issued so far have completed
     uint32_t* tmem_slot = (uint32_t*)(bars + 15);
     float* s_part = (float*)(bars + 16);      // [2][128] ladj partials of warp set 1
+    volatile int* s_tile = (volatile int*)(s_part + 2 * FM);  // tiles started by the epilogue (paces the prefetcher)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int L = p.n_linear;
     const int m_tiles = (p.M + FM - 1) / FM;
+    // CTA pairs (clusters of 2) walk the tiles together: pair `cid` takes tiles 2 (cid + i ncl) + rank.
+    // Both CTAs always run the same number of iterations (the W stream is shared through TMA
+    // multicast); a CTA whose tile index falls off the end processes an all-masked dummy tile.
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int n_iter = ((m_tiles + 1) / 2 - cid + ncl - 1) / ncl;  // iterations of this pair (>= 0)
     const int KBH = p.H / FK;
     const int nch_hidden = p.H / p.CW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < F_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs of the pair
         for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], 256); }
         for (int k = 0; k < F_MAXKB; ++k) mbar_init(&a_ready[k], 256);
         mbar_init(layer_done, 1);
+        *s_tile = 0;
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
             const uint32_t bytes = (p.n_terms == 3) ? F_KBLOCK : F_PLANE;
             int ws = 0;
             uint32_t wph = 0;
-            for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            for (int it = 0; it < n_iter; ++it) {
                 for (int l = 0; l < L; ++l) {
                     const bool last = (l == L - 1);
                     const int nch = last ? p.n_last_chunks : nch_hidden;
@@ -139,11 +154,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                     for (int ch = 0; ch < nch; ++ch) {
                         const int n0 = last ? ch * DPC * P : ch * p.CW;
                         for (int kb = 0; kb < KB; ++kb) {
+                            // the slot is written in BOTH CTAs: wait until both MMA issuers released it
                             mbar_wait(&w_empty[ws], wph ^ 1);
-                            uint8_t* st = sW + (size_t)ws * F_KBLOCK;
+                            // this CTA fetches rows [64 rank, 64 rank + 64) of the 128-row W tile and
+                            // multicasts them to the pair; the peer delivers the other half
+                            uint8_t* st = sW + (size_t)ws * F_KBLOCK + rank * (F_PLANE / 2);
                             mbar_arrive_expect_tx(&w_full[ws], bytes);
-                            tma_load_3d(st, &p.mapW[l], &w_full[ws], kb * FK, n0, 0);
-                            if (p.n_terms == 3) tma_load_3d(st + F_PLANE, &p.mapW[l], &w_full[ws], kb * FK, n0, 1);
+                            tma_load_3d_mc(st, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 0, (uint16_t)3);
+                            if (p.n_terms == 3)
+                                tma_load_3d_mc(st + F_PLANE, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 1, (uint16_t)3);
                             if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -155,7 +174,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
         if (lane == 0) {
             int ws = 0;
             uint32_t wph = 0, chunk = 0, a_par = 0;  // a_par: bit kb = parity of a_ready[kb]
-            for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            for (int mma_tile = 0; mma_tile < n_iter; ++mma_tile) {
+                const bool stamp_on = (mma_tile == 2);
                 for (int l = 0; l < L; ++l) {
                     const bool last = (l == L - 1);
                     const int nch = last ? p.n_last_chunks : nch_hidden;
@@ -170,8 +190,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                             if (ch == 0) {  // first use of this K block in this layer
                                 mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
                                 a_par ^= (1u << kb);
+                                if (kb == 0) ZK_STAMP(8 * l + 0);
+                                if (kb == KB - 1) ZK_STAMP(8 * l + 1);
                             }
                             mbar_wait(&w_full[ws], wph);
+                            if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
                             tc_fence_after();
                             const uint32_t a_hi = smem_u32(sA + (size_t)kb * F_KBLOCK), a_lo = a_hi + F_PLANE;
                             const uint32_t w_hi = smem_u32(sW + (size_t)ws * F_KBLOCK), w_lo = w_hi + F_PLANE;
@@ -185,13 +208,36 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                                     umma_bf16(d_tmem, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(w_hi + off), idesc, 1u);
                                 }
                             }
-                            umma_commit(&w_empty[ws]);
+                            umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
                             if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
                         }
                         umma_commit(&d_full[buf]);
-                        if (ch == nch - 1) umma_commit(layer_done);
+                        if (ch == nch - 1) {
+                            umma_commit(layer_done);
+                            ZK_STAMP(8 * l + 3);
+                        }
                     }
                 }
+            }
+        }
+    } else if (warp == 3) {
+        // ======================= input prefetcher =======================
+        // pulls the NEXT tile's x / c rows into L2 while the current tile computes
+        for (int it = 0; it + 1 < n_iter; ++it) {
+            const int tn = 2 * (cid + (it + 1) * ncl) + (int)rank;
+            if (tn >= m_tiles) break;
+            while (*s_tile < it + 1) __nanosleep(500);  // stay exactly one tile ahead of the epilogue
+            const int64_t r0 = (int64_t)tn * FM;
+            const int rows = (int)min((int64_t)FM, (int64_t)p.M - r0);
+            if (p.ldx == p.D) {
+                const char* base = (const char*)(p.x + r0 * p.ldx);
+                for (int off = lane * 128; off < rows * p.D * 4; off += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+            if (p.C > 0 && p.ldc == p.C) {
+                const char* base = (const char*)(p.c + r0 * p.ldc);
+                for (int off = lane * 128; off < rows * p.C * 4; off += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
             }
         }
     } else if (warp >= F_EPI_WARP0) {
@@ -200,38 +246,39 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
         const int q = warp & 3;                   // TMEM lane quadrant
         const int r = q * 32 + lane;              // row inside the tile
         uint32_t chunk = 0, ld_par = 0;
-        int tile_iter = 0;
-        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_iter) {
+        for (int tile_iter = 0; tile_iter < n_iter; ++tile_iter) {
+            const int t = 2 * (cid + tile_iter * ncl) + (int)rank;  // may be >= m_tiles: dummy tile, all rows masked
+            const bool stamp_on = (tile_iter == 2) && (threadIdx.x == F_EPI_WARP0 * 32);
+            ZK_STAMP(48);
+            if (threadIdx.x == F_EPI_WARP0 * 32) *s_tile = tile_iter + 1;
             const int64_t row = (int64_t)t * FM + r;
             const bool row_ok = row < p.M;
             // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo, K block kb by set (kb & 1) ----
             for (int kb = s; kb < p.KB0; kb += 2) {
                 uint8_t* hi = sA + (size_t)kb * F_KBLOCK;
                 uint8_t* lo = hi + F_PLANE;
+                // issue every load of the K block before the first conversion / store so that
+                // their latencies overlap (the rows were prefetched into L2 by warp 3)
+                float vals[FK];
+#pragma unroll
+                for (int j = 0; j < FK; ++j) {
+                    const int k = kb * FK + j;
+                    float val = 0.f;
+                    if (row_ok && k < p.K0) val = (k < p.D) ? __ldg(p.x + row * p.ldx + k) : __ldg(p.c + row * p.ldc + (k - p.D));
+                    vals[j] = val;
+                }
 #pragma unroll
                 for (int cidx = 0; cidx < 8; ++cidx) {
                     uint32_t ph[4], pl[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int k = kb * FK + cidx * 8 + j * 2 + u;
-                            float val = 0.f;
-                            if (row_ok) {
-                                if (k < p.D) val = p.x[row * p.ldx + k];
-                                else if (k < p.K0) val = p.c[row * p.ldc + (k - p.D)];
-                            }
-                            v[u] = val;
-                        }
-                        split2_bf16(v[0], v[1], ph[j], pl[j]);
-                    }
+                    for (int j = 0; j < 4; ++j) split2_bf16(vals[cidx * 8 + 2 * j], vals[cidx * 8 + 2 * j + 1], ph[j], pl[j]);
                     st_swizzled(hi, r, cidx, ph[0], ph[1], ph[2], ph[3]);
                     st_swizzled(lo, r, cidx, pl[0], pl[1], pl[2], pl[3]);
                 }
             }
             fence_proxy_async();
             for (int kb = 0; kb < p.KB0; ++kb) mbar_arrive(&a_ready[kb]);
+            ZK_STAMP(49);
 
             // ---- hidden layers: D -> bias, ReLU -> hi/lo -> next A operand (shared memory) ----
             for (int l = 0; l < L - 1; ++l) {
@@ -240,6 +287,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                     const uint32_t buf = chunk & 1u;
                     mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                     tc_fence_after();
+                    ZK_STAMP(64 + 16 * l + 4 * ch + 0);
                     const int ncols = p.CW >> 1;             // columns handled by this thread: 64 or 32
                     const int col0 = s * ncols;              // first column inside the chunk
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)col0;
@@ -270,10 +318,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                                         ph[17 + (j >> 1)], pl[17 + (j >> 1)]);
                         }
                     }
+                    ZK_STAMP(64 + 16 * l + 4 * ch + 1);
                     if (ch == 0) {  // the A operand may be overwritten once ALL MMAs of this layer are done
                         mbar_wait(layer_done, ld_par);
                         ld_par ^= 1u;
                     }
+                    ZK_STAMP(64 + 16 * l + 4 * ch + 2);
                     if (ncols == 64) {  // CW = 128: this set owns K block 2 ch + s entirely
                         const int kb = ch * 2 + s;
                         uint8_t* hi = sA + (size_t)kb * F_KBLOCK;
@@ -286,6 +336,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                         fence_proxy_async();
                         mbar_arrive(&a_ready[ch * 2]);
                         mbar_arrive(&a_ready[ch * 2 + 1]);
+                        ZK_STAMP(64 + 16 * l + 4 * ch + 3);
                     } else {  // CW = 64: the two sets share K block ch (32 columns = 4 chunks each)
                         uint8_t* hi = sA + (size_t)ch * F_KBLOCK;
                         uint8_t* lo = hi + F_PLANE;
@@ -307,6 +358,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                 const uint32_t buf = chunk & 1u;
                 mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                 tc_fence_after();
+                if (ch < 8) ZK_STAMP(160 + 2 * ch);
                 const int base = s ? BASE_B : 0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)base;
                 uint32_t ra[32], rb[32];
@@ -358,6 +410,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
 #pragma unroll
                     for (int j = DIMS_A; j < DPC; ++j) do_dim(&v[j * P - BASE_B], j);
                 }
+                if (ch < 8) ZK_STAMP(161 + 2 * ch);
             }
             // all MMAs of this tile are complete once the last layer_done fires: A may be restaged
             mbar_wait(layer_done, ld_par);
@@ -371,11 +424,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_
                 if (p.log_prob) p.log_prob[row] = tot;
                 else if (p.ladj) p.ladj[row] = tot;
             }
+            ZK_STAMP(50);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
@@ -394,6 +449,8 @@ zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, cudaStream_t
 }
 
 }  // namespace
+
+long long* g_timeline = nullptr;
 
 bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
@@ -415,7 +472,7 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     if (a.B == 0) return ZK_OK;
     FusedParams p;
     for (int i = 0; i < m->n_linear; ++i) {
-        p.mapW[i] = pk->layers[i].mapW128;
+        p.mapW[i] = pk->layers[i].mapW64;
         p.bias[i] = m->b[i];
     }
     p.n_linear = m->n_linear;
@@ -433,7 +490,10 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     const float absL = fabsf(logf(a.slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
-    const int grid = (int)std::min<int64_t>(ceil_div(a.B, FM), sm_count());
+    p.dbg = g_timeline;
+    // clusters of 2 CTAs: even grid, at most one CTA per SM
+    const int64_t pairs = ceil_div(ceil_div(a.B, FM), 2);
+    const int grid = 2 * (int)std::min<int64_t>(pairs, sm_count() / 2);
     if (a.univariate == ZK_UNI_RQS && a.bins == 8) {
         p.n_last_chunks = (a.D + 3) / 4;
         return launch_fused_t<ZK_UNI_RQS, 8>(p, a.fast_math, grid, st);

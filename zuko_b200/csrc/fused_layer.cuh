@@ -23,6 +23,7 @@ struct FusedLayerArgs {
 
 // true when the autoregressive layer (conditioner `m`, univariate, D, C) can run as ONE kernel
 bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C);
+extern long long* g_timeline;  // device buffer of >= 256 stamps, or null (zk_debug_timeline)
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
 
 }  // namespace zk

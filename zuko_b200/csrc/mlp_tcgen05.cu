@@ -360,6 +360,7 @@ zk_status tc_pack(zk_mlp* m, int requested_mode) {
         ZK_TRY(check_launch("split_weight_kernel"));
         ZK_TRY(make_plane_map(&pk->layers.back().mapW, L.w, L.N, L.Kp, BN));
         ZK_TRY(make_plane_map(&pk->layers.back().mapW128, L.w, L.N, L.Kp, 128));
+        ZK_TRY(make_plane_map(&pk->layers.back().mapW64, L.w, L.N, L.Kp, 64));
         if (i < m->n_linear - 1) pk->max_np = std::max(pk->max_np, pad64(L.N));
     }
     ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
