@@ -1,27 +1,41 @@
 // zuko_b200 — ONE kernel per flow layer: conditioner (all linear layers) + bijector + ladj.
 //
-//   x, c  --(bf16 hi/lo split, in-kernel)-->  A operand in shared memory
-//   for every linear layer:  tcgen05.mma (A: smem, W: TMA-streamed from L2, D: TMEM)
-//        hidden layers : epilogue (TMEM -> bias, ReLU -> hi/lo split) writes the next A operand
-//                        straight back into shared memory in the canonical 128B-swizzled
-//                        K-major layout — activations never touch HBM
-//        last layer    : epilogue thread = sample row reads its D*P raw parameters from TMEM
-//                        (tcgen05.ld 32x32b) and evaluates the spline / affine bijector, the
-//                        log-derivative and the per-sample sum in registers — phi never
-//                        touches HBM either ("lane = sample row")
-//   HBM traffic per sample per layer: 4 (D + C) read + 4 (D + 1) written  (cfg2: 164 B instead of
-//   the 9.3 kB of the unfused path) — the kernel is bound by the tensor pipe / L2 weight stream.
+//   x, c  --(bf16 hi/lo split, in-kernel)-->  A operand in TENSOR MEMORY
+//   for every linear layer:  tcgen05.mma  D[tmem] (+)= A[tmem] * W[smem]^T
+//        W tiles are streamed from L2 by TMA, each CTA of a pair fetching half a tile and
+//        multicasting it to both (cluster of 2);
+//        hidden layers : epilogue (tcgen05.ld -> bias, ReLU -> bf16 hi/lo split) writes the next
+//                        A operand straight back into tensor memory (tcgen05.st) — activations
+//                        never touch shared memory or HBM, and the MMA reads only W from smem
+//                        (with A in smem the 128-wide MMAs were shared-memory-bandwidth bound:
+//                        ~108 cycles per MMA instead of 64, profiles/r01_fused_timeline_v1.txt);
+//        last layer    : epilogue thread = sample row reads its D*P raw parameters from TMEM and
+//                        evaluates the spline / affine bijector, the log-derivative and the
+//                        per-sample sum in registers — phi never touches HBM either
+//                        ("lane = sample row").
+//   HBM traffic per sample per layer: 4 (D + C) read + 4 (D + 1) written (cfg2: 164 B instead of
+//   the 9.3 kB of the unfused path).
 //
 // Restates for one MaskedAutoregressiveTransform layer:  flows/autoregressive.py:207-215 (meta),
 // nn.py:217-218 (masked linears, mask folded into W at pack time), transforms.py:469-490,
 // 554-567 (RQS) or 426-446 (affine), transforms.py:210-214 (sum over D), and on the last
 // layer of a flow distributions.py:115-119 + torch normal.py:87-102 (DiagNormal log-prob).
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over 128-row tiles):
-//   warp 0      W producer   (TMA, 3-stage ring of 128 x 64 bf16 hi/lo tiles)
+// Tensor memory (512 columns x 128 lanes, lane = sample row of the tile):
+//   [  0,128)  A hi : bf16 pairs, K element k in column k/2 (low half = even k)   (K <= 256)
+//   [128,256)  A lo
+//   [256,384)  D buffer 0 (fp32 accumulators of one <=128-column chunk)
+//   [384,512)  D buffer 1
+//
+// Warp roles (640 threads, 1 CTA / SM, persistent over 128-row tiles, CTA pairs):
+//   warp 0      W producer   (TMA multicast, 4-stage ring of 128 x 64 bf16 hi/lo tiles)
 //   warp 1      MMA issuer   (one lane; M128 x N<=128 x K16, 3 MMAs per k-step: hh, hl, lh)
-//   warp 2      TMEM allocator (256 columns = 2 accumulator buffers of 128)
-//   warps 4-11  epilogue: two warp sets, set s handles half of the columns / dims of a chunk
+//   warp 2      TMEM allocator
+//   warp 3      input producer (1-D TMA bulk copies of the next tile's x / c rows into smem)
+//   warps 4-19  epilogue: four warp sets; hidden layers: set s owns 32 columns of a chunk;
+//               last layer: set pair (chunk parity) owns the chunk, its two sets split the dims
+
+#include <utility>
 
 #include "bijector_math.cuh"
 #include "fused_layer.cuh"
@@ -35,20 +49,29 @@ using namespace bij;
 
 constexpr int FM = 128;             // rows per tile
 constexpr int FK = 64;              // bf16 per K block (128-byte swizzle row)
-constexpr int F_WSTAGES = 3;
+constexpr int F_WSTAGES = 4;
 constexpr int F_MAXKB = 4;          // A operand: up to 4 K blocks = 256 columns
-constexpr int F_THREADS = 384;
 constexpr int F_EPI_WARP0 = 4;
-constexpr uint32_t F_PLANE = FM * FK * 2;       // 16 KB: one plane of one K block
+constexpr int F_EPI_WARPS = 16;
+constexpr int F_EPI_THREADS = F_EPI_WARPS * 32;  // 512
+constexpr int F_THREADS = (F_EPI_WARP0 + F_EPI_WARPS) * 32;  // 640
+constexpr int F_IN_MAXF = 64;       // floats per row of the staged input (D + C), TMA staging path
+constexpr int F_BIAS_MAXF = 5120;   // floats of bias kept in shared memory (else read from global)
+constexpr uint32_t F_PLANE = FM * FK * 2;       // 16 KB: one plane of one W tile
 constexpr uint32_t F_KBLOCK = 2 * F_PLANE;      // hi + lo
-constexpr uint32_t F_A_BYTES = F_MAXKB * F_KBLOCK;          // 128 KB
-constexpr uint32_t F_W_BYTES = F_WSTAGES * F_KBLOCK;        // 96 KB
-constexpr uint32_t F_AUX_BYTES = 2048;                      // barriers + ladj scratch
-constexpr size_t F_SMEM = (size_t)F_A_BYTES + F_W_BYTES + F_AUX_BYTES + 1024 /*alignment slack*/;
+constexpr uint32_t F_W_BYTES = F_WSTAGES * F_KBLOCK;        // 128 KB
+constexpr uint32_t F_IN_BYTES = FM * F_IN_MAXF * 4;         // 32 KB per input buffer
+constexpr uint32_t F_AUX_BYTES = 4096;                      // barriers + ladj scratch
+constexpr uint32_t F_BIAS_BYTES = F_BIAS_MAXF * 4;          // 20 KB
+constexpr size_t F_SMEM = (size_t)F_W_BYTES + 2 * F_IN_BYTES + F_AUX_BYTES + F_BIAS_BYTES + 1024 /*alignment slack*/;
+constexpr uint32_t TM_ALO = 128, TM_D = 256;    // tensor-memory column map (see header)
 
 struct FusedParams {
     CUtensorMap mapW[ZK_FUSED_MAX_LINEAR];
     const float* bias[ZK_FUSED_MAX_LINEAR];
+    int bias_off[ZK_FUSED_MAX_LINEAR];  // offset of layer l's bias in the shared-memory copy
+    int bias_len[ZK_FUSED_MAX_LINEAR];
+    int bias_in_smem;
     int n_linear;
     int K0, KB0;        // real input width (D + C) and its number of 64-wide K blocks
     int H, CW;          // hidden width (multiple of 64, <= 256), hidden chunk width (128 or 64)
@@ -56,6 +79,7 @@ struct FusedParams {
     int n_last_chunks;  // ceil(D / DPC)
     int n_terms;        // 3 (split bf16) or 1
     int M;
+    int in_tma;         // 1: x / c rows are staged through shared memory by 1-D TMA bulk copies
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
     float* y; int64_t ldy;
@@ -65,20 +89,57 @@ struct FusedParams {
     long long* dbg;  // optional timeline buffer (clock64 stamps of CTA 0, third tile), see zk_debug_timeline
 };
 
-// 16 bytes into the canonical K-major SWIZZLE_128B tile: row r, 16-byte chunk c (8 bf16)
-__device__ __forceinline__ void st_swizzled(uint8_t* tile, int r, int c, uint32_t a, uint32_t b, uint32_t cc, uint32_t d) {
-    const uint32_t addr = smem_u32(tile) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(cc), "r"(d) : "memory");
-}
-
-#define ZK_STAMP(slot)                                                        \
-    do {                                                                      \
+#define ZK_STAMP(slot)                                                                  \
+    do {                                                                                \
         if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on) p.dbg[(slot)] = clock64(); \
     } while (0)
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// per-(UNI, K) chunking of the last layer: DPC dims per 128-column accumulator chunk
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// compile-time loop: f(integral_constant<int, Start>), ..., f(integral_constant<int, Start + N - 1>)
+template <int Start, class F, int... I>
+__device__ __forceinline__ void for_range_impl(F& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, Start + I>{}), ...);
+}
+template <int Start, int N, class F>
+__device__ __forceinline__ void for_range(F& f) {
+    for_range_impl<Start>(f, std::make_integer_sequence<int, N>{});
+}
+
+// per-(UNI, K) chunking of the last layer: DPC dims per accumulator chunk, split between the two
+// sets of the owning pair as [0, DA) and [DA, DPC)
 template <int UNI, int KT>
 struct LastCfg;
 template <>
@@ -89,28 +150,30 @@ template <>
 struct LastCfg<ZK_UNI_AFFINE, 0> { static constexpr int P = 2, DPC = 64; };
 
 template <int UNI, int KT, bool FAST>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_layer_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
     constexpr int P = Cfg::P, DPC = Cfg::DPC;
-    constexpr int N_LAST = (DPC * P + 15) & ~15;       // MMA N of a last-layer chunk
-    constexpr int DIMS_A = (DPC + 1) / 2;              // dims of a chunk handled by warp set 0
-    constexpr int BASE_B = (DIMS_A * P) & ~31;         // first TMEM column loaded by warp set 1
-    static_assert(DIMS_A * P <= 64 && DPC * P - BASE_B <= 64 && N_LAST <= 128, "chunk windows must fit 64 columns");
+    constexpr int N_LAST = (DPC * P + 15) & ~15;  // MMA N of a last-layer chunk
+    constexpr int DA = (DPC + 1) / 2;             // dims of a chunk handled by the first set of the pair
+    static_assert(N_LAST <= 128, "a last-layer chunk must fit one accumulator buffer");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sW = smem + F_A_BYTES;
-    uint64_t* bars = (uint64_t*)(smem + F_A_BYTES + F_W_BYTES);
-    uint64_t* w_full = bars;                  // [3]
-    uint64_t* w_empty = bars + 3;             // [3]
-    uint64_t* d_full = bars + 6;              // [2]
-    uint64_t* d_empty = bars + 8;             // [2]
-    uint64_t* a_ready = bars + 10;            // [4]  K block kb of the A operand written
-    uint64_t* layer_done = bars + 14;         // [1]  all MMAs issued so far have completed
-    uint32_t* tmem_slot = (uint32_t*)(bars + 15);
-    float* s_part = (float*)(bars + 16);      // [2][128] ladj partials of warp set 1
-    volatile int* s_tile = (volatile int*)(s_part + 2 * FM);  // tiles started by the epilogue (paces the prefetcher)
+    uint8_t* sW = smem;
+    float* s_in = (float*)(smem + F_W_BYTES);  // [2][FM * F_IN_MAXF]
+    uint64_t* bars = (uint64_t*)(smem + F_W_BYTES + 2 * F_IN_BYTES);
+    uint64_t* w_full = bars;                  // [4]
+    uint64_t* w_empty = bars + 4;             // [4]
+    uint64_t* d_full = bars + 8;              // [2]
+    uint64_t* d_empty = bars + 10;            // [2]
+    uint64_t* a_ready = bars + 12;            // [4]  K block kb of the A operand written
+    uint64_t* layer_done = bars + 16;         // [1]  all MMAs issued so far have completed
+    uint64_t* in_full = bars + 17;            // [2]  input rows of a tile landed in s_in[b]
+    uint64_t* in_empty = bars + 19;           // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 21);
+    float* s_part = (float*)(bars + 24);      // [2][3][128] ladj partials of sets 1..3
+    float* s_bias = (float*)(smem + F_W_BYTES + 2 * F_IN_BYTES + F_AUX_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -121,19 +184,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
     // multicast); a CTA whose tile index falls off the end processes an all-masked dummy tile.
     const uint32_t rank = cluster_ctarank();
     const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-    const int n_iter = ((m_tiles + 1) / 2 - cid + ncl - 1) / ncl;  // iterations of this pair (>= 0)
+    const int n_iter = ((m_tiles + 1) / 2 - cid + ncl - 1) / ncl;
     const int KBH = p.H / FK;
     const int nch_hidden = p.H / p.CW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs of the pair
-        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], 256); }
-        for (int k = 0; k < F_MAXKB; ++k) mbar_init(&a_ready[k], 256);
+        for (int s = 0; s < F_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], F_EPI_THREADS);
+            mbar_init(&in_full[b], 1);
+            mbar_init(&in_empty[b], F_EPI_THREADS);
+        }
+        for (int k = 0; k < F_MAXKB; ++k) mbar_init(&a_ready[k], F_EPI_THREADS);
         mbar_init(layer_done, 1);
-        *s_tile = 0;
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    if (p.bias_in_smem)
+        for (int l = 0; l < L; ++l)
+            for (int i = threadIdx.x; i < p.bias_len[l]; i += F_THREADS) s_bias[p.bias_off[l] + i] = p.bias[l][i];
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive
@@ -185,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
                         const uint32_t buf = chunk & 1u;
                         mbar_wait(&d_empty[buf], ((chunk >> 1) & 1u) ^ 1u);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + buf * 128u;
+                        const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
                         for (int kb = 0; kb < KB; ++kb) {
                             if (ch == 0) {  // first use of this K block in this layer
                                 mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
@@ -194,18 +264,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
                                 if (kb == KB - 1) ZK_STAMP(8 * l + 1);
                             }
                             mbar_wait(&w_full[ws], wph);
-                            if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
                             tc_fence_after();
-                            const uint32_t a_hi = smem_u32(sA + (size_t)kb * F_KBLOCK), a_lo = a_hi + F_PLANE;
+                            if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
+                            const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
                             const uint32_t w_hi = smem_u32(sW + (size_t)ws * F_KBLOCK), w_lo = w_hi + F_PLANE;
 #pragma unroll
                             for (int k = 0; k < FK / 16; ++k) {
-                                const uint32_t off = (uint32_t)k * 32u;
-                                umma_bf16(d_tmem, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(w_hi + off), idesc,
-                                          (kb > 0 || k > 0) ? 1u : 0u);
+                                const uint32_t acol = (uint32_t)k * 8u;   // 16 bf16 = 8 TMEM columns
+                                const uint32_t boff = (uint32_t)k * 32u;  // 32 bytes along K in the swizzle row
+                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_k_sw128(w_hi + boff), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                                 if (p.n_terms == 3) {
-                                    umma_bf16(d_tmem, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(w_lo + off), idesc, 1u);
-                                    umma_bf16(d_tmem, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(w_hi + off), idesc, 1u);
+                                    umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_k_sw128(w_lo + boff), idesc, 1u);
+                                    umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_k_sw128(w_hi + boff), idesc, 1u);
                                 }
                             }
                             umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
@@ -221,179 +291,140 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
             }
         }
     } else if (warp == 3) {
-        // ======================= input prefetcher =======================
-        // pulls the NEXT tile's x / c rows into L2 while the current tile computes
-        for (int it = 0; it + 1 < n_iter; ++it) {
-            const int tn = 2 * (cid + (it + 1) * ncl) + (int)rank;
-            if (tn >= m_tiles) break;
-            while (*s_tile < it + 1) __nanosleep(500);  // stay exactly one tile ahead of the epilogue
-            const int64_t r0 = (int64_t)tn * FM;
-            const int rows = (int)min((int64_t)FM, (int64_t)p.M - r0);
-            if (p.ldx == p.D) {
-                const char* base = (const char*)(p.x + r0 * p.ldx);
-                for (int off = lane * 128; off < rows * p.D * 4; off += 32 * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-            }
-            if (p.C > 0 && p.ldc == p.C) {
-                const char* base = (const char*)(p.c + r0 * p.ldc);
-                for (int off = lane * 128; off < rows * p.C * 4; off += 32 * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        // ======================= input producer =======================
+        if (lane == 0 && p.in_tma) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int b = it & 1;
+                mbar_wait(&in_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+                const int t = 2 * (cid + it * ncl) + (int)rank;
+                const int64_t r0 = (int64_t)t * FM;
+                const int rows = (int)max((int64_t)0, min((int64_t)FM, (int64_t)p.M - r0));
+                float* dst = s_in + (size_t)b * (FM * F_IN_MAXF);
+                const uint32_t bx = (uint32_t)rows * p.D * 4u;
+                const uint32_t bc = (p.C == 0) ? 0u : ((p.ldc == 0) ? (uint32_t)p.C * 4u : (uint32_t)rows * p.C * 4u);
+                if (rows == 0) {
+                    mbar_arrive(&in_full[b]);  // dummy tile: nothing to copy
+                } else {
+                    mbar_arrive_expect_tx(&in_full[b], bx + bc);
+                    bulk_g2s(dst, p.x + r0 * p.ldx, bx, &in_full[b]);
+                    if (bc) bulk_g2s(dst + FM * p.D, (p.ldc == 0) ? p.c : p.c + r0 * p.ldc, bc, &in_full[b]);
+                }
             }
         }
     } else if (warp >= F_EPI_WARP0) {
         // ======================= epilogue =======================
-        const int s = (warp - F_EPI_WARP0) >> 2;  // warp set 0 / 1
+        const int s = (warp - F_EPI_WARP0) >> 2;  // warp set 0..3
         const int q = warp & 3;                   // TMEM lane quadrant
         const int r = q * 32 + lane;              // row inside the tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t chunk = 0, ld_par = 0;
         for (int tile_iter = 0; tile_iter < n_iter; ++tile_iter) {
             const int t = 2 * (cid + tile_iter * ncl) + (int)rank;  // may be >= m_tiles: dummy tile, all rows masked
             const bool stamp_on = (tile_iter == 2) && (threadIdx.x == F_EPI_WARP0 * 32);
             ZK_STAMP(48);
-            if (threadIdx.x == F_EPI_WARP0 * 32) *s_tile = tile_iter + 1;
             const int64_t row = (int64_t)t * FM + r;
             const bool row_ok = row < p.M;
-            // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo, K block kb by set (kb & 1) ----
-            for (int kb = s; kb < p.KB0; kb += 2) {
-                uint8_t* hi = sA + (size_t)kb * F_KBLOCK;
-                uint8_t* lo = hi + F_PLANE;
-                // issue every load of the K block before the first conversion / store so that
-                // their latencies overlap (the rows were prefetched into L2 by warp 3)
-                float vals[FK];
+            const int ib = tile_iter & 1;
+            const float* sx = s_in + (size_t)ib * (FM * F_IN_MAXF);
+            const float* sc = sx + FM * p.D;
+            if (p.in_tma) mbar_wait(&in_full[ib], ((uint32_t)tile_iter >> 1) & 1u);
+            // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo pairs in TMEM; set s takes
+            //      K block kb = s, s + 4, ... (one K block = 64 inputs = 32 TMEM columns) ----
+            for (int kb = s; kb < p.KB0; kb += 4) {
+                uint32_t ph[32], pl[32];
 #pragma unroll
-                for (int j = 0; j < FK; ++j) {
-                    const int k = kb * FK + j;
-                    float val = 0.f;
-                    if (row_ok && k < p.K0) val = (k < p.D) ? __ldg(p.x + row * p.ldx + k) : __ldg(p.c + row * p.ldc + (k - p.D));
-                    vals[j] = val;
+                for (int j = 0; j < 32; ++j) {
+                    float v[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int k = kb * FK + 2 * j + u;
+                        float val = 0.f;
+                        if (row_ok && k < p.K0) {
+                            if (p.in_tma) val = (k < p.D) ? sx[r * p.D + k] : sc[(p.ldc == 0 ? 0 : r * p.C) + (k - p.D)];
+                            else val = (k < p.D) ? __ldg(p.x + row * p.ldx + k) : __ldg(p.c + row * p.ldc + (k - p.D));
+                        }
+                        v[u] = val;
+                    }
+                    split2_bf16(v[0], v[1], ph[j], pl[j]);
                 }
-#pragma unroll
-                for (int cidx = 0; cidx < 8; ++cidx) {
-                    uint32_t ph[4], pl[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) split2_bf16(vals[cidx * 8 + 2 * j], vals[cidx * 8 + 2 * j + 1], ph[j], pl[j]);
-                    st_swizzled(hi, r, cidx, ph[0], ph[1], ph[2], ph[3]);
-                    st_swizzled(lo, r, cidx, pl[0], pl[1], pl[2], pl[3]);
-                }
+                const uint32_t ta = t_lane + (uint32_t)(kb * 32);
+                tmem_st_x16(ta, ph);
+                tmem_st_x16(ta + 16u, ph + 16);
+                tmem_st_x16(ta + TM_ALO, pl);
+                tmem_st_x16(ta + TM_ALO + 16u, pl + 16);
             }
-            fence_proxy_async();
+            tmem_st_wait();
+            tc_fence_before();
             for (int kb = 0; kb < p.KB0; ++kb) mbar_arrive(&a_ready[kb]);
             ZK_STAMP(49);
 
-            // ---- hidden layers: D -> bias, ReLU -> hi/lo -> next A operand (shared memory) ----
+            // ---- hidden layers: D -> bias, ReLU -> hi/lo -> next A operand (tensor memory) ----
             for (int l = 0; l < L - 1; ++l) {
-                const float* bias = p.bias[l];
+                const float* bias = p.bias_in_smem ? s_bias + p.bias_off[l] : p.bias[l];
                 for (int ch = 0; ch < nch_hidden; ++ch, ++chunk) {
                     const uint32_t buf = chunk & 1u;
                     mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                     tc_fence_after();
                     ZK_STAMP(64 + 16 * l + 4 * ch + 0);
-                    const int ncols = p.CW >> 1;             // columns handled by this thread: 64 or 32
-                    const int col0 = s * ncols;              // first column inside the chunk
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)col0;
-                    uint32_t ra[32], rb[32];
-                    tmem_ld_32x32b_x32(taddr, ra);
-                    if (ncols == 64) tmem_ld_32x32b_x32(taddr + 32u, rb);
-                    tmem_ld_wait();
+                    const int col0 = s * 32;              // this set's 32 columns of the chunk
+                    const bool owner = col0 < p.CW;       // CW = 64: sets 2, 3 have no columns
+                    uint32_t ra[32];
+                    if (owner) {
+                        tmem_ld_32x32b_x32(t_lane + TM_D + buf * 128u + (uint32_t)col0, ra);
+                        tmem_ld_wait();
+                    }
                     tc_fence_before();
                     mbar_arrive(&d_empty[buf]);  // accumulator buffer is free again
-                    uint32_t ph[32], pl[32];
-                    const int nbase = ch * p.CW + col0;
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + nbase);  // 128-byte aligned
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(b4 + (j >> 2));  // one broadcast 16-byte load per 4 columns
-                        split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
-                                    ph[j >> 1], pl[j >> 1]);
-                        split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
-                                    ph[(j >> 1) + 1], pl[(j >> 1) + 1]);
-                    }
-                    if (ncols == 64) {
+                    uint32_t ph[16], pl[16];
+                    const int nbase = ch * p.CW + col0;   // first output column = K index of the next layer
+                    if (owner) {
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + nbase);  // 128-byte aligned
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 bb = __ldg(b4 + 8 + (j >> 2));
-                            split2_bf16(fmaxf(__uint_as_float(rb[j]) + bb.x, 0.f), fmaxf(__uint_as_float(rb[j + 1]) + bb.y, 0.f),
-                                        ph[16 + (j >> 1)], pl[16 + (j >> 1)]);
-                            split2_bf16(fmaxf(__uint_as_float(rb[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(rb[j + 3]) + bb.w, 0.f),
-                                        ph[17 + (j >> 1)], pl[17 + (j >> 1)]);
+                            const float4 bb = b4[j >> 2];  // one broadcast 16-byte load per 4 columns
+                            split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
+                                        ph[j >> 1], pl[j >> 1]);
+                            split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
+                                        ph[(j >> 1) + 1], pl[(j >> 1) + 1]);
                         }
                     }
                     ZK_STAMP(64 + 16 * l + 4 * ch + 1);
                     if (ch == 0) {  // the A operand may be overwritten once ALL MMAs of this layer are done
                         mbar_wait(layer_done, ld_par);
                         ld_par ^= 1u;
+                        tc_fence_after();
                     }
                     ZK_STAMP(64 + 16 * l + 4 * ch + 2);
-                    if (ncols == 64) {  // CW = 128: this set owns K block 2 ch + s entirely
-                        const int kb = ch * 2 + s;
-                        uint8_t* hi = sA + (size_t)kb * F_KBLOCK;
-                        uint8_t* lo = hi + F_PLANE;
-#pragma unroll
-                        for (int cidx = 0; cidx < 8; ++cidx) {
-                            st_swizzled(hi, r, cidx, ph[cidx * 4], ph[cidx * 4 + 1], ph[cidx * 4 + 2], ph[cidx * 4 + 3]);
-                            st_swizzled(lo, r, cidx, pl[cidx * 4], pl[cidx * 4 + 1], pl[cidx * 4 + 2], pl[cidx * 4 + 3]);
-                        }
-                        fence_proxy_async();
+                    if (owner) {
+                        const uint32_t ta = t_lane + (uint32_t)(nbase >> 1);  // K element k lives in column k / 2
+                        tmem_st_x16(ta, ph);
+                        tmem_st_x16(ta + TM_ALO, pl);
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    if (p.CW == 128) {
                         mbar_arrive(&a_ready[ch * 2]);
                         mbar_arrive(&a_ready[ch * 2 + 1]);
-                        ZK_STAMP(64 + 16 * l + 4 * ch + 3);
-                    } else {  // CW = 64: the two sets share K block ch (32 columns = 4 chunks each)
-                        uint8_t* hi = sA + (size_t)ch * F_KBLOCK;
-                        uint8_t* lo = hi + F_PLANE;
-#pragma unroll
-                        for (int cidx = 0; cidx < 4; ++cidx) {
-                            st_swizzled(hi, r, s * 4 + cidx, ph[cidx * 4], ph[cidx * 4 + 1], ph[cidx * 4 + 2], ph[cidx * 4 + 3]);
-                            st_swizzled(lo, r, s * 4 + cidx, pl[cidx * 4], pl[cidx * 4 + 1], pl[cidx * 4 + 2], pl[cidx * 4 + 3]);
-                        }
-                        fence_proxy_async();
+                    } else {
                         mbar_arrive(&a_ready[ch]);
                     }
+                    ZK_STAMP(64 + 16 * l + 4 * ch + 3);
                 }
             }
 
             // ---- last layer: raw parameters stay in TMEM -> bijector + ladj in registers ----
             float lsum = 0.f;
-            const float* bias = p.bias[L - 1];
+            const float* bias = p.bias_in_smem ? s_bias + p.bias_off[L - 1] : p.bias[L - 1];
+            const int n_total = p.D * P;
             for (int ch = 0; ch < p.n_last_chunks; ++ch, ++chunk) {
                 const uint32_t buf = chunk & 1u;
                 mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                 tc_fence_after();
                 if (ch < 8) ZK_STAMP(160 + 2 * ch);
-                const int base = s ? BASE_B : 0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)base;
-                uint32_t ra[32], rb[32];
-                tmem_ld_32x32b_x32(taddr, ra);
-                tmem_ld_32x32b_x32(taddr + 32u, rb);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&d_empty[buf]);
-                float v[64];
-                const int nbase = ch * DPC * P + base;  // global output column of v[0]
-                const int n_total = p.D * P;
-                const float2* b2 = reinterpret_cast<const float2*>(bias + nbase);  // nbase is even
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    // float2 pairs are entirely inside or outside [0, n_total): both bounds are even
-                    const float2 ba = (nbase + j < n_total) ? __ldg(b2 + (j >> 1)) : make_float2(0.f, 0.f);
-                    const float2 bb = (nbase + 32 + j < n_total) ? __ldg(b2 + 16 + (j >> 1)) : make_float2(0.f, 0.f);
-                    v[j] = __uint_as_float(ra[j]) + ba.x;
-                    v[j + 1] = __uint_as_float(ra[j + 1]) + ba.y;
-                    v[32 + j] = __uint_as_float(rb[j]) + bb.x;
-                    v[33 + j] = __uint_as_float(rb[j + 1]) + bb.y;
-                }
-                auto do_dim = [&](const float* pp, int dloc) {
-                    const int d = ch * DPC + dloc;
-                    if (d >= p.D || !row_ok) return;
-                    const float xv = p.x[row * p.ldx + d];
-                    float yv, lj;
-                    if constexpr (UNI == ZK_UNI_RQS) {
-                        Bin b = rqs_select<KT, FAST, false>(pp, KT, xv, p.bound, p.aw, p.ad);
-                        rqs_forward_eval<FAST>(b, xv, yv, lj);
-                    } else {
-                        const float ls = softclip<FAST>(pp[1], p.ad);
-                        yv = fmaf(xv, zexp<FAST>(ls), pp[0]);
-                        lj = ls;
-                    }
+                const bool mine = ((int)buf == (s >> 1));  // the set pair that owns this chunk
+                const int h = s & 1;                       // which half of the chunk's dims
+                const uint32_t td = t_lane + TM_D + buf * 128u;
+                auto finish_dim = [&](int d, float yv, float lj) {
                     if (p.y) p.y[row * p.ldy + d] = yv;
                     if (p.log_prob) {
                         const float mu = p.base_loc ? p.base_loc[d] : 0.f;
@@ -403,24 +434,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
                     }
                     lsum += lj;
                 };
-                if (s == 0) {
+                if constexpr (UNI == ZK_UNI_RQS) {
+                    // one dim at a time: load the 16-column-aligned window covering its P parameters
+                    auto do_dim = [&](auto dloc_c) {
+                        constexpr int dloc = decltype(dloc_c)::value;
+                        constexpr int c_lo = dloc * P, c_hi = c_lo + P;  // columns inside the chunk
+                        constexpr int w0 = c_lo & ~15;                   // window start (16-aligned)
+                        constexpr int wn = ((c_hi - w0) + 15) & ~15;     // window width: 32, 48 or 64
+                        static_assert(wn <= 64 && w0 + wn <= 128, "window out of range");
+                        uint32_t rr[wn];
+                        tmem_ld_x16(td + (uint32_t)w0, rr);
+                        if constexpr (wn > 16) tmem_ld_x16(td + (uint32_t)(w0 + 16), rr + 16);
+                        if constexpr (wn > 32) tmem_ld_x16(td + (uint32_t)(w0 + 32), rr + 32);
+                        if constexpr (wn > 48) tmem_ld_x16(td + (uint32_t)(w0 + 48), rr + 48);
+                        tmem_ld_wait();
+                        const int d = ch * DPC + dloc;
+                        if (d >= p.D || !row_ok) return;
+                        float pp[P];
+                        const float* bd = bias + d * P;
 #pragma unroll
-                    for (int j = 0; j < DIMS_A; ++j) do_dim(&v[j * P], j);
+                        for (int j = 0; j < P; ++j) pp[j] = __uint_as_float(rr[c_lo - w0 + j]) + bd[j];
+                        const float xv = p.in_tma ? sx[r * p.D + d] : p.x[row * p.ldx + d];
+                        float yv, lj;
+                        Bin b = rqs_select<KT, FAST, false>(pp, KT, xv, p.bound, p.aw, p.ad);
+                        rqs_forward_eval<FAST>(b, xv, yv, lj);
+                        finish_dim(d, yv, lj);
+                    };
+                    if (mine) {
+                        if (h == 0) for_range<0, DA>(do_dim);
+                        else for_range<DA, DPC - DA>(do_dim);
+                    }
                 } else {
+                    // affine: 8 dims (16 columns: shift, scale pairs) per load; this set takes the
+                    // 4 groups [4 h, 4 h + 4) of the chunk's 8 groups
+                    if (mine) {
 #pragma unroll
-                    for (int j = DIMS_A; j < DPC; ++j) do_dim(&v[j * P - BASE_B], j);
+                        for (int g = 0; g < 4; ++g) {
+                            const int c0 = (h * 4 + g) * 16;
+                            uint32_t rr[16];
+                            tmem_ld_x16(td + (uint32_t)c0, rr);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int d = ch * DPC + (c0 >> 1) + j;
+                                if (d < p.D && row_ok) {
+                                    const float shift = __uint_as_float(rr[2 * j]) + bias[2 * d];
+                                    const float ls = softclip<FAST>(__uint_as_float(rr[2 * j + 1]) + bias[2 * d + 1], p.ad);
+                                    const float xv = p.in_tma ? sx[r * p.D + d] : p.x[row * p.ldx + d];
+                                    finish_dim(d, fmaf(xv, zexp<FAST>(ls), shift), ls);
+                                }
+                            }
+                        }
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(&d_empty[buf]);
                 if (ch < 8) ZK_STAMP(161 + 2 * ch);
             }
             // all MMAs of this tile are complete once the last layer_done fires: A may be restaged
             mbar_wait(layer_done, ld_par);
             ld_par ^= 1u;
-            // ---- per-sample sum: set 1 hands its partial to set 0 ----
-            float* part = s_part + (tile_iter & 1) * FM;
-            if (s == 1) part[r] = lsum;
+            tc_fence_after();
+            // ---- per-sample sum: sets 1..3 hand their partials to set 0 ----
+            float* part = s_part + (tile_iter & 1) * (3 * FM);
+            if (s > 0) part[(s - 1) * FM + r] = lsum;
+            if (p.in_tma) mbar_arrive(&in_empty[ib]);  // x rows no longer needed
             epi_bar_sync();
             if (s == 0 && row_ok) {
-                const float tot = lsum + part[r] + (p.accumulate ? p.ladj[row] : 0.f);
+                const float tot = lsum + part[r] + part[FM + r] + part[2 * FM + r] + (p.accumulate ? p.ladj[row] : 0.f);
                 if (p.log_prob) p.log_prob[row] = tot;
                 else if (p.ladj) p.ladj[row] = tot;
             }
@@ -433,7 +514,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1) fused_
     cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -471,10 +552,16 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     ZK_REQUIRE(a.B < ((int64_t)1 << 31) - FM, "fused layer: batch too large for one launch");
     if (a.B == 0) return ZK_OK;
     FusedParams p;
+    int off = 0;
+    for (int i = 0; i < ZK_FUSED_MAX_LINEAR; ++i) { p.bias[i] = nullptr; p.bias_off[i] = 0; p.bias_len[i] = 0; }
     for (int i = 0; i < m->n_linear; ++i) {
         p.mapW[i] = pk->layers[i].mapW64;
         p.bias[i] = m->b[i];
+        p.bias_off[i] = off;
+        p.bias_len[i] = m->dims[i + 1];
+        off += (m->dims[i + 1] + 3) & ~3;  // keep every layer's bias 16-byte aligned
     }
+    p.bias_in_smem = (off <= F_BIAS_MAXF) ? 1 : 0;
     p.n_linear = m->n_linear;
     p.K0 = a.D + a.C;
     p.KB0 = pk->layers[0].Kp / FK;
@@ -491,6 +578,11 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
     p.dbg = g_timeline;
+    // the x / c rows of a tile are one contiguous block each: stage them with 1-D TMA bulk copies
+    // when the 16-byte rules hold, else the epilogue threads load their rows directly
+    const bool x_ok = (a.ldx == a.D) && (a.D % 4 == 0) && (((uintptr_t)a.x) % 16 == 0);
+    const bool c_ok = (a.C == 0) || ((a.C % 4 == 0) && (((uintptr_t)a.c) % 16 == 0) && (a.ldc == a.C || a.ldc == 0));
+    p.in_tma = (x_ok && c_ok && a.D + a.C <= F_IN_MAXF) ? 1 : 0;
     // clusters of 2 CTAs: even grid, at most one CTA per SM
     const int64_t pairs = ceil_div(ceil_div(a.B, FM), 2);
     const int grid = 2 * (int)std::min<int64_t>(pairs, sm_count() / 2);
