@@ -14,7 +14,7 @@ flow(c).log_prob(x); torch.cuda.synchronize()
 E.lib().zk_debug_timeline(None)
 t = buf.cpu().numpy()
 t0 = t[48]
-names = {48: 'epi: tile start', 49: 'epi: input staged', 50: 'epi: tile end'}
+names = {48: 'epi: tile start', 49: 'epi: input staged', 50: 'epi: tile end', 51: 'epi: in_full seen', 52: 'epi: staging stores issued', 56: 'in-producer: waiting in_empty (tile 2)', 57: 'in-producer: issuing load (tile 2)'}
 for l in range(4):
     names[8*l+0] = f'mma L{l}: a_ready[0] seen'; names[8*l+1] = f'mma L{l}: a_ready[last] seen'; names[8*l+2] = f'mma L{l}: first W stage full'; names[8*l+3] = f'mma L{l}: all issued'
 for l in range(3):

@@ -208,7 +208,12 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     __syncthreads();
     cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // A 512-column allocation is the whole tensor memory, so its base is always lane 0 / column 0.
+    // Using the literal keeps every tcgen05 address in uniform registers: with the address read
+    // back from shared memory ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST waterfall
+    // loop (~110 cycles per MMA instead of 64).
+    if (*tmem_slot != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
 
     if (warp == 0) {
         // ======================= W producer =======================
@@ -295,7 +300,10 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         if (lane == 0 && p.in_tma) {
             for (int it = 0; it < n_iter; ++it) {
                 const int b = it & 1;
+                const bool stamp_on = (it == 2);
+                ZK_STAMP(56);
                 mbar_wait(&in_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+                ZK_STAMP(57);
                 const int t = 2 * (cid + it * ncl) + (int)rank;
                 const int64_t r0 = (int64_t)t * FM;
                 const int rows = (int)max((int64_t)0, min((int64_t)FM, (int64_t)p.M - r0));
@@ -328,6 +336,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             const float* sx = s_in + (size_t)ib * (FM * F_IN_MAXF);
             const float* sc = sx + FM * p.D;
             if (p.in_tma) mbar_wait(&in_full[ib], ((uint32_t)tile_iter >> 1) & 1u);
+            ZK_STAMP(51);
             // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo pairs in TMEM; set s takes
             //      K block kb = s, s + 4, ... (one K block = 64 inputs = 32 TMEM columns) ----
             for (int kb = s; kb < p.KB0; kb += 4) {
@@ -353,6 +362,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 tmem_st_x16(ta + TM_ALO, pl);
                 tmem_st_x16(ta + TM_ALO + 16u, pl + 16);
             }
+            ZK_STAMP(52);
             tmem_st_wait();
             tc_fence_before();
             for (int kb = 0; kb < p.KB0; ++kb) mbar_arrive(&a_ready[kb]);

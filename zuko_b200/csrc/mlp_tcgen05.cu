@@ -95,7 +95,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // A 512-column allocation is the whole tensor memory, so its base is always lane 0 / column 0.
+    // Using the literal keeps every tcgen05 address in uniform registers: with the address read
+    // back from shared memory ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST waterfall
+    // loop (~110 cycles per MMA instead of 64).
+    if (*tmem_slot != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
 
     if (warp == 0) {
         // ================= TMA producer =================
