@@ -246,52 +246,55 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
-            int ws = 0;
-            uint32_t wph = 0, chunk = 0, a_par = 0;  // a_par: bit kb = parity of a_ready[kb]
-            for (int mma_tile = 0; mma_tile < n_iter; ++mma_tile) {
-                const bool stamp_on = (mma_tile == 2);
-                for (int l = 0; l < L; ++l) {
-                    const bool last = (l == L - 1);
-                    const int nch = last ? p.n_last_chunks : nch_hidden;
-                    const int KB = (l == 0) ? p.KB0 : KBH;
-                    const uint32_t idesc = umma_idesc_bf16(FM, last ? N_LAST : p.CW);
-                    for (int ch = 0; ch < nch; ++ch, ++chunk) {
-                        const uint32_t buf = chunk & 1u;
-                        mbar_wait(&d_empty[buf], ((chunk >> 1) & 1u) ^ 1u);
+        // The whole warp walks the (warp-uniform) loops and waits on the barriers; one elected lane
+        // issues the MMAs and commits.  (Issuing from inside an `if (lane == 0)` region made ptxas
+        // wrap every UTCHMMA in an ELECT / BRA.U.ANY waterfall loop: ~110 cycles per MMA.)
+        int ws = 0;
+        uint32_t wph = 0, chunk = 0, a_par = 0;  // a_par: bit kb = parity of a_ready[kb]
+        for (int mma_tile = 0; mma_tile < n_iter; ++mma_tile) {
+            const bool stamp_on = (mma_tile == 2) && (lane == 0);
+            for (int l = 0; l < L; ++l) {
+                const bool last = (l == L - 1);
+                const int nch = last ? p.n_last_chunks : nch_hidden;
+                const int KB = (l == 0) ? p.KB0 : KBH;
+                const uint32_t idesc = umma_idesc_bf16(FM, last ? N_LAST : p.CW);
+                for (int ch = 0; ch < nch; ++ch, ++chunk) {
+                    const uint32_t buf = chunk & 1u;
+                    mbar_wait(&d_empty[buf], ((chunk >> 1) & 1u) ^ 1u);
+                    const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (ch == 0) {  // first use of this K block in this layer
+                            mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
+                            a_par ^= (1u << kb);
+                            if (kb == 0) ZK_STAMP(8 * l + 0);
+                            if (kb == KB - 1) ZK_STAMP(8 * l + 1);
+                        }
+                        mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
-                        for (int kb = 0; kb < KB; ++kb) {
-                            if (ch == 0) {  // first use of this K block in this layer
-                                mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
-                                a_par ^= (1u << kb);
-                                if (kb == 0) ZK_STAMP(8 * l + 0);
-                                if (kb == KB - 1) ZK_STAMP(8 * l + 1);
-                            }
-                            mbar_wait(&w_full[ws], wph);
-                            tc_fence_after();
-                            if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
-                            const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
-                            const uint32_t w_hi = smem_u32(sW + (size_t)ws * F_KBLOCK), w_lo = w_hi + F_PLANE;
+                        if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
+                        const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
+                        const uint32_t w_addr = smem_u32(sW) + (uint32_t)ws * F_KBLOCK;
+                        const uint64_t dw_hi = umma_desc_k_sw128(w_addr), dw_lo = umma_desc_k_sw128(w_addr + F_PLANE);
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < FK / 16; ++k) {
-                                const uint32_t acol = (uint32_t)k * 8u;   // 16 bf16 = 8 TMEM columns
-                                const uint32_t boff = (uint32_t)k * 32u;  // 32 bytes along K in the swizzle row
-                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_k_sw128(w_hi + boff), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                                const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
+                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                                 if (p.n_terms == 3) {
-                                    umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_k_sw128(w_lo + boff), idesc, 1u);
-                                    umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_k_sw128(w_hi + boff), idesc, 1u);
+                                    umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
+                                    umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_advance(dw_hi, k), idesc, 1u);
                                 }
                             }
                             umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
-                            if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
+                            if (kb == KB - 1) {
+                                umma_commit(&d_full[buf]);
+                                if (ch == nch - 1) umma_commit(layer_done);
+                            }
                         }
-                        umma_commit(&d_full[buf]);
-                        if (ch == nch - 1) {
-                            umma_commit(layer_done);
-                            ZK_STAMP(8 * l + 3);
-                        }
+                        __syncwarp();
+                        if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
                     }
+                    if (ch == nch - 1) ZK_STAMP(8 * l + 3);
                 }
             }
         }
@@ -339,28 +342,28 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             ZK_STAMP(51);
             // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo pairs in TMEM; set s takes
             //      K block kb = s, s + 4, ... (one K block = 64 inputs = 32 TMEM columns) ----
-            for (int kb = s; kb < p.KB0; kb += 4) {
-                uint32_t ph[32], pl[32];
+            {
+                // generic pointers to this row's x / c values (shared-memory staging buffer or global)
+                const float* srcx = p.in_tma ? (sx + r * p.D) : (p.x + row * p.ldx);
+                const float* srcc = (p.C == 0) ? srcx : (p.in_tma ? (sc + (p.ldc == 0 ? 0 : r * p.C)) : (p.c + row * p.ldc));
+                const int kx = row_ok ? p.D : 0, kc = row_ok ? p.K0 : 0;  // masked rows stage zeros
+                for (int kb = s; kb < p.KB0; kb += 4) {
+#pragma unroll 1
+                    for (int g = 0; g < 2; ++g) {  // 32 inputs = 16 TMEM columns per plane
+                        const int k0 = kb * FK + g * 32;
+                        uint32_t ph[16], pl[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int k = kb * FK + 2 * j + u;
-                        float val = 0.f;
-                        if (row_ok && k < p.K0) {
-                            if (p.in_tma) val = (k < p.D) ? sx[r * p.D + k] : sc[(p.ldc == 0 ? 0 : r * p.C) + (k - p.D)];
-                            else val = (k < p.D) ? __ldg(p.x + row * p.ldx + k) : __ldg(p.c + row * p.ldc + (k - p.D));
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = k0 + 2 * j;
+                            const float v0 = (k < kx) ? srcx[k] : ((k < kc) ? srcc[k - p.D] : 0.f);
+                            const float v1 = (k + 1 < kx) ? srcx[k + 1] : ((k + 1 < kc) ? srcc[k + 1 - p.D] : 0.f);
+                            split2_bf16(v0, v1, ph[j], pl[j]);
                         }
-                        v[u] = val;
+                        const uint32_t ta = t_lane + (uint32_t)(kb * 32 + g * 16);
+                        tmem_st_x16(ta, ph);
+                        tmem_st_x16(ta + TM_ALO, pl);
                     }
-                    split2_bf16(v[0], v[1], ph[j], pl[j]);
                 }
-                const uint32_t ta = t_lane + (uint32_t)(kb * 32);
-                tmem_st_x16(ta, ph);
-                tmem_st_x16(ta + 16u, ph + 16);
-                tmem_st_x16(ta + TM_ALO, pl);
-                tmem_st_x16(ta + TM_ALO + 16u, pl + 16);
             }
             ZK_STAMP(52);
             tmem_st_wait();

@@ -38,6 +38,20 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// one leader lane of a converged warp (PTX elect.sync); lets the single-thread tcgen05 / TMA issue
+// sit inside warp-uniform control flow so that its operands stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// descriptor of the k-th 16-element K step inside a 64-wide swizzled K block: +32 bytes = +2 units
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, int k) { return desc + (uint64_t)(2 * k); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
