@@ -4,7 +4,10 @@ import zuko_b200 as zuko
 from zuko_b200 import _engine as E
 torch.manual_seed(0)
 dev = torch.device('cuda:0')
-flow = zuko.flows.NSF(16, 8, transforms=1, bins=8, hidden_features=[256]*3).to(dev)
+flow = zuko.flows.NSF(16, 8, transforms=1, bins=8, hidden_features=[256]*3)
+if len(sys.argv) > 1:
+    flow.transform.transforms[0].hyper.gemm_mode = sys.argv[1]
+flow = flow.to(dev)
 B = 1 << 20
 x = torch.randn(B, 16, device=dev); c = torch.randn(B, 8, device=dev)
 flow(c).log_prob(x); torch.cuda.synchronize()

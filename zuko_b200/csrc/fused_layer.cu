@@ -49,7 +49,7 @@ using namespace bij;
 
 constexpr int FM = 128;             // rows per tile
 constexpr int FK = 64;              // bf16 per K block (128-byte swizzle row)
-constexpr int F_WSTAGES = 4;
+constexpr int F_MAX_WSTAGES = 8;   // the W ring is as deep as shared memory allows (see launch_fused_layer)
 constexpr int F_MAXKB = 4;          // A operand: up to 4 K blocks = 256 columns
 constexpr int F_EPI_WARP0 = 4;
 constexpr int F_EPI_WARPS = 16;
@@ -59,11 +59,8 @@ constexpr int F_IN_MAXF = 64;       // floats per row of the staged input (D + C
 constexpr int F_BIAS_MAXF = 5120;   // floats of bias kept in shared memory (else read from global)
 constexpr uint32_t F_PLANE = FM * FK * 2;       // 16 KB: one plane of one W tile
 constexpr uint32_t F_KBLOCK = 2 * F_PLANE;      // hi + lo
-constexpr uint32_t F_W_BYTES = F_WSTAGES * F_KBLOCK;        // 128 KB
-constexpr uint32_t F_IN_BYTES = FM * F_IN_MAXF * 4;         // 32 KB per input buffer
-constexpr uint32_t F_AUX_BYTES = 4096;                      // barriers + ladj scratch
-constexpr uint32_t F_BIAS_BYTES = F_BIAS_MAXF * 4;          // 20 KB
-constexpr size_t F_SMEM = (size_t)F_W_BYTES + 2 * F_IN_BYTES + F_AUX_BYTES + F_BIAS_BYTES + 1024 /*alignment slack*/;
+constexpr uint32_t F_AUX_BYTES = 256 + 3 * 2 * FM * 4;     // 32 barrier slots + ladj partials [2][3][128]
+constexpr uint32_t F_SMEM_MAX = 232448;                    // 227 KB per CTA on sm_100
 constexpr uint32_t TM_ALO = 128, TM_D = 256;    // tensor-memory column map (see header)
 
 struct FusedParams {
@@ -80,6 +77,8 @@ struct FusedParams {
     int n_terms;        // 3 (split bf16) or 1
     int M;
     int in_tma;         // 1: x / c rows are staged through shared memory by 1-D TMA bulk copies
+    int n_wstages;      // depth of the W ring (32 KB per stage)
+    uint32_t in_bytes;  // bytes of one input staging buffer (0 when !in_tma)
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
     float* y; int64_t ldy;
@@ -160,20 +159,23 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // [W ring: n_wstages x 32 KB][input buffers: 2 x in_bytes][barriers + ladj scratch][bias copy]
+    const int NW = p.n_wstages;
     uint8_t* sW = smem;
-    float* s_in = (float*)(smem + F_W_BYTES);  // [2][FM * F_IN_MAXF]
-    uint64_t* bars = (uint64_t*)(smem + F_W_BYTES + 2 * F_IN_BYTES);
-    uint64_t* w_full = bars;                  // [4]
-    uint64_t* w_empty = bars + 4;             // [4]
-    uint64_t* d_full = bars + 8;              // [2]
-    uint64_t* d_empty = bars + 10;            // [2]
-    uint64_t* a_ready = bars + 12;            // [4]  K block kb of the A operand written
-    uint64_t* layer_done = bars + 16;         // [1]  all MMAs issued so far have completed
-    uint64_t* in_full = bars + 17;            // [2]  input rows of a tile landed in s_in[b]
-    uint64_t* in_empty = bars + 19;           // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 21);
-    float* s_part = (float*)(bars + 24);      // [2][3][128] ladj partials of sets 1..3
-    float* s_bias = (float*)(smem + F_W_BYTES + 2 * F_IN_BYTES + F_AUX_BYTES);
+    float* s_in = (float*)(smem + (size_t)NW * F_KBLOCK);
+    const uint32_t in_floats = p.in_bytes / 4;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)NW * F_KBLOCK + 2 * p.in_bytes);
+    uint64_t* w_full = bars;                  // [8]
+    uint64_t* w_empty = bars + 8;             // [8]
+    uint64_t* d_full = bars + 16;             // [2]
+    uint64_t* d_empty = bars + 18;            // [2]
+    uint64_t* a_ready = bars + 20;            // [4]  K block kb of the A operand written
+    uint64_t* layer_done = bars + 24;         // [1]  all MMAs issued so far have completed
+    uint64_t* in_full = bars + 25;            // [2]  input rows of a tile landed in s_in[b]
+    uint64_t* in_empty = bars + 27;           // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 29);
+    float* s_part = (float*)(bars + 32);      // [2][3][128] ladj partials of sets 1..3
+    float* s_bias = (float*)((uint8_t*)bars + F_AUX_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -189,7 +191,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     const int nch_hidden = p.H / p.CW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs
+        for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], F_EPI_THREADS);
@@ -238,7 +240,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             tma_load_3d_mc(st, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 0, (uint16_t)3);
                             if (p.n_terms == 3)
                                 tma_load_3d_mc(st + F_PLANE, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 1, (uint16_t)3);
-                            if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
+                            if (++ws == NW) { ws = 0; wph ^= 1; }
                         }
                     }
                 }
@@ -292,7 +294,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             }
                         }
                         __syncwarp();
-                        if (++ws == F_WSTAGES) { ws = 0; wph ^= 1; }
+                        if (++ws == NW) { ws = 0; wph ^= 1; }
                     }
                     if (ch == nch - 1) ZK_STAMP(8 * l + 3);
                 }
@@ -310,7 +312,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 const int t = 2 * (cid + it * ncl) + (int)rank;
                 const int64_t r0 = (int64_t)t * FM;
                 const int rows = (int)max((int64_t)0, min((int64_t)FM, (int64_t)p.M - r0));
-                float* dst = s_in + (size_t)b * (FM * F_IN_MAXF);
+                float* dst = s_in + (size_t)b * in_floats;
                 const uint32_t bx = (uint32_t)rows * p.D * 4u;
                 const uint32_t bc = (p.C == 0) ? 0u : ((p.ldc == 0) ? (uint32_t)p.C * 4u : (uint32_t)rows * p.C * 4u);
                 if (rows == 0) {
@@ -336,27 +338,50 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             const int64_t row = (int64_t)t * FM + r;
             const bool row_ok = row < p.M;
             const int ib = tile_iter & 1;
-            const float* sx = s_in + (size_t)ib * (FM * F_IN_MAXF);
+            const float* sx = s_in + (size_t)ib * in_floats;
             const float* sc = sx + FM * p.D;
             if (p.in_tma) mbar_wait(&in_full[ib], ((uint32_t)tile_iter >> 1) & 1u);
             ZK_STAMP(51);
             // ---- stage the layer-0 operand: cat(x, c) -> bf16 hi/lo pairs in TMEM; set s takes
             //      K block kb = s, s + 4, ... (one K block = 64 inputs = 32 TMEM columns) ----
-            {
-                // generic pointers to this row's x / c values (shared-memory staging buffer or global)
-                const float* srcx = p.in_tma ? (sx + r * p.D) : (p.x + row * p.ldx);
-                const float* srcc = (p.C == 0) ? srcx : (p.in_tma ? (sc + (p.ldc == 0 ? 0 : r * p.C)) : (p.c + row * p.ldc));
-                const int kx = row_ok ? p.D : 0, kc = row_ok ? p.K0 : 0;  // masked rows stage zeros
+            if (p.in_tma) {
+                // the rows sit in shared memory (TMA): 16-byte loads, 8 lanes cover 8 consecutive rows
+                const float4* sx4 = reinterpret_cast<const float4*>(sx + r * p.D);
+                const float4* sc4 = reinterpret_cast<const float4*>(sc + (p.ldc == 0 ? 0 : r * p.C));
+                const int d4 = row_ok ? (p.D >> 2) : 0, k4 = row_ok ? (p.K0 >> 2) : 0;  // masked rows stage zeros
                 for (int kb = s; kb < p.KB0; kb += 4) {
 #pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {  // 32 inputs = 16 TMEM columns per plane
+                    for (int g = 0; g < 2; ++g) {  // 32 inputs = 8 float4 = 16 TMEM columns per plane
+                        const int i0 = kb * 16 + g * 8;
+                        uint32_t ph[16], pl[16];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int i = i0 + j;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (i < d4) v = sx4[i];
+                            else if (i < k4) v = sc4[i - (p.D >> 2)];
+                            split2_bf16(v.x, v.y, ph[2 * j], pl[2 * j]);
+                            split2_bf16(v.z, v.w, ph[2 * j + 1], pl[2 * j + 1]);
+                        }
+                        const uint32_t ta = t_lane + (uint32_t)(kb * 32 + g * 16);
+                        tmem_st_x16(ta, ph);
+                        tmem_st_x16(ta + TM_ALO, pl);
+                    }
+                }
+            } else {
+                const float* srcx = p.x + row * p.ldx;
+                const float* srcc = (p.C == 0) ? srcx : (p.c + row * p.ldc);
+                const int kx = row_ok ? p.D : 0, kc = row_ok ? p.K0 : 0;
+                for (int kb = s; kb < p.KB0; kb += 4) {
+#pragma unroll 1
+                    for (int g = 0; g < 2; ++g) {
                         const int k0 = kb * FK + g * 32;
                         uint32_t ph[16], pl[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int k = k0 + 2 * j;
-                            const float v0 = (k < kx) ? srcx[k] : ((k < kc) ? srcc[k - p.D] : 0.f);
-                            const float v1 = (k + 1 < kx) ? srcx[k + 1] : ((k + 1 < kc) ? srcc[k + 1 - p.D] : 0.f);
+                            const float v0 = (k < kx) ? __ldg(srcx + k) : ((k < kc) ? __ldg(srcc + k - p.D) : 0.f);
+                            const float v1 = (k + 1 < kx) ? __ldg(srcx + k + 1) : ((k + 1 < kc) ? __ldg(srcc + k + 1 - p.D) : 0.f);
                             split2_bf16(v0, v1, ph[j], pl[j]);
                         }
                         const uint32_t ta = t_lane + (uint32_t)(kb * 32 + g * 16);
@@ -428,7 +453,6 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             // ---- last layer: raw parameters stay in TMEM -> bijector + ladj in registers ----
             float lsum = 0.f;
             const float* bias = p.bias_in_smem ? s_bias + p.bias_off[L - 1] : p.bias[L - 1];
-            const int n_total = p.D * P;
             for (int ch = 0; ch < p.n_last_chunks; ++ch, ++chunk) {
                 const uint32_t buf = chunk & 1u;
                 mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
@@ -508,15 +532,20 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             mbar_wait(layer_done, ld_par);
             ld_par ^= 1u;
             tc_fence_after();
-            // ---- per-sample sum: sets 1..3 hand their partials to set 0 ----
+            // ---- per-sample sum: sets 0..2 hand their partials to set 3 without waiting for it ----
             float* part = s_part + (tile_iter & 1) * (3 * FM);
-            if (s > 0) part[(s - 1) * FM + r] = lsum;
             if (p.in_tma) mbar_arrive(&in_empty[ib]);  // x rows no longer needed
-            epi_bar_sync();
-            if (s == 0 && row_ok) {
-                const float tot = lsum + part[r] + part[FM + r] + part[2 * FM + r] + (p.accumulate ? p.ladj[row] : 0.f);
-                if (p.log_prob) p.log_prob[row] = tot;
-                else if (p.ladj) p.ladj[row] = tot;
+            if (s < 3) {
+                part[s * FM + r] = lsum;
+                __threadfence_block();
+                asm volatile("bar.arrive 1, 512;" ::: "memory");
+            } else {
+                epi_bar_sync();
+                if (row_ok) {
+                    const float tot = lsum + part[r] + part[FM + r] + part[2 * FM + r] + (p.accumulate ? p.ladj[row] : 0.f);
+                    if (p.log_prob) p.log_prob[row] = tot;
+                    else if (p.ladj) p.ladj[row] = tot;
+                }
             }
             ZK_STAMP(50);
         }
@@ -532,10 +561,10 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
 }
 
 template <int UNI, int KT>
-zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, cudaStream_t st) {
+zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> zk_status {
-        ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        kern<<<grid, F_THREADS, F_SMEM, st>>>(p);
+        ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM_MAX));
+        kern<<<grid, F_THREADS, smem, st>>>(p);
         return check_launch("fused_layer_kernel");
     };
     if (fast) return go(fused_layer_kernel<UNI, KT, true>);
@@ -575,6 +604,7 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
         off += (m->dims[i + 1] + 3) & ~3;  // keep every layer's bias 16-byte aligned
     }
     p.bias_in_smem = (off <= F_BIAS_MAXF) ? 1 : 0;
+    const uint32_t bias_bytes = p.bias_in_smem ? (uint32_t)off * 4u : 0u;
     p.n_linear = m->n_linear;
     p.K0 = a.D + a.C;
     p.KB0 = pk->layers[0].Kp / FK;
@@ -596,19 +626,27 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     const bool x_ok = (a.ldx == a.D) && (a.D % 4 == 0) && (((uintptr_t)a.x) % 16 == 0);
     const bool c_ok = (a.C == 0) || ((a.C % 4 == 0) && (((uintptr_t)a.c) % 16 == 0) && (a.ldc == a.C || a.ldc == 0));
     p.in_tma = (x_ok && c_ok && a.D + a.C <= F_IN_MAXF) ? 1 : 0;
+    p.in_bytes = p.in_tma ? (uint32_t)FM * (uint32_t)(a.D + a.C) * 4u : 0u;
+    // The W ring must cover (weight bytes per MMA time) x (TMA round trip ~4000 cycles): with 4
+    // stages the MMA issuer waited ~1000 cycles per stage regardless of the MMA count per stage
+    // (profiles/r01_fused_timeline_v4.txt).  Give it every byte of shared memory that is left.
+    const uint32_t fixed = 1024u /*alignment slack*/ + 2u * p.in_bytes + F_AUX_BYTES + bias_bytes;
+    p.n_wstages = (int)std::min<uint32_t>(F_MAX_WSTAGES, (F_SMEM_MAX - fixed) / F_KBLOCK);
+    ZK_REQUIRE(p.n_wstages >= 3, "fused layer: not enough shared memory for the weight ring");
+    const size_t smem = (size_t)p.n_wstages * F_KBLOCK + fixed;
     // clusters of 2 CTAs: even grid, at most one CTA per SM
     const int64_t pairs = ceil_div(ceil_div(a.B, FM), 2);
     const int grid = 2 * (int)std::min<int64_t>(pairs, sm_count() / 2);
     if (a.univariate == ZK_UNI_RQS && a.bins == 8) {
         p.n_last_chunks = (a.D + 3) / 4;
-        return launch_fused_t<ZK_UNI_RQS, 8>(p, a.fast_math, grid, st);
+        return launch_fused_t<ZK_UNI_RQS, 8>(p, a.fast_math, grid, smem, st);
     }
     if (a.univariate == ZK_UNI_RQS && a.bins == 16) {
         p.n_last_chunks = (a.D + 1) / 2;
-        return launch_fused_t<ZK_UNI_RQS, 16>(p, a.fast_math, grid, st);
+        return launch_fused_t<ZK_UNI_RQS, 16>(p, a.fast_math, grid, smem, st);
     }
     p.n_last_chunks = (a.D + 63) / 64;
-    return launch_fused_t<ZK_UNI_AFFINE, 0>(p, a.fast_math, grid, st);
+    return launch_fused_t<ZK_UNI_AFFINE, 0>(p, a.fast_math, grid, smem, st);
 }
 
 }  // namespace zk
