@@ -26,5 +26,8 @@ for l in range(3):
         names[b] = f'epi L{l}c{ch}: d_full seen'; names[b+1] = f'epi L{l}c{ch}: computed'; names[b+2] = f'epi L{l}c{ch}: layer_done seen'; names[b+3] = f'epi L{l}c{ch}: A written'
 for ch in range(8):
     names[160+2*ch] = f'epi last c{ch}: d_full seen'; names[161+2*ch] = f'epi last c{ch}: dims done'
+for kb in range(4):
+    names[200+3*kb] = f'mma L1c1 kb{kb}: waiting w_full'; names[201+3*kb] = f'mma L1c1 kb{kb}: w_full seen'; names[202+3*kb] = f'mma L1c1 kb{kb}: issued+committed'
+    names[220+3*kb] = f'producer L1c1 kb{kb}: waiting w_empty'; names[221+3*kb] = f'producer L1c1 kb{kb}: w_empty seen'; names[222+3*kb] = f'producer L1c1 kb{kb}: TMA issued'
 ev = sorted((int(v - t0), names.get(i, str(i))) for i, v in enumerate(t) if v != 0)
 for dt, n in ev: print(f'{dt:8d}  {n}')

@@ -224,6 +224,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             int ws = 0;
             uint32_t wph = 0;
             for (int it = 0; it < n_iter; ++it) {
+                const bool stamp_on = (it == 2);
                 for (int l = 0; l < L; ++l) {
                     const bool last = (l == L - 1);
                     const int nch = last ? p.n_last_chunks : nch_hidden;
@@ -232,7 +233,9 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         const int n0 = last ? ch * DPC * P : ch * p.CW;
                         for (int kb = 0; kb < KB; ++kb) {
                             // the slot is written in BOTH CTAs: wait until both MMA issuers released it
+                            if (l == 1 && ch == 1) ZK_STAMP(220 + 3 * kb);
                             mbar_wait(&w_empty[ws], wph ^ 1);
+                            if (l == 1 && ch == 1) ZK_STAMP(221 + 3 * kb);
                             // this CTA fetches rows [64 rank, 64 rank + 64) of the 128-row W tile and
                             // multicasts them to the pair; the peer delivers the other half
                             uint8_t* st = sW + (size_t)ws * F_KBLOCK + rank * (F_PLANE / 2);
@@ -240,6 +243,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             tma_load_3d_mc(st, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 0, (uint16_t)3);
                             if (p.n_terms == 3)
                                 tma_load_3d_mc(st + F_PLANE, &p.mapW[l], &w_full[ws], kb * FK, n0 + 64 * (int)rank, 1, (uint16_t)3);
+                            if (l == 1 && ch == 1) ZK_STAMP(222 + 3 * kb);
                             if (++ws == NW) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -271,8 +275,10 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             if (kb == 0) ZK_STAMP(8 * l + 0);
                             if (kb == KB - 1) ZK_STAMP(8 * l + 1);
                         }
+                        if (l == 1 && ch == 1) ZK_STAMP(200 + 3 * kb);
                         mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
+                        if (l == 1 && ch == 1) ZK_STAMP(201 + 3 * kb);
                         if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
                         const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
                         const uint32_t w_addr = smem_u32(sW) + (uint32_t)ws * F_KBLOCK;
@@ -294,6 +300,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             }
                         }
                         __syncwarp();
+                        if (l == 1 && ch == 1) ZK_STAMP(202 + 3 * kb);
                         if (++ws == NW) { ws = 0; wph ^= 1; }
                     }
                     if (ch == nch - 1) ZK_STAMP(8 * l + 3);
