@@ -312,6 +312,11 @@ def gemm_mode_name(flow) -> str:
     return {E.ZK_GEMM_FP32: "fp32 FMA", E.ZK_GEMM_BF16X3: "tcgen05 bf16x3, fp32 accumulate", E.ZK_GEMM_BF16X1: "tcgen05 bf16"}.get(E.lib().zk_mlp_gemm_mode(h), "?")
 
 
+def ncu_traffic() -> dict:
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    return json.loads(f.read_text()) if f.exists() else {}
+
+
 def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     """Times each kernel class of one flow layer in isolation through the C-ABI entry points
     (CUDA events on the current stream) and converts to roofline terms.  Algorithmic bytes /
@@ -345,6 +350,7 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     rqs_bytes = 4.0 * (D + D * P + D + 1) * B  # x + phi + y + ladj
     fused_bytes = 4.0 * (D + C + D + 1) * B    # fused layer: x, c in; y, ladj out
     out = []
+    traffic = ncu_traffic()
     n0 = L.zk_launch_count()
     fused()
     is_fused = (L.zk_launch_count() - n0) == 1
@@ -354,7 +360,7 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
         tf = flops / (t * 1e-3) / 1e12
         out.append({"name": "fused_layer_kernel<RQS,8> (conditioner 24-256-256-256-368 on tcgen05 + RQS + ladj), one flow layer",
                     "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "ms_per_launch": t, "ms_per_step": t * T,
+                    "frac": tf / peaks["bf16_tflops_sustained"], "traffic": traffic.get("fused_layer_kernel"), "ms_per_launch": t, "ms_per_step": t * T,
                     "algorithmic_flops": flops, "issued_flops": 3 * flops, "frac_issued": 3 * tf / peaks["bf16_tflops_sustained"],
                     "algorithmic_hbm_bytes": fused_bytes, "in_step": True})  # fmt: skip
     prev = L.zk_set_fused_layers(0)
@@ -371,9 +377,9 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     out += [
         {"name": "unfused conditioner: split_input + 4 x linear_tc_kernel (24-256-256-256-368), one flow layer", "bound": "tensor",
          "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
-         "traffic": None, "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops, "in_step": not is_fused},
+         "traffic": traffic.get("linear_tc_kernel_stack"), "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops, "in_step": not is_fused},
         {"name": "uni_kernel<RQS,8> stand-alone fused RQS + ladj (phi in HBM), one flow layer", "bound": "hbm", "achieved": gbs,
-         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": t_rqs,
+         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("uni_kernel"), "ms_per_launch": t_rqs,
          "ms_per_step": t_rqs * T, "algorithmic_bytes": rqs_bytes, "in_step": not is_fused},
     ]  # fmt: skip
     return out
