@@ -136,6 +136,7 @@ def cpu_reference_rate(rows: int, repeats: int = 1):
     on `rows` rows of the bench workload.  Returns (samples/s, seconds, threads)."""
     from oracle import oracle
 
+    threads = oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     flow = build_model()
     spec = oracle.flowspec_from_module(flow)
     g = torch.Generator().manual_seed(1234)
@@ -147,7 +148,7 @@ def cpu_reference_rate(rows: int, repeats: int = 1):
         t0 = time.perf_counter()
         spec.log_prob(x, c, dtype=np.float32)
         best = min(best, time.perf_counter() - t0)
-    return rows / best, best, os.cpu_count()
+    return rows / best, best, threads
 
 
 def run_reference(args) -> None:
@@ -196,6 +197,7 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     peaks = measured_peaks()
@@ -294,7 +296,7 @@ def run_ours(args) -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (conditioner GEMMs: %s)" % gemm_mode_name(flow), "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"dp{world}", "l2": f"inputs rotate over {NBUF} buffers ({NBUF * B * (D + C) * 4 >> 20} MB > 126 MB L2); phi intermediates {B * D * P * 4 >> 20} MB per layer"},
+                       "parallelism": f"dp{world}", "l2": f"inputs rotate over {NBUF} buffers ({NBUF * B * (D + C) * 4 >> 20} MB > 126 MB L2)"},
             "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4, "d2h_bytes_per_step": B * 4,
                                              "steps": e2e_steps, "api": "FlowCall.log_prob_host -> zk_flow_log_prob_host (pinned host buffers)"},
             "gpu_launches": int(launches), "mean_nll": nll_value, "roofline": roofline, "kernels": kernels,

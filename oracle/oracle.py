@@ -61,6 +61,12 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Sets the OpenMP thread count of the C restatement; returns the count in effect."""
+    lib().zo_set_threads(int(n))
+    return int(lib().zo_get_threads())
+
+
 _i64 = ctypes.c_int64
 _int = ctypes.c_int
 

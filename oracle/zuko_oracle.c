@@ -37,3 +37,13 @@
 #include "zuko_oracle_impl.h"
 
 int zo_max_bins(void) { return ZO_MAX_BINS; }
+
+#ifdef _OPENMP
+#include <omp.h>
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its thread count explicitly. */
+void zo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int zo_get_threads(void) { return omp_get_max_threads(); }
+#else
+void zo_set_threads(int n) { (void)n; }
+int zo_get_threads(void) { return 1; }
+#endif
