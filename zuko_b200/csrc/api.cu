@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 
+#include "ar_inverse.cuh"
 #include "bijectors.cuh"
 #include "fused_layer.cuh"
 #include "mlp.cuh"
@@ -95,6 +96,7 @@ struct zk_layer {
     int* idx_a = nullptr;          // device: constant-split columns (coupling), owned
     int* idx_b = nullptr;          // device: transformed columns (coupling), owned
     int n_a = 0, n_b = 0;
+    zk::ArInvPack* inv = nullptr;  // step-ordered weights for the dimension-sequential inverse (owned)
 };
 
 extern "C" {
@@ -293,6 +295,7 @@ zk_status zk_mlp_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, c
 zk_status zk_layer_destroy(zk_layer* l) {
     if (!l) return ZK_OK;
     zk_mlp_destroy(l->hyper);
+    ar_inverse_free(l->inv);
     cudaFree(l->phi_shared);
     cudaFree(l->rotation);
     cudaFree(l->perm);
@@ -326,6 +329,15 @@ static zk_status layer_create_impl(const zk_layer_desc* d, zk_layer* l) {
             ZK_REQUIRE(l->hyper->dims[l->hyper->n_linear] == l->D * l->P,
                        "layer_create: conditioner out_features %d != D*P %d",
                        l->hyper->dims[l->hyper->n_linear], l->D * l->P);
+            {
+                int T = 0;
+                size_t smem = 0;
+                ZK_TRY(ar_inverse_pack(l->hyper, d->hyper->mask, d->order, l->D, l->C, l->uni, l->K, l->passes, &l->inv));
+                if (l->inv && !ar_inverse_threads(l->inv, &T, &smem)) {  // state too large: use the sweeps
+                    ar_inverse_free(l->inv);
+                    l->inv = nullptr;
+                }
+            }
             return ZK_OK;
         }
         case ZK_LAYER_COUPLING: {
@@ -536,6 +548,8 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:994-1000: x = zeros_like(y); for _ in range(passes): x = meta(x).inv(y)
+            if (l->inv && g_fused.load())  // same fixed point, every weight visited once (ar_inverse.cu)
+                return launch_ar_inverse(l->inv, y, ldy, c, ldc, B, x, ldx, l->bound, l->slope, g_fast_math.load() != 0, st);
             float* phi = ar.take<float>((size_t)B * l->D * l->P);
             ZK_REQUIRE(ar.ok, "layer_inverse: workspace too small");
             if (ldx == l->D) {

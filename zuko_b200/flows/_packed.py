@@ -63,6 +63,9 @@ class PackedLayerMixin:
                 ts += [m.weight, m.bias, getattr(m, "mask", None)]
         for p in getattr(self, "phi", []) or []:
             ts.append(p)
+        order = getattr(self, "order", None)
+        if torch.is_tensor(order):
+            ts.append(order)
         return ts
 
     def _layer_signature(self) -> tuple:

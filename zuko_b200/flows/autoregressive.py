@@ -129,7 +129,13 @@ class MaskedAutoregressiveTransform(PackedLayerMixin, LazyTransform):
         import ctypes
 
         desc.hyper = ctypes.pointer(hyper)
-        return desc, [hyper, keep]
+        keep = [hyper, keep]
+        if self.order is not None:  # order classes let the engine run the dimension-sequential inverse
+            host = self.order.detach().to("cpu", torch.int64).tolist()
+            arr = (ctypes.c_int64 * self.features)(*host)
+            desc.order = arr
+            keep.append(arr)
+        return desc, keep
 
     def forward(self, c: Tensor | None = None) -> Transform:
         return AutoregressiveTransform(self, c)
