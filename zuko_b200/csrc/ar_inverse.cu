@@ -36,7 +36,7 @@ struct ArInvPack {
     int D = 0, C = 0, P = 0, uni = 0, bins = 0, passes = 0;
     int n_linear = 0;
     std::vector<int> dims;         // n_linear + 1
-    std::vector<int> sec_off;      // state section offsets (floats): IN, H1.., Y
+    std::vector<int> sec_off;      // state section offsets (floats): IN, H1 .. H_{L-1}, end
     int state_floats = 0;
     int max_step_words = 0;
     float* stream = nullptr;       // device: all step blocks
@@ -55,7 +55,7 @@ struct InvParams {
     const int* step_off;
     int passes, n_linear, D, C, P;
     int dims[8];       // layer widths
-    int sec_off[9];    // state sections: IN, H1 .. H_{L-1}, Y
+    int sec_off[9];    // state sections: IN, H1 .. H_{L-1}, end
     const float* y; int64_t ldy;
     const float* c; int64_t ldc;
     float* x; int64_t ldx;
@@ -86,12 +86,11 @@ __global__ void ar_inverse_kernel(const InvParams p) {
     const int T = blockDim.x;
     const int tid = threadIdx.x;
     float* state = smem_f;                                   // [state_floats][T]
-    float* wbuf = smem_f + (size_t)p.sec_off[p.n_linear + 1] * T;  // one step block
+    float* wbuf = smem_f + (size_t)p.sec_off[p.n_linear] * T;  // one step block
     const int L = p.n_linear;
     const int64_t row = (int64_t)blockIdx.x * T + tid;
     const bool row_ok = row < p.B;
     float* S_in = state + (size_t)p.sec_off[0] * T + tid;
-    float* S_y = state + (size_t)p.sec_off[L] * T + tid;
 
     // x = zeros_like(y) (transforms.py:995); context and y are constant inputs
     for (int k = 0; k < p.D; ++k) S_in[k * T] = 0.f;
@@ -100,7 +99,6 @@ __global__ void ar_inverse_kernel(const InvParams p) {
         float* Sh = state + (size_t)p.sec_off[l] * T + tid;
         for (int k = 0; k < p.dims[l]; ++k) Sh[k * T] = 0.f;
     }
-    for (int d = 0; d < p.D; ++d) S_y[d * T] = row_ok ? p.y[row * p.ldy + d] : 0.f;
 
     for (int step = 0; step < p.passes; ++step) {
         const int off = p.step_off[step], len = p.step_off[step + 1] - off;
@@ -148,6 +146,7 @@ __global__ void ar_inverse_kernel(const InvParams p) {
             const float* Sl = state + (size_t)p.sec_off[L - 1] * T + tid;
             for (int i = 0; i < n_dims; ++i) {
                 const int d = dim_ids[i];
+                const float yv = row_ok ? __ldg(p.y + row * p.ldy + d) : 0.f;  // issued early: overlaps the dot products
                 float phi[PT * TILE];
 #pragma unroll
                 for (int t = 0; t < PT; ++t) {
@@ -159,7 +158,6 @@ __global__ void ar_inverse_kernel(const InvParams p) {
 #pragma unroll
                     for (int j = 0; j < TILE; ++j) phi[t * TILE + j] = acc[j];
                 }
-                const float yv = S_y[d * T];
                 float xv;
                 if constexpr (UNI == ZK_UNI_RQS) {
                     Bin b = rqs_select<KT, FAST, true>(phi, KT, yv, p.bound, p.aw, p.ad);
@@ -246,8 +244,6 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
     pk->sec_off.push_back(off);
     off += D + C;
     for (int l = 1; l < L; ++l) { pk->sec_off.push_back(off); off += m->dims[l]; }
-    pk->sec_off.push_back(off);  // Y
-    off += D;
     pk->sec_off.push_back(off);  // end
     pk->state_floats = off;
 
@@ -321,14 +317,22 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
 }
 
 bool ar_inverse_threads(const ArInvPack* pk, int* threads, size_t* smem) {
-    const size_t budget = 200 * 1024;
     const size_t wbytes = (size_t)pk->max_step_words * 4 + 16;
+    const size_t per_thread = (size_t)pk->state_floats * 4;
+    // two CTAs of 128 samples per SM when they fit (8 warps hide the FMA / LDS latencies of the
+    // dot products far better than 4), else one CTA with as many samples as 200 KB hold
+    if (per_thread * 128 + wbytes <= 112 * 1024) {
+        *threads = 128;
+        *smem = per_thread * 128 + wbytes;
+        return true;
+    }
+    const size_t budget = 200 * 1024;
     if (wbytes >= budget) return false;
-    int T = (int)((budget - wbytes) / ((size_t)pk->state_floats * 4));
+    int T = (int)((budget - wbytes) / per_thread);
     T = std::min(128, T / 32 * 32);
     if (T < 32) return false;
     *threads = T;
-    *smem = (size_t)pk->state_floats * 4 * T + wbytes;
+    *smem = per_thread * T + wbytes;
     return true;
 }
 
