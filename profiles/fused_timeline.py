@@ -29,5 +29,6 @@ for ch in range(8):
 for kb in range(4):
     names[200+3*kb] = f'mma L1c1 kb{kb}: waiting w_full'; names[201+3*kb] = f'mma L1c1 kb{kb}: w_full seen'; names[202+3*kb] = f'mma L1c1 kb{kb}: issued+committed'
     names[220+3*kb] = f'producer L1c1 kb{kb}: waiting w_empty'; names[221+3*kb] = f'producer L1c1 kb{kb}: w_empty seen'; names[222+3*kb] = f'producer L1c1 kb{kb}: TMA issued'
+names[240]='epi L1c1: LDTM + wait::ld done'; names[241]='epi L1c1: d_empty arrived'; names[242]='epi L1c1: STTM issued'; names[243]='epi L1c1: wait::st done'
 ev = sorted((int(v - t0), names.get(i, str(i))) for i, v in enumerate(t) if v != 0)
 for dt, n in ev: print(f'{dt:8d}  {n}')

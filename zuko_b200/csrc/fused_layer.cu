@@ -413,26 +413,31 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                     ZK_STAMP(64 + 16 * l + 4 * ch + 0);
                     const int col0 = s * 32;              // this set's 32 columns of the chunk
                     const bool owner = col0 < p.CW;       // CW = 64: sets 2, 3 have no columns
-                    uint32_t ra[32];
-                    if (owner) {
-                        tmem_ld_32x32b_x32(t_lane + TM_D + buf * 128u + (uint32_t)col0, ra);
-                        tmem_ld_wait();
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&d_empty[buf]);  // accumulator buffer is free again
+                    // two halves of 16 columns: at most 16 raw + 32 packed registers live (the x32
+                    // variant spilled the packed values to local memory under the 96-register cap)
                     uint32_t ph[16], pl[16];
                     const int nbase = ch * p.CW + col0;   // first output column = K index of the next layer
                     if (owner) {
                         const float4* b4 = reinterpret_cast<const float4*>(bias + nbase);  // 128-byte aligned
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 bb = b4[j >> 2];  // one broadcast 16-byte load per 4 columns
-                            split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
-                                        ph[j >> 1], pl[j >> 1]);
-                            split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
-                                        ph[(j >> 1) + 1], pl[(j >> 1) + 1]);
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t ra[16];
+                            tmem_ld_x16(t_lane + TM_D + buf * 128u + (uint32_t)(col0 + 16 * half), ra);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bb = b4[4 * half + (j >> 2)];  // one broadcast 16-byte load per 4 columns
+                                split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
+                                            ph[8 * half + (j >> 1)], pl[8 * half + (j >> 1)]);
+                                split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
+                                            ph[8 * half + (j >> 1) + 1], pl[8 * half + (j >> 1) + 1]);
+                            }
                         }
                     }
+                    if (l == 1 && ch == 1) ZK_STAMP(240);
+                    tc_fence_before();
+                    mbar_arrive(&d_empty[buf]);  // accumulator buffer is free again
+                    if (l == 1 && ch == 1) ZK_STAMP(241);
                     ZK_STAMP(64 + 16 * l + 4 * ch + 1);
                     if (ch == 0) {  // the A operand may be overwritten once ALL MMAs of this layer are done
                         mbar_wait(layer_done, ld_par);
@@ -444,8 +449,10 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         const uint32_t ta = t_lane + (uint32_t)(nbase >> 1);  // K element k lives in column k / 2
                         tmem_st_x16(ta, ph);
                         tmem_st_x16(ta + TM_ALO, pl);
+                        if (l == 1 && ch == 1) ZK_STAMP(242);
                         tmem_st_wait();
                     }
+                    if (l == 1 && ch == 1) ZK_STAMP(243);
                     tc_fence_before();
                     if (p.CW == 128) {
                         mbar_arrive(&a_ready[ch * 2]);

@@ -142,12 +142,15 @@ zk_status make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int K
 
 // bf16 hi / lo split of two fp32 values, packed as (low 16 bits = first, high 16 = second).
 // hi = rn_bf16(v) (one cvt.rn.bf16x2.f32 for the pair), lo = rn_bf16(v - hi): 6 instructions / pair.
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo_half, float hi_half) {
+    uint32_t d;  // cvt.rn.bf16x2.f32 d, a, b : a -> upper 16 bits, b -> lower 16 bits
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
 __device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-    hi = *reinterpret_cast<uint32_t*>(&h);
+    hi = pack_bf16x2_rn(v0, v1);  // registers only (taking the address of a __nv_bfloat162 went through local memory)
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-    __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    lo = pack_bf16x2_rn(v0 - h0, v1 - h1);
 }
 
 }  // namespace zk
