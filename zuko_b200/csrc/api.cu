@@ -329,6 +329,7 @@ static zk_status layer_create_impl(const zk_layer_desc* d, zk_layer* l) {
             ZK_REQUIRE(l->hyper->dims[l->hyper->n_linear] == l->D * l->P,
                        "layer_create: conditioner out_features %d != D*P %d",
                        l->hyper->dims[l->hyper->n_linear], l->D * l->P);
+            ZK_TRY(fused_layer_prepare(l->hyper, d->hyper->mask, l->uni, l->K, l->D, l->C));
             {
                 int T = 0;
                 size_t smem = 0;

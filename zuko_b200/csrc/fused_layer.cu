@@ -35,7 +35,11 @@
 //   warps 4-19  epilogue: four warp sets; hidden layers: set s owns 32 columns of a chunk;
 //               last layer: set pair (chunk parity) owns the chunk, its two sets split the dims
 
+#include <string.h>
+
+#include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "bijector_math.cuh"
 #include "fused_layer.cuh"
@@ -69,6 +73,7 @@ struct FusedParams {
     int bias_off[ZK_FUSED_MAX_LINEAR];  // offset of layer l's bias in the shared-memory copy
     int bias_len[ZK_FUSED_MAX_LINEAR];
     int bias_in_smem;
+    uint8_t kbmask[ZK_FUSED_MAX_LINEAR][128];  // [layer][chunk]: K blocks with non-zero weights
     int n_linear;
     int K0, KB0;        // real input width (D + C) and its number of 64-wide K blocks
     int H, CW;          // hidden width (multiple of 64, <= 256), hidden chunk width (128 or 64)
@@ -231,7 +236,9 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                     const int KB = (l == 0) ? p.KB0 : KBH;
                     for (int ch = 0; ch < nch; ++ch) {
                         const int n0 = last ? ch * DPC * P : ch * p.CW;
+                        const uint32_t kbm = p.kbmask[l][ch];
                         for (int kb = 0; kb < KB; ++kb) {
+                            if (!((kbm >> kb) & 1u)) continue;  // all-zero tile of the masked matrix: skipped
                             // the slot is written in BOTH CTAs: wait until both MMA issuers released it
                             if (l == 1 && ch == 1) ZK_STAMP(220 + 3 * kb);
                             mbar_wait(&w_empty[ws], wph ^ 1);
@@ -264,14 +271,20 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 const int nch = last ? p.n_last_chunks : nch_hidden;
                 const int KB = (l == 0) ? p.KB0 : KBH;
                 const uint32_t idesc = umma_idesc_bf16(FM, last ? N_LAST : p.CW);
+                uint32_t waited = 0;  // K blocks of this layer whose a_ready phase has been consumed
                 for (int ch = 0; ch < nch; ++ch, ++chunk) {
                     const uint32_t buf = chunk & 1u;
                     mbar_wait(&d_empty[buf], ((chunk >> 1) & 1u) ^ 1u);
                     const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
+                    const uint32_t kbm = p.kbmask[l][ch];
+                    const int kb_last = 31 - __clz((int)kbm);  // kbm != 0 (host guarantees)
+                    bool first = true;
                     for (int kb = 0; kb < KB; ++kb) {
-                        if (ch == 0) {  // first use of this K block in this layer
+                        if (!((kbm >> kb) & 1u)) continue;  // all-zero tile: nothing to accumulate
+                        if (!((waited >> kb) & 1u)) {  // first use of this K block in this layer
                             mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
                             a_par ^= (1u << kb);
+                            waited |= (1u << kb);
                             if (kb == 0) ZK_STAMP(8 * l + 0);
                             if (kb == KB - 1) ZK_STAMP(8 * l + 1);
                         }
@@ -279,7 +292,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
                         if (l == 1 && ch == 1) ZK_STAMP(201 + 3 * kb);
-                        if (ch == 0 && kb == 0) ZK_STAMP(8 * l + 2);
+                        if (ch == 0 && first) ZK_STAMP(8 * l + 2);
                         const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
                         const uint32_t w_addr = smem_u32(sW) + (uint32_t)ws * F_KBLOCK;
                         const uint64_t dw_hi = umma_desc_k_sw128(w_addr), dw_lo = umma_desc_k_sw128(w_addr + F_PLANE);
@@ -287,21 +300,30 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
 #pragma unroll
                             for (int k = 0; k < FK / 16; ++k) {
                                 const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
-                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
                                 if (p.n_terms == 3) {
                                     umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
                                     umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_advance(dw_hi, k), idesc, 1u);
                                 }
                             }
                             umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
-                            if (kb == KB - 1) {
+                            if (kb == kb_last) {
                                 umma_commit(&d_full[buf]);
                                 if (ch == nch - 1) umma_commit(layer_done);
                             }
                         }
                         __syncwarp();
+                        first = false;
                         if (l == 1 && ch == 1) ZK_STAMP(202 + 3 * kb);
                         if (++ws == NW) { ws = 0; wph ^= 1; }
+                    }
+                    if (ch == nch - 1) {
+                        // K blocks no chunk of this layer read: still consume their a_ready phase
+                        for (int kb = 0; kb < KB; ++kb)
+                            if (!((waited >> kb) & 1u)) {
+                                mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
+                                a_par ^= (1u << kb);
+                            }
                     }
                     if (ch == nch - 1) ZK_STAMP(8 * l + 3);
                 }
@@ -602,6 +624,126 @@ bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int
     return univariate == ZK_UNI_AFFINE;
 }
 
+namespace {
+__global__ void split_permuted_kernel(const float* W, int N, int K, int Kp, const int* row_perm, const int* col_perm,
+                                      __nv_bfloat16* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * Kp) return;
+    const int n = (int)(i / Kp), k = (int)(i - (int64_t)n * Kp);
+    const int sn = row_perm ? row_perm[n] : n;
+    const float v = (k < K) ? W[(int64_t)sn * K + (col_perm ? col_perm[k] : k)] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[(int64_t)N * Kp + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__global__ void permute_bias_kernel(const float* b, int N, const int* perm, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = b[perm ? perm[i] : i];
+}
+}  // namespace
+
+zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {
+    if (!fused_layer_supported(m, univariate, bins, D, C)) return ZK_OK;
+    TcPack* pk = (TcPack*)m->tc;
+    FusedPack& f = pk->fused;
+    const int L = m->n_linear;
+    const int H = m->dims[1];
+    const int CW = (H % 128 == 0) ? 128 : 64;
+    const int P = (univariate == ZK_UNI_RQS) ? 3 * bins - 1 : 2;
+    const int DPC = (univariate == ZK_UNI_RQS) ? (bins == 8 ? 4 : 2) : 64;
+    // ---- host copies of the masks (dense layers: all ones) ----
+    std::vector<std::vector<uint8_t>> Mk(L);
+    for (int l = 0; l < L; ++l) {
+        const size_t n = (size_t)m->dims[l + 1] * m->dims[l];
+        Mk[l].assign(n, 1);
+        if (mask_dev && mask_dev[l]) ZK_CUDA(cudaMemcpy(Mk[l].data(), mask_dev[l], n, cudaMemcpyDeviceToHost));
+    }
+    // ---- dependency degree of every hidden unit = number of network inputs it can see ----
+    // (flows/autoregressive.py:121-124 + nn.py:270-293: units of a lower order class see fewer
+    // inputs; sorting by degree makes hidden -> hidden masks block lower-triangular)
+    const int K0 = m->dims[0];
+    std::vector<std::vector<int>> perm(L - 1);  // perm[l][new] = old index of hidden layer l+1's units
+    std::vector<std::vector<std::vector<uint8_t>>> dep(L);  // dep[l][unit][input]
+    for (int l = 0; l < L - 1; ++l) {
+        const int K = m->dims[l], N = m->dims[l + 1];
+        dep[l].assign(N, std::vector<uint8_t>(K0, 0));
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) {
+                if (!Mk[l][(size_t)n * K + k]) continue;
+                if (l == 0) dep[l][n][k] = 1;
+                else for (int i = 0; i < K0; ++i) dep[l][n][i] |= dep[l - 1][k][i];
+            }
+        std::vector<int> deg(N, 0);
+        for (int n = 0; n < N; ++n) for (int i = 0; i < K0; ++i) deg[n] += dep[l][n][i];
+        perm[l].resize(N);
+        for (int n = 0; n < N; ++n) perm[l][n] = n;
+        std::stable_sort(perm[l].begin(), perm[l].end(), [&](int a, int b) { return deg[a] < deg[b]; });
+    }
+    // ---- permuted planes, biases, tensor maps ----
+    for (auto* q : f.w) cudaFree(q);
+    for (auto* q : f.bias) cudaFree(q);
+    f.w.clear(); f.bias.clear(); f.map64.clear();
+    f.map64.resize(L);
+    std::vector<int*> dperm(L - 1, nullptr);
+    zk_status st = ZK_OK;
+    for (int l = 0; l < L - 1 && st == ZK_OK; ++l) {
+        if (cudaMalloc((void**)&dperm[l], perm[l].size() * 4) != cudaSuccess ||
+            cudaMemcpy(dperm[l], perm[l].data(), perm[l].size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            st = fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");
+    }
+    for (int l = 0; l < L && st == ZK_OK; ++l) {
+        const int K = m->dims[l], N = m->dims[l + 1], Kp = pk->layers[l].Kp;
+        __nv_bfloat16* w = nullptr;
+        float* b = nullptr;
+        if (cudaMalloc((void**)&w, (size_t)2 * N * Kp * 2) != cudaSuccess || cudaMalloc((void**)&b, ((size_t)N + 4) * 4) != cudaSuccess) {
+            cudaFree(w);
+            st = fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");
+            break;
+        }
+        f.w.push_back(w);
+        f.bias.push_back(b);
+        const int* rp = (l < L - 1) ? dperm[l] : nullptr;      // output units of hidden layers are permuted
+        const int* cp = (l > 0) ? dperm[l - 1] : nullptr;       // and so are the inputs of the layer after
+        split_permuted_kernel<<<(unsigned)ceil_div((int64_t)N * Kp, 256), 256, 0, 0>>>(m->w[l], N, K, Kp, rp, cp, w);
+        st = check_launch("split_permuted_kernel");
+        if (st != ZK_OK) break;
+        cudaMemsetAsync(b, 0, ((size_t)N + 4) * 4, 0);
+        permute_bias_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, 0>>>(m->b[l], N, rp, b);
+        st = check_launch("permute_bias_kernel");
+        if (st != ZK_OK) break;
+        st = make_plane_map(&f.map64[l], w, N, Kp, 64);
+    }
+    if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "fused_layer_prepare: sync failed");
+    for (int* q : dperm) cudaFree(q);
+    if (st != ZK_OK) return st;
+    // ---- which (chunk, K block) tiles of the permuted masked matrices are non-zero ----
+    memset(f.kbmask, 0, sizeof(f.kbmask));
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        const int K = m->dims[l], N = m->dims[l + 1];
+        const int nch = last ? (D + DPC - 1) / DPC : H / CW;
+        const int KB = pk->layers[l].Kp / 64;
+        for (int ch = 0; ch < nch && ch < 128; ++ch) {
+            const int n0 = last ? ch * DPC * P : ch * CW;
+            const int n1 = std::min(N, last ? n0 + DPC * P : n0 + CW);
+            uint8_t bits = 0;
+            for (int n = n0; n < n1; ++n) {
+                const int sn = (l < L - 1) ? perm[l][n] : n;
+                for (int k = 0; k < K; ++k) {
+                    const int sk = (l > 0) ? perm[l - 1][k] : k;
+                    if (Mk[l][(size_t)sn * K + sk]) bits |= (uint8_t)(1u << (k / 64));
+                }
+            }
+            if (bits == 0) bits = 1;  // the accumulator still has to be defined (bias-only outputs)
+            (void)KB;
+            f.kbmask[l][ch] = bits;
+        }
+    }
+    f.uni = univariate; f.bins = bins; f.D = D; f.C = C;
+    f.ready = true;
+    return ZK_OK;
+}
+
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t st) {
     const TcPack* pk = (const TcPack*)m->tc;
     ZK_REQUIRE(pk && fused_layer_supported(m, a.univariate, a.bins, a.D, a.C), "fused layer: unsupported shape");
@@ -610,9 +752,13 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     FusedParams p;
     int off = 0;
     for (int i = 0; i < ZK_FUSED_MAX_LINEAR; ++i) { p.bias[i] = nullptr; p.bias_off[i] = 0; p.bias_len[i] = 0; }
+    const FusedPack& f = pk->fused;
+    const bool packed = f.ready && f.uni == a.univariate && f.bins == a.bins && f.D == a.D && f.C == a.C;
+    memset(p.kbmask, 0xff, sizeof(p.kbmask));  // unprepared handles: every tile is streamed
+    if (packed) memcpy(p.kbmask, f.kbmask, sizeof(p.kbmask));
     for (int i = 0; i < m->n_linear; ++i) {
-        p.mapW[i] = pk->layers[i].mapW64;
-        p.bias[i] = m->b[i];
+        p.mapW[i] = packed ? f.map64[i] : pk->layers[i].mapW64;
+        p.bias[i] = packed ? f.bias[i] : m->b[i];
         p.bias_off[i] = off;
         p.bias_len[i] = m->dims[i + 1];
         off += (m->dims[i + 1] + 3) & ~3;  // keep every layer's bias 16-byte aligned

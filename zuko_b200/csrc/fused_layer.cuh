@@ -23,6 +23,10 @@ struct FusedLayerArgs {
 
 // true when the autoregressive layer (conditioner `m`, univariate, D, C) can run as ONE kernel
 bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C);
+// Builds the fused kernel's weight pack for this conditioner (degree-sorted hidden units, zero-tile
+// map); `mask_dev` are the DEVICE mask pointers of zk_mlp_desc (may be null = dense).  No-op when
+// the shape is not supported by the fused kernel.
+zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C);
 extern long long* g_timeline;  // device buffer of >= 256 stamps, or null (zk_debug_timeline)
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
 

@@ -326,6 +326,8 @@ void tc_destroy(zk_mlp* m) {
     TcPack* pk = (TcPack*)m->tc;
     if (!pk) return;
     for (auto& l : pk->layers) cudaFree(l.w);
+    for (auto* q : pk->fused.w) cudaFree(q);
+    for (auto* q : pk->fused.bias) cudaFree(q);
     delete pk;
     m->tc = nullptr;
 }

@@ -128,10 +128,22 @@ struct TcLayer {
     CUtensorMap mapW128;  // box (64 x 128 x 1)
     CUtensorMap mapW64;   // box (64 x 64 x 1): fused layer kernel, one half per CTA of a pair (multicast)
 };
+// weights as the fused layer kernel streams them: hidden units sorted by dependency degree (so
+// that the masked matrices are block lower-triangular) and the all-zero (chunk, K block) tiles
+// of every layer recorded so that their TMA loads and MMAs are skipped
+struct FusedPack {
+    bool ready = false;
+    int uni = 0, bins = 0, D = 0, C = 0;
+    std::vector<__nv_bfloat16*> w;  // per layer [2][N][Kp], permuted (owned)
+    std::vector<float*> bias;       // per layer, permuted, padded (owned)
+    std::vector<CUtensorMap> map64; // box (64 x 64 x 1)
+    uint8_t kbmask[8][128];         // [layer][chunk]: bit kb = K block kb has non-zero weights
+};
 struct TcPack {
     std::vector<TcLayer> layers;
     int n_terms = 3;
     int max_np = 0;  // widest padded hidden activation
+    FusedPack fused;
 };
 
 inline int pad64(int v) { return (v + 63) / 64 * 64; }
