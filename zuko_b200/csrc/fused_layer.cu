@@ -159,8 +159,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
     constexpr int P = Cfg::P, DPC = Cfg::DPC;
     constexpr int N_LAST = (DPC * P + 15) & ~15;  // MMA N of a last-layer chunk
-    constexpr int SPG = (DPC >= 4) ? 4 : DPC;      // warp sets that share one chunk (one dim each when DPC <= 4)
-    constexpr int NG = 4 / SPG;                   // chunk groups that work on consecutive chunks concurrently
+    constexpr int DA = (DPC + 1) / 2;             // dims of a chunk handled by the first set of the pair
     static_assert(N_LAST <= 128, "a last-layer chunk must fit one accumulator buffer");
 
     extern __shared__ uint8_t smem_raw[];
@@ -495,8 +494,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                 tc_fence_after();
                 if (ch < 8) ZK_STAMP(160 + 2 * ch);
-                const bool mine = (NG == 1) || ((int)(buf % NG) == (s / SPG));  // the set group that owns this chunk
-                const int si = s % SPG;                    // this set's share of the chunk's dims: si, si + SPG, ...
+                const bool mine = ((int)buf == (s >> 1));  // the set pair that owns this chunk
+                const int h = s & 1;                       // which half of the chunk's dims
                 const uint32_t td = t_lane + TM_D + buf * 128u;
                 auto finish_dim = [&](int d, float yv, float lj) {
                     if (p.y) p.y[row * p.ldy + d] = yv;
@@ -534,17 +533,17 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         rqs_forward_eval<FAST>(b, xv, yv, lj);
                         finish_dim(d, yv, lj);
                     };
-                    auto my_dims = [&](auto dloc_c) {
-                        if ((decltype(dloc_c)::value % SPG) == si) do_dim(dloc_c);  // warp-uniform
-                    };
-                    if (mine) for_range<0, DPC>(my_dims);
+                    if (mine) {
+                        if (h == 0) for_range<0, DA>(do_dim);
+                        else for_range<DA, DPC - DA>(do_dim);
+                    }
                 } else {
                     // affine: 8 dims (16 columns: shift, scale pairs) per load; this set takes the
-                    // 2 groups [2 si, 2 si + 2) of the chunk's 8 groups
+                    // 4 groups [4 h, 4 h + 4) of the chunk's 8 groups
                     if (mine) {
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int c0 = (si * 2 + g) * 16;
+                        for (int g = 0; g < 4; ++g) {
+                            const int c0 = (h * 4 + g) * 16;
                             uint32_t rr[16];
                             tmem_ld_x16(td + (uint32_t)c0, rr);
                             tmem_ld_wait();
