@@ -127,39 +127,40 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n0 = (t % p.n_chunks) * BN;
-                int n_sz = p.N - n0;                       // columns of this chunk
-                n_sz = n_sz > BN ? BN : ((n_sz + 15) & ~15);  // UMMA N: multiple of 16 (M = 128)
-                const uint32_t idesc = umma_idesc_bf16(BM, n_sz);
-                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        // whole warp converged, one elected lane issues (keeps every tcgen05 operand in uniform
+        // registers; see fused_layer.cu)
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n0 = (t % p.n_chunks) * BN;
+            int n_sz = p.N - n0;                       // columns of this chunk
+            n_sz = n_sz > BN ? BN : ((n_sz + 15) & ~15);  // UMMA N: multiple of 16 (M = 128)
+            const uint32_t idesc = umma_idesc_bf16(BM, n_sz);
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint32_t a_hi = sbase, a_lo = sbase + A_TILE_BYTES;
-                    const uint32_t w_hi = sbase + 2 * A_TILE_BYTES, w_lo = w_hi + W_TILE_BYTES;
+                const uint32_t sbase = smem_u32(smem) + (uint32_t)stage * STAGE_BYTES;
+                const uint64_t da_hi = umma_desc_k_sw128(sbase), da_lo = umma_desc_k_sw128(sbase + A_TILE_BYTES);
+                const uint64_t dw_hi = umma_desc_k_sw128(sbase + 2 * A_TILE_BYTES);
+                const uint64_t dw_lo = umma_desc_k_sw128(sbase + 2 * A_TILE_BYTES + W_TILE_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t off = (uint32_t)k * UMMA_K * 2;  // 32 bytes along K inside the swizzle row
-                        const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-                        umma_bf16(d_tmem, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(w_hi + off), idesc, first);
+                        umma_bf16(d_tmem, umma_desc_advance(da_hi, k), umma_desc_advance(dw_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         if (p.n_terms == 3) {
-                            umma_bf16(d_tmem, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(w_lo + off), idesc, 1u);
-                            umma_bf16(d_tmem, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(w_hi + off), idesc, 1u);
+                            umma_bf16(d_tmem, umma_desc_advance(da_hi, k), umma_desc_advance(dw_lo, k), idesc, 1u);
+                            umma_bf16(d_tmem, umma_desc_advance(da_lo, k), umma_desc_advance(dw_hi, k), idesc, 1u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // slot free once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);  // accumulator complete
                 }
-                umma_commit(&acc_full[acc]);  // accumulator complete
-                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kEpiWarp0) {
         // ================= epilogue =================
