@@ -6,8 +6,8 @@ dev = torch.device('cuda:0')
 def run(name, flow, B, D, C):
     flow = flow.to(dev)
     x = torch.randn(B, D, device=dev); c = torch.randn(B, C, device=dev) if C else None
-    d = flow(c); d.log_prob(x[:4096]); torch.cuda.synchronize()
-    d.log_prob(x); torch.cuda.synchronize()
+    flow(None if c is None else c[:4096]).log_prob(x[:4096]); torch.cuda.synchronize()
+    d = flow(c); d.log_prob(x); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3): lp = d.log_prob(x)
