@@ -14,19 +14,46 @@ constexpr float kHalfLog2Pi = 0.9189385332046727f;
 // ---------------------------------------------------------------------------
 // scalar math, FAST = MUFU approximations (rcp / ex2 / lg2), else IEEE
 // ---------------------------------------------------------------------------
+// The MUFU approximations are issued in their .ftz form through inline PTX: the plain
+// `__fdividef` / `exp2f` / `__log2f` intrinsics compile (without -ftz=true) to the MUFU plus a
+// predicated rescaling sequence for denormal operands — FSETP + 2-3 FMUL around every one of the
+// ~43 MUFUs of a spline evaluation, a quarter of its instructions.  None of the operands here can
+// be denormal: soft-clip denominators are >= 1, softmax sums >= K * slope^(1/2), bin widths and
+// the rational's denominator are bounded below through the min-slope 1e-3, exponents lie in
+// [-10, 10].
+__device__ __forceinline__ float rcp_ftz(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ex2_ftz(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float lg2_ftz(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+template <bool FAST>
+__device__ __forceinline__ float zrcp(float b) {
+    if constexpr (FAST) return rcp_ftz(b);
+    return 1.0f / b;
+}
 template <bool FAST>
 __device__ __forceinline__ float zdiv(float a, float b) {
-    if constexpr (FAST) return __fdividef(a, b);
+    if constexpr (FAST) return a * rcp_ftz(b);
     return a / b;
 }
 template <bool FAST>
 __device__ __forceinline__ float zexp(float v) {
-    if constexpr (FAST) return exp2f(v * kLog2e);  // ex2.approx after one FMUL
+    if constexpr (FAST) return ex2_ftz(v * kLog2e);
     return expf(v);
 }
 template <bool FAST>
 __device__ __forceinline__ float zlog(float v) {
-    if constexpr (FAST) return __log2f(v) * kLn2;
+    if constexpr (FAST) return lg2_ftz(v) * kLn2;
     return logf(v);
 }
 // v / (1 + |v| * a)   — the soft clip of transforms.py:480-482 with a = 2/|ln slope| (w, h)
@@ -125,15 +152,29 @@ __device__ __forceinline__ Bin rqs_select(const float* __restrict__ p, int Krt, 
 template <bool FAST>
 __device__ __forceinline__ void rqs_forward_eval(const Bin& b, float x, float& y, float& ladj) {
     const float dx = b.dx, dy = b.dy;
-    const float s = zdiv<FAST>(dy, dx);
-    const float z = zdiv<FAST>(x - b.x0, dx);
+    float s, z;
+    if constexpr (FAST) {  // one reciprocal of the bin width serves the slope and the position
+        const float rdx = rcp_ftz(dx);
+        s = dy * rdx;
+        z = (x - b.x0) * rdx;
+    } else {
+        s = dy / dx;
+        z = (x - b.x0) / dx;
+    }
     const float omz = 1.f - z;
     const float z1 = z * omz;
     const float den = fmaf(b.d0 + b.d1 - 2.f * s, z1, s);
     const float num = fmaf(s * z, z, b.d0 * z1);
-    const float yy = fmaf(dy, zdiv<FAST>(num, den), b.y0);
     const float jn = s * s * (2.f * s * z1 + b.d0 * omz * omz + b.d1 * z * z);
-    const float lj = zlog<FAST>(zdiv<FAST>(jn, den * den));
+    float yy, lj;
+    if constexpr (FAST) {  // and one reciprocal of the denominator serves y and the Jacobian
+        const float rden = rcp_ftz(den);
+        yy = fmaf(dy, num * rden, b.y0);
+        lj = lg2_ftz(jn * rden * rden) * kLn2;
+    } else {
+        yy = fmaf(dy, num / den, b.y0);
+        lj = logf(jn / (den * den));
+    }
     y = b.inside ? yy : x;
     // outside the domain the reference yields mask * log(jac) = 0 for finite x and NaN for
     // non-finite x (0 * inf); (x - x) reproduces exactly that.
