@@ -11,7 +11,7 @@ flow = flow.to(dev)
 B = 1 << 20
 x = torch.randn(B, 16, device=dev); c = torch.randn(B, 8, device=dev)
 flow(c).log_prob(x); torch.cuda.synchronize()
-buf = torch.zeros(256, dtype=torch.int64, device=dev)
+buf = torch.zeros(512, dtype=torch.int64, device=dev)
 E.lib().zk_debug_timeline(buf.data_ptr())
 flow(c).log_prob(x); torch.cuda.synchronize()
 E.lib().zk_debug_timeline(None)
@@ -23,12 +23,17 @@ for l in range(4):
 for l in range(3):
     for ch in range(2):
         b = 64 + 16*l + 4*ch
-        names[b] = f'epi L{l}c{ch}: d_full seen'; names[b+1] = f'epi L{l}c{ch}: computed'; names[b+2] = f'epi L{l}c{ch}: layer_done seen'; names[b+3] = f'epi L{l}c{ch}: A written'
+        names[b] = f'epi L{l}c{ch}: d_full seen'; names[b+1] = f'epi L{l}c{ch}: computed'; names[b+2] = f'epi L{l}c{ch}: a_free seen'; names[b+3] = f'epi L{l}c{ch}: A written'
 for ch in range(8):
     names[160+2*ch] = f'epi last c{ch}: d_full seen'; names[161+2*ch] = f'epi last c{ch}: dims done'
 for kb in range(4):
     names[200+3*kb] = f'mma L1c1 kb{kb}: waiting w_full'; names[201+3*kb] = f'mma L1c1 kb{kb}: w_full seen'; names[202+3*kb] = f'mma L1c1 kb{kb}: issued+committed'
     names[220+3*kb] = f'producer L1c1 kb{kb}: waiting w_empty'; names[221+3*kb] = f'producer L1c1 kb{kb}: w_empty seen'; names[222+3*kb] = f'producer L1c1 kb{kb}: TMA issued'
+for l in range(4):
+    names[100+l] = f'mma L{l}: reached layer start'; names[104+l] = f'mma L{l}: d_empty seen'
+for l in range(3):
+    for ch in range(2): names[110+2*l+ch] = f'epi(warp 19) L{l}c{ch}: A written'
 names[240]='epi L1c1: LDTM + wait::ld done'; names[241]='epi L1c1: d_empty arrived'; names[242]='epi L1c1: STTM issued'; names[243]='epi L1c1: wait::st done'
+for i in range(256, 512): names[i] = f'mma: schedule entry {i - 256} issued + committed'
 ev = sorted((int(v - t0), names.get(i, str(i))) for i, v in enumerate(t) if v != 0)
 for dt, n in ev: print(f'{dt:8d}  {n}')

@@ -63,7 +63,7 @@ constexpr int F_IN_MAXF = 64;       // floats per row of the staged input (D + C
 constexpr int F_BIAS_MAXF = 5120;   // floats of bias kept in shared memory (else read from global)
 constexpr uint32_t F_PLANE = FM * FK * 2;       // 16 KB: one plane of one W tile
 constexpr uint32_t F_KBLOCK = 2 * F_PLANE;      // hi + lo
-constexpr uint32_t F_AUX_BYTES = 256 + 3 * 2 * FM * 4;     // 32 barrier slots + ladj partials [2][3][128]
+constexpr uint32_t F_AUX_BYTES = 272 + 3 * 2 * FM * 4;     // 34 barrier slots + ladj partials [2][3][128]
 constexpr uint32_t F_SMEM_MAX = 232448;                    // 227 KB per CTA on sm_100
 constexpr uint32_t TM_ALO = 128, TM_D = 256;    // tensor-memory column map (see header)
 
@@ -74,6 +74,8 @@ struct FusedParams {
     int bias_len[ZK_FUSED_MAX_LINEAR];
     int bias_in_smem;
     uint8_t kbmask[ZK_FUSED_MAX_LINEAR][128];  // [layer][chunk]: K blocks with non-zero weights
+    const uint32_t* sched;  // MMA issue schedule of one tile (device memory), see FusedPack::sched
+    int n_items;
     int n_linear;
     int K0, KB0;        // real input width (D + C) and its number of 64-wide K blocks
     int H, CW;          // hidden width (multiple of 64, <= 256), hidden chunk width (128 or 64)
@@ -93,9 +95,12 @@ struct FusedParams {
     long long* dbg;  // optional timeline buffer (clock64 stamps of CTA 0, third tile), see zk_debug_timeline
 };
 
-#define ZK_STAMP(slot)                                                                  \
-    do {                                                                                \
-        if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on) p.dbg[(slot)] = clock64(); \
+// timeline instrumentation: compiled in only for the DBG instantiation (zk_debug_timeline)
+#define ZK_STAMP(slot)                                                                      \
+    do {                                                                                    \
+        if constexpr (DBG) {                                                                \
+            if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on) p.dbg[(slot)] = clock64(); \
+        }                                                                                   \
     } while (0)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -153,7 +158,7 @@ struct LastCfg<ZK_UNI_RQS, 16> { static constexpr int P = 47, DPC = 2; };
 template <>
 struct LastCfg<ZK_UNI_AFFINE, 0> { static constexpr int P = 2, DPC = 64; };
 
-template <int UNI, int KT, bool FAST>
+template <int UNI, int KT, bool FAST, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
@@ -175,11 +180,11 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     uint64_t* d_full = bars + 16;             // [2]
     uint64_t* d_empty = bars + 18;            // [2]
     uint64_t* a_ready = bars + 20;            // [4]  K block kb of the A operand written
-    uint64_t* layer_done = bars + 24;         // [1]  all MMAs issued so far have completed
-    uint64_t* in_full = bars + 25;            // [2]  input rows of a tile landed in s_in[b]
-    uint64_t* in_empty = bars + 27;           // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 29);
-    float* s_part = (float*)(bars + 32);      // [2][3][128] ladj partials of sets 1..3
+    uint64_t* a_free = bars + 24;             // [4]  every MMA of the current layer that reads K block kb of A is complete
+    uint64_t* in_full = bars + 28;            // [2]  input rows of a tile landed in s_in[b]
+    uint64_t* in_empty = bars + 30;           // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 32);
+    float* s_part = (float*)(bars + 34);      // [2][3][128] ladj partials of sets 1..3
     float* s_bias = (float*)((uint8_t*)bars + F_AUX_BYTES);
 
     const int warp = threadIdx.x >> 5;
@@ -196,15 +201,14 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     const int nch_hidden = p.H / p.CW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs
+        for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 2); mbar_init(&w_empty[s], 2); }  // full: producer + scout; empty: both CTAs
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], F_EPI_THREADS);
             mbar_init(&in_full[b], 1);
             mbar_init(&in_empty[b], F_EPI_THREADS);
         }
-        for (int k = 0; k < F_MAXKB; ++k) mbar_init(&a_ready[k], F_EPI_THREADS);
-        mbar_init(layer_done, 1);
+        for (int k = 0; k < F_MAXKB; ++k) { mbar_init(&a_ready[k], F_EPI_THREADS); mbar_init(&a_free[k], 1); }
         fence_mbar_init();
     }
     if (p.bias_in_smem)
@@ -236,7 +240,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                     const int KB = (l == 0) ? p.KB0 : KBH;
                     for (int ch = 0; ch < nch; ++ch) {
                         const int n0 = last ? ch * DPC * P : ch * p.CW;
-                        const uint32_t kbm = p.kbmask[l][ch];
+                        const uint32_t kbm = p.kbmask[l][ch] & ((1u << KB) - 1u);
                         for (int kb = 0; kb < KB; ++kb) {
                             if (!((kbm >> kb) & 1u)) continue;  // all-zero tile of the masked matrix: skipped
                             // the slot is written in BOTH CTAs: wait until both MMA issuers released it
@@ -259,74 +263,96 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        // The whole warp walks the (warp-uniform) loops and waits on the barriers; one elected lane
+        // The whole warp walks the tile's issue schedule (FusedPack::sched, one entry per non-zero
+        // (layer, chunk, K block) tile in the order the W producer streams them); one elected lane
         // issues the MMAs and commits.  (Issuing from inside an `if (lane == 0)` region made ptxas
         // wrap every UTCHMMA in an ELECT / BRA.U.ANY waterfall loop: ~110 cycles per MMA.)
-        int ws = 0;
-        uint32_t wph = 0, chunk = 0, a_par = 0;  // a_par: bit kb = parity of a_ready[kb]
-        for (int mma_tile = 0; mma_tile < n_iter; ++mma_tile) {
-            const bool stamp_on = (mma_tile == 2) && (lane == 0);
-            for (int l = 0; l < L; ++l) {
-                const bool last = (l == L - 1);
-                const int nch = last ? p.n_last_chunks : nch_hidden;
-                const int KB = (l == 0) ? p.KB0 : KBH;
-                const uint32_t idesc = umma_idesc_bf16(FM, last ? N_LAST : p.CW);
-                uint32_t waited = 0;  // K blocks of this layer whose a_ready phase has been consumed
-                for (int ch = 0; ch < nch; ++ch, ++chunk) {
-                    const uint32_t buf = chunk & 1u;
-                    mbar_wait(&d_empty[buf], ((chunk >> 1) & 1u) ^ 1u);
-                    const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
-                    const uint32_t kbm = p.kbmask[l][ch];
-                    const int kb_last = 31 - __clz((int)kbm);  // kbm != 0 (host guarantees)
-                    bool first = true;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (!((kbm >> kb) & 1u)) continue;  // all-zero tile: nothing to accumulate
-                        if (!((waited >> kb) & 1u)) {  // first use of this K block in this layer
-                            mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
-                            a_par ^= (1u << kb);
-                            waited |= (1u << kb);
-                            if (kb == 0) ZK_STAMP(8 * l + 0);
-                            if (kb == KB - 1) ZK_STAMP(8 * l + 1);
-                        }
-                        if (l == 1 && ch == 1) ZK_STAMP(200 + 3 * kb);
-                        mbar_wait(&w_full[ws], wph);
-                        tc_fence_after();
-                        if (l == 1 && ch == 1) ZK_STAMP(201 + 3 * kb);
-                        if (ch == 0 && first) ZK_STAMP(8 * l + 2);
-                        const uint32_t a_hi = tmem_base + (uint32_t)(kb * (FK / 2)), a_lo = a_hi + TM_ALO;
-                        const uint32_t w_addr = smem_u32(sW) + (uint32_t)ws * F_KBLOCK;
-                        const uint64_t dw_hi = umma_desc_k_sw128(w_addr), dw_lo = umma_desc_k_sw128(w_addr + F_PLANE);
-                        if (elect_one()) {
+        //
+        // The tensor pipe queues only ~4 MMAs (profiles/micro/mma_queue.cu: the issue loop returns
+        // ~290 cycles before the last MMA completes), and this warp shares its scheduler with four
+        // epilogue warps, so every instruction between the last MMA of one entry and the first of the
+        // next starves the pipe.  The issuer therefore waits on ONE barrier per entry: the stage's
+        // w_full, which completes when the TMA bytes have landed AND the scout (warp 2) has seen the
+        // entry's other prerequisites (accumulator buffer drained, A block written).
+        const uint32_t idesc_h = umma_idesc_bf16(FM, p.CW), idesc_l = umma_idesc_bf16(FM, N_LAST);
+        const int n_items = p.n_items;
+        const int total = n_iter * n_items;
+        int ws = 0, j = 0;
+        uint32_t wph = 0, c = 0;  // c: running chunk counter (accumulator buffer = c & 1)
+        uint32_t cur = (total > 0) ? __ldg(p.sched) : 0u;
+        // entry bits: [1:0] kb, [2] first K block of its chunk, [3] last K block of its chunk,
+        // [5] first use of A block kb in this layer (wait a_ready), [6] last reader of A block kb in this
+        // layer (signal a_free), [7] last entry of the layer, [11:8] A blocks the layer never reads
+        // (a_free at the layer's end), [15:12] a_ready phases the layer does not consume by reading
+        // (set on the layer's first entry), [16] output layer
+        for (int i = 0; i < total; ++i) {
+            const bool stamp_on = (i / n_items == 2) && (lane == 0);
+            const int jn = (j + 1 == n_items) ? 0 : j + 1;
+            const uint32_t nxt = __ldg(p.sched + jn);
+            const uint32_t kb = cur & 3u, buf = c & 1u;
+            const uint32_t d_tmem = tmem_base + TM_D + buf * 128u;
+            const uint32_t a_hi = tmem_base + kb * (uint32_t)(FK / 2), a_lo = a_hi + TM_ALO;
+            const uint32_t w_addr = smem_u32(sW) + (uint32_t)ws * F_KBLOCK;
+            const uint64_t dw_hi = umma_desc_k_sw128(w_addr), dw_lo = umma_desc_k_sw128(w_addr + F_PLANE);
+            const uint32_t idesc = (cur & 0x10000u) ? idesc_l : idesc_h;
+            const bool first = (cur & 4u) != 0;
+            while (!mbar_test_wait(&w_full[ws], wph)) {}
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < FK / 16; ++k) {
-                                const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
-                                umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
-                                if (p.n_terms == 3) {
-                                    umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
-                                    umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_advance(dw_hi, k), idesc, 1u);
-                                }
-                            }
-                            umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
-                            if (kb == kb_last) {
-                                umma_commit(&d_full[buf]);
-                                if (ch == nch - 1) umma_commit(layer_done);
-                            }
-                        }
-                        __syncwarp();
-                        first = false;
-                        if (l == 1 && ch == 1) ZK_STAMP(202 + 3 * kb);
-                        if (++ws == NW) { ws = 0; wph ^= 1; }
+                for (int k = 0; k < FK / 16; ++k) {
+                    const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
+                    umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
+                    if (p.n_terms == 3) {
+                        umma_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
+                        umma_bf16_ts(d_tmem, a_lo + acol, umma_desc_advance(dw_hi, k), idesc, 1u);
                     }
-                    if (ch == nch - 1) {
-                        // K blocks no chunk of this layer read: still consume their a_ready phase
-                        for (int kb = 0; kb < KB; ++kb)
-                            if (!((waited >> kb) & 1u)) {
-                                mbar_wait(&a_ready[kb], (a_par >> kb) & 1u);
-                                a_par ^= (1u << kb);
-                            }
-                    }
-                    if (ch == nch - 1) ZK_STAMP(8 * l + 3);
                 }
+                umma_commit_mc(&w_empty[ws], (uint16_t)3);  // releases the slot in both CTAs
+                // a_free[kb] completes exactly once per layer: when the last MMA of the layer reading
+                // K block kb of the A operand is done, the epilogue may overwrite that block with the
+                // next layer's activations while the rest of the layer is still being multiplied
+                if (cur & 64u) umma_commit(&a_free[kb]);
+                if (cur & 8u) umma_commit(&d_full[buf]);
+                if (cur & 128u) {  // blocks the layer does not read are released at its END: the epilogue
+                                   // has consumed their previous phase by then (parity waits alias after two)
+#pragma unroll
+                    for (uint32_t k2 = 0; k2 < (uint32_t)F_MAXKB; ++k2)
+                        if ((cur >> (8 + k2)) & 1u) umma_commit(&a_free[k2]);
+                }
+            }
+            __syncwarp();
+            if constexpr (DBG)
+                if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on && j < 240) p.dbg[256 + j] = clock64();
+            c += (nxt >> 2) & 1u;
+            cur = nxt;
+            j = jn;
+            if (++ws == NW) { ws = 0; wph ^= 1u; }
+        }
+    } else if (warp == 2) {
+        // ======================= scout =======================
+        // Walks the same schedule ahead of the MMA issuer and turns every entry's prerequisites other
+        // than the weights into the second arrival on the stage's w_full barrier.
+        if (lane == 0) {
+            const int n_items = p.n_items;
+            const int total = n_iter * n_items;
+            int ws = 0, j = 0;
+            uint32_t wph = 0, c = 0, a_par = 0;  // a_par: bit kb = parity of a_ready[kb]
+            for (int i = 0; i < total; ++i) {
+                const uint32_t it = __ldg(p.sched + j);
+                if (i > 0) c += (it >> 2) & 1u;
+                // the slot's previous phase must be complete (and consumed by both CTAs) before this
+                // phase may receive an arrival
+                mbar_wait(&w_empty[ws], wph ^ 1u);
+                if (it & 4u) mbar_wait(&d_empty[c & 1u], ((c >> 1) & 1u) ^ 1u);
+                if (it & 0xF000u) {  // A blocks this layer never reads: their a_ready phase is consumed here
+                    for (uint32_t k2 = 0; k2 < (uint32_t)F_MAXKB; ++k2)
+                        if ((it >> (12 + k2)) & 1u) { mbar_wait(&a_ready[k2], (a_par >> k2) & 1u); a_par ^= 1u << k2; }
+                }
+                if (it & 32u) { mbar_wait(&a_ready[it & 3u], (a_par >> (it & 3u)) & 1u); a_par ^= 1u << (it & 3u); }
+                mbar_arrive(&w_full[ws]);
+                if (++j == n_items) j = 0;
+                if (++ws == NW) { ws = 0; wph ^= 1u; }
             }
         }
     } else if (warp == 3) {
@@ -359,7 +385,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         const int q = warp & 3;                   // TMEM lane quadrant
         const int r = q * 32 + lane;              // row inside the tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t chunk = 0, ld_par = 0;
+        uint32_t chunk = 0, f_par = 0;  // f_par: bit kb = parity of a_free[kb]
         for (int tile_iter = 0; tile_iter < n_iter; ++tile_iter) {
             const int t = 2 * (cid + tile_iter * ncl) + (int)rank;  // may be >= m_tiles: dummy tile, all rows masked
             const bool stamp_on = (tile_iter == 2) && (threadIdx.x == F_EPI_WARP0 * 32);
@@ -461,9 +487,13 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                     mbar_arrive(&d_empty[buf]);  // accumulator buffer is free again
                     if (l == 1 && ch == 1) ZK_STAMP(241);
                     ZK_STAMP(64 + 16 * l + 4 * ch + 1);
-                    if (ch == 0) {  // the A operand may be overwritten once ALL MMAs of this layer are done
-                        mbar_wait(layer_done, ld_par);
-                        ld_par ^= 1u;
+                    {   // the K blocks this chunk overwrites must have been read by every MMA of this layer
+                        const int kb0 = (p.CW == 128) ? 2 * ch : ch;
+                        const int kb1 = (ch == nch_hidden - 1) ? F_MAXKB : ((p.CW == 128) ? 2 * ch + 2 : ch + 1);
+                        for (int kb = kb0; kb < kb1; ++kb) {  // (the last chunk also consumes the unused blocks' phases)
+                            mbar_wait(&a_free[kb], (f_par >> kb) & 1u);
+                            f_par ^= (1u << kb);
+                        }
                         tc_fence_after();
                     }
                     ZK_STAMP(64 + 16 * l + 4 * ch + 2);
@@ -483,6 +513,9 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         mbar_arrive(&a_ready[ch]);
                     }
                     ZK_STAMP(64 + 16 * l + 4 * ch + 3);
+                    if constexpr (DBG)
+                        if (p.dbg != nullptr && blockIdx.x == 0 && tile_iter == 2 && threadIdx.x == F_THREADS - 32)
+                            p.dbg[110 + 2 * l + ch] = clock64();  // the last epilogue warp's view of "A written"
                 }
             }
 
@@ -564,9 +597,11 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 mbar_arrive(&d_empty[buf]);
                 if (ch < 8) ZK_STAMP(161 + 2 * ch);
             }
-            // all MMAs of this tile are complete once the last layer_done fires: A may be restaged
-            mbar_wait(layer_done, ld_par);
-            ld_par ^= 1u;
+            // all MMAs of this tile are complete once the last layer's a_free phases fire: A may be restaged
+            for (int kb = 0; kb < F_MAXKB; ++kb) {
+                mbar_wait(&a_free[kb], (f_par >> kb) & 1u);
+                f_par ^= (1u << kb);
+            }
             tc_fence_after();
             // ---- per-sample sum: sets 0..2 hand their partials to set 3 without waiting for it ----
             float* part = s_part + (tile_iter & 1) * (3 * FM);
@@ -603,8 +638,9 @@ zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, size_t smem,
         kern<<<grid, F_THREADS, smem, st>>>(p);
         return check_launch("fused_layer_kernel");
     };
-    if (fast) return go(fused_layer_kernel<UNI, KT, true>);
-    return go(fused_layer_kernel<UNI, KT, false>);
+    if (p.dbg != nullptr) return fast ? go(fused_layer_kernel<UNI, KT, true, true>) : go(fused_layer_kernel<UNI, KT, false, true>);
+    if (fast) return go(fused_layer_kernel<UNI, KT, true, false>);
+    return go(fused_layer_kernel<UNI, KT, false, false>);
 }
 
 }  // namespace
@@ -739,6 +775,47 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
             f.kbmask[l][ch] = bits;
         }
     }
+    // ---- MMA issue schedule of one tile: one entry per non-zero (layer, chunk, K block) tile, in the
+    //      order the W producer streams them (bit layout: see the MMA issuer in the kernel) ----
+    std::vector<uint32_t> items;
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        const int nch = std::min(128, last ? (D + DPC - 1) / DPC : H / CW);
+        const int KB = (l == 0) ? pk->layers[0].Kp / 64 : H / 64;
+        int last_reader[F_MAXKB];
+        for (int kb = 0; kb < F_MAXKB; ++kb) last_reader[kb] = -1;
+        for (int ch = 0; ch < nch; ++ch)
+            for (int kb = 0; kb < KB; ++kb)
+                if ((f.kbmask[l][ch] >> kb) & 1u) last_reader[kb] = ch;
+        uint32_t waited = 0;
+        const size_t layer_first = items.size();
+        for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t kbm = f.kbmask[l][ch] & ((1u << KB) - 1u);
+            int hi = 0;
+            for (int kb = 0; kb < KB; ++kb) if ((kbm >> kb) & 1u) hi = kb;
+            bool first = true;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (!((kbm >> kb) & 1u)) continue;
+                uint32_t it = (uint32_t)kb | (first ? 4u : 0u) | (kb == hi ? 8u : 0u);
+                if (!((waited >> kb) & 1u)) { it |= 32u; waited |= 1u << kb; }
+                if (last_reader[kb] == ch) it |= 64u;
+                if (last) it |= 0x10000u;
+                items.push_back(it);
+                first = false;
+            }
+        }
+        uint32_t nofree = 0, unread = 0;
+        for (int kb = 0; kb < F_MAXKB; ++kb) if (last_reader[kb] < 0) nofree |= 1u << kb;
+        for (int kb = 0; kb < KB; ++kb) if (!((waited >> kb) & 1u)) unread |= 1u << kb;
+        items.back() |= 128u | (nofree << 8);
+        items[layer_first] |= unread << 12;
+    }
+    cudaFree(f.sched);
+    f.sched = nullptr;
+    f.n_items = (int)items.size();
+    if (cudaMalloc((void**)&f.sched, items.size() * 4) != cudaSuccess ||
+        cudaMemcpy(f.sched, items.data(), items.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");
     f.uni = univariate; f.bins = bins; f.D = D; f.C = C;
     f.ready = true;
     return ZK_OK;
@@ -755,7 +832,8 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     const FusedPack& f = pk->fused;
     const bool packed = f.ready && f.uni == a.univariate && f.bins == a.bins && f.D == a.D && f.C == a.C;
     memset(p.kbmask, 0xff, sizeof(p.kbmask));  // unprepared handles: every tile is streamed
-    if (packed) memcpy(p.kbmask, f.kbmask, sizeof(p.kbmask));
+    ZK_REQUIRE(packed && f.sched != nullptr, "fused layer: the conditioner was not prepared for this bijector");
+    memcpy(p.kbmask, f.kbmask, sizeof(p.kbmask));
     for (int i = 0; i < m->n_linear; ++i) {
         p.mapW[i] = packed ? f.map64[i] : pk->layers[i].mapW64;
         p.bias[i] = packed ? f.bias[i] : m->b[i];
@@ -797,15 +875,12 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     // clusters of 2 CTAs: even grid, at most one CTA per SM
     const int64_t pairs = ceil_div(ceil_div(a.B, FM), 2);
     const int grid = 2 * (int)std::min<int64_t>(pairs, sm_count() / 2);
-    if (a.univariate == ZK_UNI_RQS && a.bins == 8) {
-        p.n_last_chunks = (a.D + 3) / 4;
-        return launch_fused_t<ZK_UNI_RQS, 8>(p, a.fast_math, grid, smem, st);
-    }
-    if (a.univariate == ZK_UNI_RQS && a.bins == 16) {
-        p.n_last_chunks = (a.D + 1) / 2;
-        return launch_fused_t<ZK_UNI_RQS, 16>(p, a.fast_math, grid, smem, st);
-    }
-    p.n_last_chunks = (a.D + 63) / 64;
+    const bool rqs8 = a.univariate == ZK_UNI_RQS && a.bins == 8, rqs16 = a.univariate == ZK_UNI_RQS && a.bins == 16;
+    p.n_last_chunks = rqs8 ? (a.D + 3) / 4 : (rqs16 ? (a.D + 1) / 2 : (a.D + 63) / 64);
+    p.sched = f.sched;
+    p.n_items = f.n_items;
+    if (rqs8) return launch_fused_t<ZK_UNI_RQS, 8>(p, a.fast_math, grid, smem, st);
+    if (rqs16) return launch_fused_t<ZK_UNI_RQS, 16>(p, a.fast_math, grid, smem, st);
     return launch_fused_t<ZK_UNI_AFFINE, 0>(p, a.fast_math, grid, smem, st);
 }
 

@@ -329,6 +329,7 @@ void tc_destroy(zk_mlp* m) {
     for (auto& l : pk->layers) cudaFree(l.w);
     for (auto* q : pk->fused.w) cudaFree(q);
     for (auto* q : pk->fused.bias) cudaFree(q);
+    cudaFree(pk->fused.sched);
     delete pk;
     m->tc = nullptr;
 }

@@ -138,6 +138,8 @@ struct FusedPack {
     std::vector<float*> bias;       // per layer, permuted, padded (owned)
     std::vector<CUtensorMap> map64; // box (64 x 64 x 1)
     uint8_t kbmask[8][128];         // [layer][chunk]: bit kb = K block kb has non-zero weights
+    uint32_t* sched = nullptr;      // device: MMA issue schedule of one tile, one entry per non-zero tile (owned)
+    int n_items = 0;
 };
 struct TcPack {
     std::vector<TcLayer> layers;
