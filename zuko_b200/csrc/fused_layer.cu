@@ -184,6 +184,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     uint64_t* in_full = bars + 28;            // [2]  input rows of a tile landed in s_in[b]
     uint64_t* in_empty = bars + 30;           // [2]
     uint32_t* tmem_slot = (uint32_t*)(bars + 32);
+    uint32_t* s_ready = tmem_slot + 1;        // number of schedule entries whose prerequisites are all met (scout -> MMA issuer)
     float* s_part = (float*)(bars + 34);      // [2][3][128] ladj partials of sets 1..3
     float* s_bias = (float*)((uint8_t*)bars + F_AUX_BYTES);
 
@@ -201,7 +202,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     const int nch_hidden = p.H / p.CW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 2); mbar_init(&w_empty[s], 2); }  // full: producer + scout; empty: both CTAs
+        for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // empty: both CTAs
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], F_EPI_THREADS);
@@ -209,6 +210,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             mbar_init(&in_empty[b], F_EPI_THREADS);
         }
         for (int k = 0; k < F_MAXKB; ++k) { mbar_init(&a_ready[k], F_EPI_THREADS); mbar_init(&a_free[k], 1); }
+        *s_ready = 0u;
         fence_mbar_init();
     }
     if (p.bias_in_smem)
@@ -271,14 +273,16 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         // The tensor pipe queues only ~4 MMAs (profiles/micro/mma_queue.cu: the issue loop returns
         // ~290 cycles before the last MMA completes), and this warp shares its scheduler with four
         // epilogue warps, so every instruction between the last MMA of one entry and the first of the
-        // next starves the pipe.  The issuer therefore waits on ONE barrier per entry: the stage's
-        // w_full, which completes when the TMA bytes have landed AND the scout (warp 2) has seen the
-        // entry's other prerequisites (accumulator buffer drained, A block written).
+        // next starves the pipe — and an mbarrier probe issued behind pending tcgen05.commits costs
+        // ~100 cycles by itself (profiles/micro/issuer_contention.cu).  The issuer therefore touches no
+        // mbarrier at all: the scout (warp 2) waits for every prerequisite of an entry (weights landed,
+        // accumulator buffer drained, A block written) and publishes the count of ready entries in
+        // shared memory, which the issuer reads with one acquire load.
         const uint32_t idesc_h = umma_idesc_bf16(FM, p.CW), idesc_l = umma_idesc_bf16(FM, N_LAST);
         const int n_items = p.n_items;
         const int total = n_iter * n_items;
         int ws = 0, j = 0;
-        uint32_t wph = 0, c = 0;  // c: running chunk counter (accumulator buffer = c & 1)
+        uint32_t c = 0, seen = 0;  // c: running chunk counter (accumulator buffer = c & 1); seen: cached *s_ready
         uint32_t cur = (total > 0) ? __ldg(p.sched) : 0u;
         // entry bits: [1:0] kb, [2] first K block of its chunk, [3] last K block of its chunk,
         // [5] first use of A block kb in this layer (wait a_ready), [6] last reader of A block kb in this
@@ -296,7 +300,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             const uint64_t dw_hi = umma_desc_k_sw128(w_addr), dw_lo = umma_desc_k_sw128(w_addr + F_PLANE);
             const uint32_t idesc = (cur & 0x10000u) ? idesc_l : idesc_h;
             const bool first = (cur & 4u) != 0;
-            while (!mbar_test_wait(&w_full[ws], wph)) {}
+            while (seen <= (uint32_t)i) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_ready)) : "memory");
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -327,12 +331,12 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             c += (nxt >> 2) & 1u;
             cur = nxt;
             j = jn;
-            if (++ws == NW) { ws = 0; wph ^= 1u; }
+            if (++ws == NW) ws = 0;
         }
     } else if (warp == 2) {
         // ======================= scout =======================
-        // Walks the same schedule ahead of the MMA issuer and turns every entry's prerequisites other
-        // than the weights into the second arrival on the stage's w_full barrier.
+        // Walks the same schedule ahead of the MMA issuer, waits for every entry's prerequisites and
+        // publishes the number of entries that may be issued.
         if (lane == 0) {
             const int n_items = p.n_items;
             const int total = n_iter * n_items;
@@ -341,16 +345,14 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             for (int i = 0; i < total; ++i) {
                 const uint32_t it = __ldg(p.sched + j);
                 if (i > 0) c += (it >> 2) & 1u;
-                // the slot's previous phase must be complete (and consumed by both CTAs) before this
-                // phase may receive an arrival
-                mbar_wait(&w_empty[ws], wph ^ 1u);
                 if (it & 4u) mbar_wait(&d_empty[c & 1u], ((c >> 1) & 1u) ^ 1u);
                 if (it & 0xF000u) {  // A blocks this layer never reads: their a_ready phase is consumed here
                     for (uint32_t k2 = 0; k2 < (uint32_t)F_MAXKB; ++k2)
                         if ((it >> (12 + k2)) & 1u) { mbar_wait(&a_ready[k2], (a_par >> k2) & 1u); a_par ^= 1u << k2; }
                 }
                 if (it & 32u) { mbar_wait(&a_ready[it & 3u], (a_par >> (it & 3u)) & 1u); a_par ^= 1u << (it & 3u); }
-                mbar_arrive(&w_full[ws]);
+                mbar_wait(&w_full[ws], wph);
+                asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_ready)), "r"((uint32_t)(i + 1)) : "memory");
                 if (++j == n_items) j = 0;
                 if (++ws == NW) { ws = 0; wph ^= 1u; }
             }
