@@ -122,13 +122,17 @@ def cuda_time_ms(fn, iters: int, stream=None) -> float:
 
 
 def cpu_reference_adaptive(target_s: float, rows0: int = 1 << 15, max_rows: int = 1 << 22):
-    """Sizes the bounded CPU sample so that it takes about target_s seconds on this host."""
-    rate0, _, _ = cpu_reference_rate(rows0)
-    rows = int(min(max_rows, max(rows0, rate0 * target_s)))
-    rows = 1 << max(10, rows.bit_length() - 1)  # power of two
-    if rows <= rows0:
-        return cpu_reference_rate(rows0) + (rows0,)
-    return cpu_reference_rate(rows) + (rows,)
+    """Sizes the bounded CPU sample so that it takes about target_s seconds on this host (the
+    rate grows with the sample size on a many-core host, so the size is refined twice)."""
+    rows = rows0
+    rate, sec, threads = cpu_reference_rate(rows)
+    for _ in range(3):
+        if sec >= 0.6 * target_s or rows >= max_rows:
+            break
+        want = int(min(max_rows, max(rows * 2, rate * target_s)))
+        rows = 1 << max(10, want.bit_length() - 1)  # power of two
+        rate, sec, threads = cpu_reference_rate(rows)
+    return rate, sec, threads, rows
 
 
 def cpu_reference_rate(rows: int, repeats: int = 1):
@@ -157,8 +161,12 @@ def run_reference(args) -> None:
         return
     # one step = a bounded sample of the workload, sized for ~4 s per step on this host
     rate0, _, threads = cpu_reference_rate(1 << 15)  # also the warm-up
-    rows = args.cpu_rows or (1 << max(15, int(rate0 * 4.0).bit_length() - 1))
-    rows = min(rows, 1 << 22)
+    rows = args.cpu_rows
+    if not rows:  # refine once: the rate grows with the sample size on a many-core host
+        rows = min(1 << 22, 1 << max(15, int(rate0 * 4.0).bit_length() - 1))
+        rate1, sec1, _ = cpu_reference_rate(rows)
+        if sec1 < 2.0:
+            rows = min(1 << 22, 1 << max(15, int(rate1 * 4.0).bit_length() - 1))
     times = []
     for _ in range(args.steps):
         rate, sec, threads = cpu_reference_rate(rows)
