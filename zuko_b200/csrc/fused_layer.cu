@@ -38,6 +38,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -164,7 +165,6 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
     constexpr int P = Cfg::P, DPC = Cfg::DPC;
     constexpr int N_LAST = (DPC * P + 15) & ~15;  // MMA N of a last-layer chunk
-    constexpr int DA = (DPC + 1) / 2;             // dims of a chunk handled by the first set of the pair
     static_assert(N_LAST <= 128, "a last-layer chunk must fit one accumulator buffer");
 
     extern __shared__ uint8_t smem_raw[];
@@ -529,9 +529,18 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                 mbar_wait(&d_full[buf], (chunk >> 1) & 1u);
                 tc_fence_after();
                 if (ch < 8) ZK_STAMP(160 + 2 * ch);
-                const bool mine = ((int)buf == (s >> 1));  // the set pair that owns this chunk
-                const int h = s & 1;                       // which half of the chunk's dims
+                // SPC sets share a chunk (all four when it holds >= 4 dims, else the set pairs alternate
+                // chunks).  Every thread first pulls the raw parameters of its dims out of tensor memory
+                // and releases the accumulator buffer, THEN evaluates: the MMAs of chunk c + 2 never
+                // wait for the spline evaluation of chunk c.
+                constexpr int SPC = (DPC >= 4) ? 4 : 2;
+                const bool mine = (SPC == 4) || ((int)buf == (s >> 1));
+                const int h = (SPC == 4) ? s : (s & 1);  // which share of the chunk's dims
                 const uint32_t td = t_lane + TM_D + buf * 128u;
+                auto release = [&]() {
+                    tc_fence_before();
+                    mbar_arrive(&d_empty[buf]);
+                };
                 auto finish_dim = [&](int d, float yv, float lj) {
                     if (p.y) p.y[row * p.ldy + d] = yv;
                     if (p.log_prob) {
@@ -543,7 +552,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                     lsum += lj;
                 };
                 if constexpr (UNI == ZK_UNI_RQS) {
-                    // one dim at a time: load the 16-column-aligned window covering its P parameters
+                    static_assert(DPC == SPC, "one dim per set and chunk");
+                    // load the 16-column-aligned window covering the dim's P parameters
                     auto do_dim = [&](auto dloc_c) {
                         constexpr int dloc = decltype(dloc_c)::value;
                         constexpr int c_lo = dloc * P, c_hi = c_lo + P;  // columns inside the chunk
@@ -556,6 +566,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         if constexpr (wn > 32) tmem_ld_x16(td + (uint32_t)(w0 + 32), rr + 32);
                         if constexpr (wn > 48) tmem_ld_x16(td + (uint32_t)(w0 + 48), rr + 48);
                         tmem_ld_wait();
+                        release();
                         const int d = ch * DPC + dloc;
                         if (d >= p.D || !row_ok) return;
                         float pp[P];
@@ -568,35 +579,37 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                         rqs_forward_eval<FAST>(b, xv, yv, lj);
                         finish_dim(d, yv, lj);
                     };
-                    if (mine) {
-                        if (h == 0) for_range<0, DA>(do_dim);
-                        else for_range<DA, DPC - DA>(do_dim);
+                    if (!mine) release();
+                    else if (h == 0) do_dim(std::integral_constant<int, 0>{});
+                    else if (h == 1) do_dim(std::integral_constant<int, 1>{});
+                    else if constexpr (SPC == 4) {
+                        if (h == 2) do_dim(std::integral_constant<int, 2>{});
+                        else do_dim(std::integral_constant<int, 3>{});
                     }
                 } else {
                     // affine: 8 dims (16 columns: shift, scale pairs) per load; this set takes the
-                    // 4 groups [4 h, 4 h + 4) of the chunk's 8 groups
-                    if (mine) {
+                    // 2 groups [2 h, 2 h + 2) of the chunk's 8 groups
+                    static_assert(SPC == 4 && DPC == 64, "affine chunk layout");
+                    uint32_t rr[2][16];
+                    tmem_ld_x16(td + (uint32_t)((h * 2) * 16), rr[0]);
+                    tmem_ld_x16(td + (uint32_t)((h * 2 + 1) * 16), rr[1]);
+                    tmem_ld_wait();
+                    release();
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int c0 = (h * 4 + g) * 16;
-                            uint32_t rr[16];
-                            tmem_ld_x16(td + (uint32_t)c0, rr);
-                            tmem_ld_wait();
+                    for (int g = 0; g < 2; ++g) {
+                        const int c0 = (h * 2 + g) * 16;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int d = ch * DPC + (c0 >> 1) + j;
-                                if (d < p.D && row_ok) {
-                                    const float shift = __uint_as_float(rr[2 * j]) + bias[2 * d];
-                                    const float ls = softclip<FAST>(__uint_as_float(rr[2 * j + 1]) + bias[2 * d + 1], p.ad);
-                                    const float xv = p.in_tma ? sx[r * p.D + d] : p.x[row * p.ldx + d];
-                                    finish_dim(d, fmaf(xv, zexp<FAST>(ls), shift), ls);
-                                }
+                        for (int j = 0; j < 8; ++j) {
+                            const int d = ch * DPC + (c0 >> 1) + j;
+                            if (d < p.D && row_ok) {
+                                const float shift = __uint_as_float(rr[g][2 * j]) + bias[2 * d];
+                                const float ls = softclip<FAST>(__uint_as_float(rr[g][2 * j + 1]) + bias[2 * d + 1], p.ad);
+                                const float xv = p.in_tma ? sx[r * p.D + d] : p.x[row * p.ldx + d];
+                                finish_dim(d, fmaf(xv, zexp<FAST>(ls), shift), ls);
                             }
                         }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&d_empty[buf]);
                 if (ch < 8) ZK_STAMP(161 + 2 * ch);
             }
             // all MMAs of this tile are complete once the last layer's a_free phases fire: A may be restaged
