@@ -56,52 +56,89 @@ def measured_peaks() -> dict:
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU WHILE the timed region runs: an NVML
+    polling thread (2 ms period, so even a 40 ms region gets samples); `nvidia-smi -lms` is the
+    fallback when NVML cannot be initialised."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int) -> None:
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber devices: address the GPU by UUID
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            return N, N.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return N, N.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll_nvml(self, N, h):
+        bits = [N.nvmlClocksEventReasonHwSlowdown, N.nvmlClocksEventReasonHwThermalSlowdown,
+                N.nvmlClocksEventReasonSwThermalSlowdown, N.nvmlClocksEventReasonSwPowerCap]  # fmt: skip
+        smax = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append([sm, smax, [n for n, b in zip(self.NAMES, bits) if r & b]])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
+            N, h = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll_nvml, args=(N, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return self
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
+            self.source = "nvidia-smi"
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([s.strip() for s in line.split(",")])
+            r = [s.strip() for s in line.split(",")]
+            try:
+                self.rows.append([float(r[0]), float(r[1]), [n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")]])
+            except (ValueError, IndexError):
+                continue
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self) -> dict:
-        sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax = max(smax, float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                continue
+        sm = [r[0] for r in self.rows]
+        smax = max((r[1] for r in self.rows), default=0.0)
+        reasons = sorted({n for r in self.rows for n in r[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}  # fmt: skip
+                "reasons": reasons, "samples": len(sm), "source": self.source}  # fmt: skip
 
 
 def cuda_time_ms(fn, iters: int, stream=None) -> float:

@@ -129,3 +129,79 @@ def assert_log_prob_parity(ours, g: dict, rtol: float = 1e-5):
         f"log_prob parity: sample {worst}: ours={ours[worst]!r} ref64={ref64[worst]!r} ref32={ref32[worst]!r} "
         f"err={err[worst]:.3e} tol={tol[worst]:.3e}"
     )
+
+
+# --------------------------------------------------------------------------- #
+# gradients
+# --------------------------------------------------------------------------- #
+
+GRAD_CASES_FULL = ["cfg1_maf", "nsf35_row", "maf35_batch", "nice35", "nsf5_passes2", "maf5_randperm",
+                   "nsf1_elementwise", "nsf6_stress", "composed", "composed_uncond"]  # fmt: skip
+GRAD_CASES_SAMPLED = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
+GRAD_SAMPLE = 2048
+
+
+def grad_sample_idx(n: int) -> np.ndarray:
+    """Mirror of tests/golden/make_golden_grad.py:sample_idx."""
+    if n <= GRAD_SAMPLE:
+        return np.arange(n)
+    return (np.arange(GRAD_SAMPLE, dtype=np.int64) * (n // GRAD_SAMPLE)) % n
+
+
+def grad_inputs(name: str):
+    """(golden-grad dict, x, c) of a gradient case: the first `rows` rows of the forward case."""
+    gg = load(f"grad_{name}")
+    g = load(f"flow_{name}")
+    rows = int(gg["rows"])
+    x = g["x"][:rows]
+    c = g.get("c")
+    if c is not None and c.ndim == 2:
+        c = c[:rows]
+    return gg, x, c
+
+
+def oracle_named_grads(flow, layer_grads) -> dict:
+    """Maps oracle_grad.LayerGrads (one per member of the composed transform) onto the
+    state-dict parameter names of the flow module."""
+    out = {}
+    for i, (t, lg) in enumerate(zip(flow.transform.transforms, layer_grads, strict=True)):
+        pre = f"transform.transforms.{i}."
+        if lg.hyper is not None:
+            lins = [(j, m) for j, m in enumerate(t.hyper) if hasattr(m, "weight")]
+            for (j, m), gw, gb in zip(lins, lg.hyper.weights, lg.hyper.biases, strict=True):
+                out[f"{pre}hyper.{j}.weight"] = np.asarray(gw).reshape(-1)
+                if m.bias is not None:
+                    out[f"{pre}hyper.{j}.bias"] = np.asarray(gb).reshape(-1)
+        if lg.phi is not None:
+            col = 0
+            D = lg.phi.shape[0]
+            for k, p in enumerate(t.phi):
+                w = int(np.prod(p.shape[1:])) if p.dim() > 1 else 1
+                out[f"{pre}phi.{k}"] = np.asarray(lg.phi[:, col : col + w]).reshape(-1)
+                col += w
+            assert col == lg.phi.shape[1] and D == t.features
+    return out
+
+
+def assert_param_grads(named: dict, gg: dict, prefix: str, rtol: float, what: str = ""):
+    """Compares a name -> flat-gradient dict with the golden gradients (full or sampled).
+    Error is measured relative to the largest entry of each tensor's golden gradient
+    (`|ours - ref| <= rtol * max|ref|`), the natural scale of a summed-over-batch gradient."""
+    checked = 0
+    for key in gg:
+        if key.startswith(prefix + "pg/"):
+            name, ref, full = key[len(prefix) + 3 :], gg[key], True
+        elif key.startswith(prefix + "pg_sample/"):
+            name, ref, full = key[len(prefix) + 10 :], gg[key], False
+        else:
+            continue
+        assert name in named, f"{what}: no gradient produced for {name}"
+        ours = np.asarray(named[name], dtype=np.float64).reshape(-1)
+        if not full:
+            ours = ours[grad_sample_idx(ours.size)]
+        scale = max(float(np.abs(ref).max()), 1e-30)
+        err = float(np.abs(ours - ref).max()) / scale
+        assert err <= rtol, f"{what}: d/d{name}: max err {err:.3e} of max|grad| {scale:.3e} (bar {rtol:.1e})"
+        checked += 1
+    assert checked > 0, f"{what}: golden file holds no parameter gradients under {prefix}"
+    return checked
