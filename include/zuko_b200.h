@@ -220,6 +220,71 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* flow, const float* x_host, i
                                 double* sum_log_prob_host, void* workspace, size_t workspace_bytes,
                                 zk_stream stream);
 
+/* ------------------------------------------------------------------------- *
+ * Backward pass (reverse mode) — what torch.autograd computes for the reference
+ * when a training loop calls (-flow(c).log_prob(x).mean()).backward()
+ * (README.md:43-49, tests/test_flows.py:22-29), SURVEY section 8(f) rank 1.
+ * The forward activations are recomputed inside the call (nothing is saved by the
+ * forward entry points).  Parameter gradients are ACCUMULATED (+=) into caller
+ * buffers with the shapes of the reference's parameters, so a batch processed in
+ * several calls / row chunks sums up like autograd's .grad does; grad_x is
+ * overwritten.  Gradients w.r.t. a masked weight are w.r.t. the RAW weight
+ * (already multiplied by the mask, nn.py:218).  Reductions over the batch run in a
+ * fixed order (bit-reproducible run to run).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    float* const* grad_weight; /* host array [n_linear] of DEVICE (dims[i+1], dims[i]) buffers; NULL array / entries = not wanted */
+    float* const* grad_bias;   /* host array [n_linear] of DEVICE (dims[i+1]) buffers; NULL array / entries = not wanted */
+    float* grad_phi;           /* DEVICE (D, P): element-wise layer with a shared table (gaussianization.py:74-77) */
+    float* grad_rotation;      /* DEVICE (D, D): dL/dR of a rotation layer (the caller chains through matrix_exp) */
+} zk_layer_grads;
+
+/* d/d(x, phi) of MonotonicRQSTransform(*phi).call_and_ladj(x) (transforms.py:469-567) for upstream
+ * gradients grad_y (B, D) and grad_ladj (B, of the per-sample summed ladj); either may be NULL (= 0).
+ * grad_phi: (B, D*P) per-sample gradients when phi_ld != 0 (may alias phi when phi_ld == D*P), or the
+ * (D, P) table gradient, ACCUMULATED, when phi_ld == 0.  grad_x / grad_phi may be NULL.
+ * workspace >= zk_univariate_backward_workspace_bytes(B, D, P, phi_ld). */
+size_t zk_univariate_backward_workspace_bytes(int64_t B, int D, int P, int64_t phi_ld);
+zk_status zk_rqs_backward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld, int64_t B,
+                          int D, int K, float bound, float slope, const float* grad_y, int64_t ldgy,
+                          const float* grad_ladj, float* grad_x, int64_t ldgx, float* grad_phi,
+                          void* workspace, size_t workspace_bytes, zk_stream stream);
+/* same for MonotonicAffineTransform (transforms.py:426-446), P = 2 */
+zk_status zk_affine_backward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld, int64_t B,
+                             int D, float slope, const float* grad_y, int64_t ldgy,
+                             const float* grad_ladj, float* grad_x, int64_t ldgx, float* grad_phi,
+                             void* workspace, size_t workspace_bytes, zk_stream stream);
+/* SoftclipTransform (transforms.py:299-316) */
+zk_status zk_softclip_backward(const float* x, int64_t ldx, int64_t B, int D, float bound,
+                               const float* grad_y, int64_t ldgy, const float* grad_ladj,
+                               float* grad_x, int64_t ldgx, zk_stream stream);
+
+/* Reverse mode of zk_layer_forward: given x, c and the upstream gradients grad_y (B, D) and
+ * grad_ladj (B, may be NULL), writes grad_x (B, D) and accumulates the parameter gradients
+ * selected in `grads` (may be NULL) and, when grad_c != NULL, the context gradient: += into
+ * (B, C) rows (ldgc >= C), or into ONE row (C) holding the sum over the batch when ldc == 0. */
+size_t zk_layer_backward_workspace_bytes(const zk_layer* layer, int64_t B);
+zk_status zk_layer_backward(const zk_layer* layer, const float* x, int64_t ldx, const float* c,
+                            int64_t ldc, int64_t B, const float* grad_y, int64_t ldgy,
+                            const float* grad_ladj, float* grad_x, int64_t ldgx, float* grad_c,
+                            int64_t ldgc, const zk_layer_grads* grads, void* workspace,
+                            size_t workspace_bytes, zk_stream stream);
+
+/* Reverse mode of zk_flow_forward and / or zk_flow_log_prob in one call:
+ *   L = <grad_z, z> + <grad_ladj, ladj> + <grad_log_prob, log_prob>      (each may be NULL)
+ * writes grad_x (B, D) (may be NULL), OVERWRITES grad_c ((B, C) rows, or one summed row when
+ * ldc == 0; may be NULL) and accumulates parameter gradients: grads[i] belongs to layers[i]
+ * (array or entries may be NULL).  Any workspace >= zk_flow_backward_min_workspace_bytes() is
+ * accepted: the batch is processed in row chunks that fit. */
+size_t zk_flow_backward_workspace_bytes(const zk_flow_desc* flow, int64_t B);
+size_t zk_flow_backward_min_workspace_bytes(const zk_flow_desc* flow);
+zk_status zk_flow_backward(const zk_flow_desc* flow, const float* x, int64_t ldx, const float* c,
+                           int64_t ldc, int64_t B, const float* grad_z, int64_t ldgz,
+                           const float* grad_ladj, const float* grad_log_prob, float* grad_x,
+                           int64_t ldgx, float* grad_c, int64_t ldgc,
+                           const zk_layer_grads* const* grads, void* workspace,
+                           size_t workspace_bytes, zk_stream stream);
+
 /* Transcendental arithmetic of the bijector kernels: 1 (default) = MUFU rcp / ex2 / lg2
  * approximations, 0 = IEEE division + expf / logf.  Process-wide; returns the previous
  * value.  Both settings meet the 1e-5 parity bar on the BASELINE configs (tests/). */

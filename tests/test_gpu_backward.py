@@ -1,0 +1,230 @@
+"""GPU tests of the backward pass: gradients of ``flow(c).log_prob(x)`` and of
+``flow(c).transform.call_and_ladj(x)`` through the public API (torch.autograd -> zk_flow_backward)
+against gradients that torch.autograd produced on the UNMODIFIED reference in fp64
+(tests/golden/grad_*.npz) and against the gradient oracle (oracle/oracle_grad.py).
+
+Bar: every gradient tensor within ``rtol`` of the golden one relative to its largest entry
+(gradients are sums over the batch; fp32 accumulation of 32-256 rows and an fp32 conditioner keep
+them at ~1e-6; the bar is 2e-5, 1e-3 for the stress set with x3 weights whose spline is
+ill-conditioned in fp32).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from cases import (
+    GRAD_CASES_FULL,
+    GRAD_CASES_SAMPLED,
+    assert_param_grads,
+    build_flow,
+    grad_inputs,
+    load,
+    oracle_named_grads,
+)
+from oracle import oracle as O
+from oracle import oracle_grad as OG
+from zuko_b200 import _engine as E
+from zuko_b200.transforms import MonotonicAffineTransform, MonotonicRQSTransform, SoftclipTransform
+
+pytestmark = pytest.mark.gpu
+U = load("units")
+GU = load("grad_units")
+
+
+def dev_t(a, device, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+    return t.requires_grad_() if grad else t
+
+
+def cpu(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def close(ours, ref, rtol, what):
+    ours, ref = np.asarray(ours, np.float64), np.asarray(ref, np.float64)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(ours - ref).max()) / scale
+    assert err <= rtol, f"{what}: max err {err:.3e} of max|ref| {scale:.3e} (bar {rtol:.1e})"
+
+
+def named_param_grads(flow):
+    return {n: cpu(p.grad).reshape(-1) for n, p in flow.named_parameters() if p.grad is not None}
+
+
+# --------------------------------------------------------------------------- #
+# stand-alone bijectors: zk_rqs_backward / zk_affine_backward / zk_softclip_backward
+# --------------------------------------------------------------------------- #
+
+
+@pytest.mark.parametrize("tag,tol", [("s01", 2e-5), ("s1", 5e-5), ("s3", 2e-3)])
+def test_rqs_backward_per_sample(device, tag, tol):
+    K = 8
+    x = dev_t(GU[f"rqs_{tag}_x"], device, grad=True)
+    phi = dev_t(U[f"rqs_{tag}_phi"], device, grad=True)
+    t = MonotonicRQSTransform(phi[..., :K], phi[..., K : 2 * K], phi[..., 2 * K :])
+    y, ladj = t.call_and_ladj(x)
+    ((dev_t(GU[f"rqs_{tag}_gy"], device) * y).sum() + (dev_t(GU[f"rqs_{tag}_gl"], device) * ladj).sum()).backward()
+    ok = np.abs(GU[f"rqs_{tag}_x"]) != 5.0  # on-knot element, see tests/test_oracle_grad.py
+    ref_gx, ref_gphi = GU[f"rqs_{tag}_gx"], GU[f"rqs_{tag}_gphi"]
+    scale = np.maximum(np.abs(ref_gphi).max(-1, keepdims=True), 1.0)
+    assert np.all(np.abs(cpu(x.grad) - ref_gx)[ok] <= tol * np.maximum(np.abs(ref_gx), 1.0)[ok])
+    assert np.all((np.abs(cpu(phi.grad) - ref_gphi) / scale)[ok] <= tol)
+
+
+@pytest.mark.parametrize("K", [16, 5])
+def test_rqs_backward_shared_table(device, K):
+    x = dev_t(U[f"rqs_shared{K}_x"], device, grad=True)
+    phi = dev_t(U[f"rqs_shared{K}_phi"], device, grad=True)
+    # one shared table per feature: feature d uses row d => evaluate column by column
+    gy, gl = dev_t(GU[f"rqs_shared{K}_gy"], device), dev_t(GU[f"rqs_shared{K}_gl"], device)
+    loss = 0
+    for d in range(x.shape[1]):
+        t = MonotonicRQSTransform(phi[d, :K], phi[d, K : 2 * K], phi[d, 2 * K :])
+        y, ladj = t.call_and_ladj(x[:, d])
+        loss = loss + (gy[:, d] * y).sum() + (gl[:, d] * ladj).sum()
+    loss.backward()
+    close(cpu(x.grad), GU[f"rqs_shared{K}_gx"], 5e-5, "gx")
+    close(cpu(phi.grad), GU[f"rqs_shared{K}_gphi"], 5e-5, "gphi (table, summed over the batch)")
+
+
+def test_affine_and_softclip_backward(device):
+    x = dev_t(U["affine_x"], device, grad=True)
+    phi = dev_t(U["affine_phi"], device, grad=True)
+    t = MonotonicAffineTransform(phi[..., 0], phi[..., 1])
+    y, ladj = t.call_and_ladj(x)
+    ((dev_t(GU["affine_gy"], device) * y).sum() + (dev_t(GU["affine_gl"], device) * ladj).sum()).backward()
+    close(cpu(x.grad), GU["affine_gx"], 1e-5, "affine gx")
+    close(cpu(phi.grad), GU["affine_gphi"], 1e-5, "affine gphi")
+    for b in (1, 11):
+        xs = dev_t(U["softclip_x"], device, grad=True)
+        t = SoftclipTransform(bound=float(b))
+        y, ladj = t.call_and_ladj(xs)
+        ((dev_t(GU["softclip_gy"], device) * y).sum() + (dev_t(GU["softclip_gl"], device) * ladj).sum()).backward()
+        close(cpu(xs.grad), GU[f"softclip{b}_gx"], 1e-5, f"softclip{b} gx")
+
+
+# --------------------------------------------------------------------------- #
+# flows: golden gradients of the reference (fp64 autograd)
+# --------------------------------------------------------------------------- #
+
+
+def _flow_grads(flow, x, c, mode, gg, device):
+    for p in flow.parameters():
+        p.grad = None
+    xt = dev_t(x, device, grad=True)
+    ct = None if c is None else dev_t(c, device, grad=True)
+    if mode == "lp":
+        lp = flow(ct).log_prob(xt)
+        (dev_t(gg["g"], device) * lp).sum().backward()
+    else:
+        z, ladj = flow(ct).transform.call_and_ladj(xt)
+        ((dev_t(gg["gz"], device) * z).sum() + (dev_t(gg["gl"], device) * ladj).sum()).backward()
+    return cpu(xt.grad), (None if ct is None else cpu(ct.grad)), named_param_grads(flow)
+
+
+@pytest.mark.parametrize("mode", ["lp", "tr"])
+@pytest.mark.parametrize("name", GRAD_CASES_FULL + GRAD_CASES_SAMPLED)
+def test_flow_gradients_vs_reference_autograd(device, name, mode):
+    gg, x, c = grad_inputs(name)
+    flow = build_flow(name).to(device)
+    rtol = 1e-3 if name == "nsf6_stress" else 2e-5
+    gx, gc, pg = _flow_grads(flow, x, c, mode, gg, device)
+    close(gx, gg[f"{mode}/gx"], rtol, f"{name} d/dx")
+    if c is not None:
+        close(gc, gg[f"{mode}/gc"], rtol, f"{name} d/dc")
+    assert_param_grads(pg, gg, f"{mode}/", rtol, name)
+
+
+def test_log_prob_value_unchanged_by_autograd(device):
+    """The forward value through the autograd seam is the engine's usual log_prob, bit for bit."""
+    gg, x, c = grad_inputs("cfg2_nsf")
+    flow = build_flow("cfg2_nsf").to(device)
+    xt, ct = dev_t(x, device), dev_t(c, device)
+    with torch.no_grad():
+        ref = flow(ct).log_prob(xt)
+    lp = flow(ct).log_prob(xt)
+    assert lp.requires_grad and torch.equal(lp.detach(), ref)
+
+
+def test_chunked_backward_and_determinism(device):
+    """Row chunking (small workspace) accumulates the same parameter gradients; two runs agree
+    bit for bit (fixed-order reductions)."""
+    name = "cfg2_nsf"
+    flow = build_flow(name).to(device)
+    spec = O.flowspec_from_module(build_flow(name))
+    gen = torch.Generator().manual_seed(5)
+    B = 6000
+    x, c, g = torch.randn(B, 16, generator=gen).numpy(), torch.randn(B, 8, generator=gen).numpy(), torch.randn(B, generator=gen).numpy()
+    gg = {"g": g}
+    full = _flow_grads(flow, x, c, "lp", gg, device)
+    again = _flow_grads(flow, x, c, "lp", gg, device)
+    assert np.array_equal(full[0], again[0]) and all(np.array_equal(full[2][k], again[2][k]) for k in full[2])
+    prev = E.Workspace.max_bytes
+    E.Workspace.clear()
+    try:
+        L = E.lib()
+        import ctypes
+
+        fc = flow(dev_t(c, device))._flow_call()[0]
+        E.Workspace.max_bytes = int(L.zk_flow_backward_workspace_bytes(ctypes.byref(fc.desc), 1024))  # => 6 chunks
+        chunked = _flow_grads(flow, x, c, "lp", gg, device)
+    finally:
+        E.Workspace.max_bytes = prev
+        E.Workspace.clear()
+    close(chunked[0], full[0], 1e-6, "chunked gx")
+    for k in full[2]:
+        close(chunked[2][k], full[2][k], 2e-5, f"chunked d/d{k}")
+    # and the whole thing against the gradient oracle (fp64) on the first rows
+    n = 512
+    ogx, ogc, _ = OG.flow_backward(spec, x[:n], c[:n], g_log_prob=g[:n])
+    close(full[0][:n], ogx, 2e-5, "gx vs oracle")
+    close(full[1][:n], ogc, 2e-5, "gc vs oracle")
+
+
+def test_training_step_decreases_nll(device):
+    """README.md:43-49: a few Adam steps through the engine's backward reduce the NLL, and the
+    packed weights follow the optimizer (re-pack on version change)."""
+    import zuko_b200 as zuko
+
+    torch.manual_seed(0)
+    flow = zuko.flows.NSF(3, 2, transforms=2, hidden_features=[64, 64]).to(device)
+    gen = torch.Generator().manual_seed(0)
+    c = torch.randn(2048, 2, generator=gen).to(device)
+    x = (torch.randn(2048, 3, generator=gen) * 0.3).to(device) + torch.cat([c, c[:, :1]], -1)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-2)
+    losses = []
+    for _ in range(30):
+        loss = -flow(c).log_prob(x).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    # the unmodified reference, same seed / data / optimizer, on CPU (measured in the build
+    # container): 4.6403 (step 0), 1.7908 (5), 1.2259 (10), 0.8521 (20), 0.6912 (29)
+    assert abs(losses[0] - 4.6403) < 2e-3, losses[0]
+    assert abs(losses[5] - 1.7908) < 0.05 and abs(losses[10] - 1.2259) < 0.05, losses[:11]
+    assert abs(losses[29] - 0.6912) < 0.08, losses[::5]
+
+
+def test_broadcast_context_and_oracle(device):
+    """c of shape (C,) (one broadcast row): d/dc is the sum over the batch."""
+    gg, x, c = grad_inputs("nsf35_row")
+    assert c.ndim == 1
+    flow = build_flow("nsf35_row").to(device)
+    gx, gc, _ = _flow_grads(flow, x, c, "lp", gg, device)
+    assert gc.shape == c.shape
+    close(gc, gg["lp/gc"], 2e-5, "d/dc (broadcast row)")
+
+
+def test_accelerated_reference_style_module_gets_grads(device):
+    """Gradients land on the parameters the engine handle was packed from (the objects an
+    optimizer holds), also through accelerate()."""
+    import zuko_b200 as zuko
+
+    gg, x, c = grad_inputs("maf35_batch")
+    src = build_flow("maf35_batch").to(device)
+    acc = zuko.accelerate(src)
+    xt, ct = dev_t(x, device), dev_t(c, device)
+    (dev_t(gg["g"], device) * acc(ct).log_prob(xt)).sum().backward()
+    assert_param_grads(named_param_grads(src), gg, "lp/", 2e-5, "accelerate(maf35)")

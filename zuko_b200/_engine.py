@@ -67,6 +67,17 @@ class LayerDesc(ctypes.Structure):
     ]
 
 
+class LayerGrads(ctypes.Structure):
+    """``zk_layer_grads``: where one layer's parameter gradients are accumulated."""
+
+    _fields_ = [
+        ("grad_weight", POINTER(c_void_p)),
+        ("grad_bias", POINTER(c_void_p)),
+        ("grad_phi", c_void_p),
+        ("grad_rotation", c_void_p),
+    ]
+
+
 class FlowDesc(ctypes.Structure):
     _fields_ = [
         ("n_layers", c_int),
@@ -112,6 +123,16 @@ _SIGNATURES = {
     "zk_flow_forward": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
     "zk_flow_log_prob": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
     "zk_flow_inverse": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "zk_univariate_backward_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int64]),
+    "zk_rqs_backward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_float, c_float, _P, c_int64, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "zk_affine_backward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "zk_softclip_backward": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P, _P, c_int64, _P]),
+    "zk_layer_backward_workspace_bytes": (c_size_t, [_P, c_int64]),
+    "zk_layer_backward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, POINTER(LayerGrads), _P, c_size_t, _P]),
+    "zk_flow_backward_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),
+    "zk_flow_backward_min_workspace_bytes": (c_size_t, [POINTER(FlowDesc)]),
+    "zk_flow_backward": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64,
+                                 POINTER(POINTER(LayerGrads)), _P, c_size_t, _P]),
     "zk_flow_log_prob_host": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, POINTER(c_double), _P, c_size_t, _P]),
 }  # fmt: skip
 

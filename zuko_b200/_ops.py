@@ -9,6 +9,7 @@ taken as contiguous fp32 copies when they are not already.
 from __future__ import annotations
 
 import ctypes
+import warnings
 from collections.abc import Sequence
 
 import torch
@@ -20,11 +21,6 @@ from . import _engine as E
 def _flatten(x: Tensor, c: Tensor | None, D: int):
     """Returns (x2 (B, D), c2 or None, ldc, lead_shape)."""
     E.require_cuda(x, "input")
-    if x.requires_grad or (c is not None and c.requires_grad):
-        raise NotImplementedError(
-            "zuko_b200: inputs that require grad are not supported (the engine is forward-only; "
-            "the backward pass is listed as next in SURVEY §8f)"
-        )
     if x.shape[-1] != D:
         raise ValueError(f"zuko_b200: expected {D} features in the last dimension, got {tuple(x.shape)}")
     lead = x.shape[:-1]
@@ -89,12 +85,57 @@ def layer_inverse(handle, D: int, y: Tensor, c: Tensor | None) -> Tensor:
     return x.reshape(*lead, D)
 
 
+class _FlowFunction(torch.autograd.Function):
+    """Autograd seam of the engine: the forward is the usual engine call
+    (``zk_flow_log_prob`` / ``zk_flow_forward``), the backward ONE ``zk_flow_backward`` call that
+    recomputes the activations and returns d/d(x, c, every conditioner weight and bias, shared
+    tables, rotation matrices) — what torch.autograd yields for the reference's eager graph."""
+
+    @staticmethod
+    def forward(ctx, call, mode, ldc, x2, c2, *params):  # noqa: ANN001
+        ctx.call, ctx.mode, ctx.ldc = call, mode, ldc
+        ctx.has_c = c2 is not None
+        ctx.save_for_backward(*([x2, c2] if c2 is not None else [x2]))
+        lead = x2.shape[:-1]
+        if mode == "log_prob":
+            return call._run_log_prob(x2, c2, ldc, lead)
+        return call._run_forward(x2, c2, ldc, lead)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):  # noqa: ANN001
+        saved = ctx.saved_tensors
+        x2 = saved[0]
+        c2 = saved[1] if ctx.has_c else None
+        need = ctx.needs_input_grad
+        gx, gc, pg = ctx.call._run_backward(ctx.mode, x2, c2, ctx.ldc, gouts, need[3], need[4], need[5:])
+        return (None, None, None, gx, gc, *pg)
+
+
 class FlowCall:
     """A ``zk_flow_desc`` over packed layers + DiagNormal base, ready to be invoked."""
 
-    def __init__(self, handles: Sequence, D: int, C: int, loc: Tensor | None, scale: Tensor | None) -> None:
+    _warned_inverse = False
+
+    def __init__(self, handles: Sequence, D: int, C: int, loc: Tensor | None, scale: Tensor | None,
+                 sources: Sequence[dict] | None = None, keep: Sequence | None = None) -> None:  # fmt: skip
         self.D, self.C = D, C
         self._handles = list(handles)
+        # per layer: the tensors its parameter gradients belong to ({"weights", "biases"} of the
+        # conditioner, {"phi"} shared table pieces, {"R"} rotation matrix) — see _FlowFunction
+        self._sources = [dict(s) for s in sources] if sources is not None else [{} for _ in self._handles]
+        self._keep = list(keep) if keep is not None else []  # owners of the zk_layer handles
+        self._params: list[Tensor] = []
+        self._slots: list[tuple[int, str, int]] = []  # (layer, kind, index) of every entry of _params
+        for li, src in enumerate(self._sources):
+            for kind in ("weights", "biases", "phi"):
+                for k, t in enumerate(src.get(kind) or []):
+                    if t is not None:
+                        self._params.append(t)
+                        self._slots.append((li, kind, k))
+            if src.get("R") is not None:
+                self._params.append(src["R"])
+                self._slots.append((li, "R", 0))
         self._arr = (ctypes.c_void_p * max(1, len(handles)))(*[h.value if isinstance(h, ctypes.c_void_p) else h for h in handles])
         self._loc = None if loc is None else loc.detach().contiguous()
         self._scale = None if scale is None else scale.detach().contiguous()
@@ -114,6 +155,18 @@ class FlowCall:
     def forward(self, x: Tensor, c: Tensor | None) -> tuple[Tensor, Tensor]:
         """``transform.call_and_ladj(x)`` — zuko/transforms.py:141-150."""
         x2, c2, ldc, lead = _flatten(x, c if self.C else None, self.D)
+        if self._wants_grad(x2, c2):
+            z, ladj = _FlowFunction.apply(self, "forward", ldc, x2, c2, *self._params)
+            return z.reshape(*lead, self.D), ladj.reshape(lead)
+        return self._run_forward(x2, c2, ldc, lead)
+
+    def _wants_grad(self, x2: Tensor, c2: Tensor | None) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return x2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
+
+    def _run_forward(self, x2: Tensor, c2: Tensor | None, ldc: int, lead) -> tuple[Tensor, Tensor]:
+        x2, c2 = x2.detach(), (None if c2 is None else c2.detach())
         B = x2.shape[0]
         z = torch.empty_like(x2)
         ladj = torch.empty(B, device=x2.device, dtype=torch.float32)
@@ -133,6 +186,13 @@ class FlowCall:
         ``with_sum`` also returns a device double holding ``sum(log_prob)`` (fixed-order
         reduction; the per-rank term of the mean NLL)."""
         x2, c2, ldc, lead = _flatten(x, c if self.C else None, self.D)
+        if self._wants_grad(x2, c2):
+            lp = _FlowFunction.apply(self, "log_prob", ldc, x2, c2, *self._params).reshape(lead)
+            return (lp, lp.detach().double().sum().reshape(1)) if with_sum else lp
+        return self._run_log_prob(x2, c2, ldc, lead, with_sum)
+
+    def _run_log_prob(self, x2: Tensor, c2: Tensor | None, ldc: int, lead, with_sum: bool = False):
+        x2, c2 = x2.detach(), (None if c2 is None else c2.detach())
         B = x2.shape[0]
         lp = torch.empty(B, device=x2.device, dtype=torch.float32)
         total = torch.zeros(1, device=x2.device, dtype=torch.float64) if with_sum else None
@@ -154,6 +214,16 @@ class FlowCall:
         """``transform.inv(z)`` (and the log-density of the result when ``with_log_prob``,
         zuko/distributions.py:129-138)."""
         z2, c2, ldc, lead = _flatten(z, c if self.C else None, self.D)
+        if torch.is_grad_enabled() and not FlowCall._warned_inverse and (
+            z2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
+        ):
+            FlowCall._warned_inverse = True
+            warnings.warn(
+                "zuko_b200: rsample() / transform.inv() return tensors that are NOT differentiable in this "
+                "version (a backward pass exists for log_prob and call_and_ladj only); the result is detached.",
+                stacklevel=3,
+            )
+        z2, c2 = z2.detach(), (None if c2 is None else c2.detach())
         B = z2.shape[0]
         x = torch.empty_like(z2)
         lp = torch.empty(B, device=z2.device, dtype=torch.float32) if with_log_prob else None
@@ -168,6 +238,87 @@ class FlowCall:
                 )  # fmt: skip
         x = x.reshape(*lead, self.D)
         return (x, lp.reshape(lead)) if with_log_prob else x
+
+    def _run_backward(self, mode: str, x2: Tensor, c2: Tensor | None, ldc: int, gouts, need_x: bool, need_c: bool,
+                      need_p: Sequence[bool]):  # fmt: skip
+        """One ``zk_flow_backward`` call: returns (gx | None, gc | None, [param grads | None])."""
+        L = E.lib()
+        dev = x2.device
+        B, D, C = x2.shape[0], self.D, self.C
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        def dense(t):
+            return None if t is None else t.detach().to(torch.float32).contiguous()
+
+        g_lp = g_z = g_l = None
+        if mode == "log_prob":
+            g_lp = dense(gouts[0])
+        else:
+            g_z, g_l = dense(gouts[0]), dense(gouts[1])
+        gx = torch.empty(B, D, **f32) if need_x else None
+        gc = None
+        if need_c and c2 is not None:
+            gc = torch.zeros(C, **f32) if ldc == 0 else torch.empty(B, C, **f32)
+        # parameter gradient buffers (accumulated into by the engine => zero-initialised)
+        nL = len(self._handles)
+        pg: list[Tensor | None] = [None] * len(self._params)
+        tables: dict[int, Tensor] = {}
+        structs = (ctypes.POINTER(E.LayerGrads) * max(1, nL))()
+        keep = []
+        per_layer: dict[int, dict] = {}
+        for i, (li, kind, k) in enumerate(self._slots):
+            if not need_p[i]:
+                continue
+            d = per_layer.setdefault(li, {"weights": {}, "biases": {}, "phi": False, "R": None})
+            p = self._params[i]
+            if kind in ("weights", "biases"):
+                pg[i] = torch.zeros(p.shape, **f32)
+                d[kind][k] = pg[i]
+            elif kind == "phi":
+                d["phi"] = True
+            else:
+                pg[i] = torch.zeros(p.shape, **f32)
+                d["R"] = pg[i]
+        for li, d in per_layer.items():
+            src = self._sources[li]
+            lg = E.LayerGrads()
+            n = len(src.get("weights") or [])
+            if d["weights"] or d["biases"]:
+                gw = (ctypes.c_void_p * n)(*[d["weights"][k].data_ptr() if k in d["weights"] else None for k in range(n)])
+                gb = (ctypes.c_void_p * n)(*[d["biases"][k].data_ptr() if k in d["biases"] else None for k in range(n)])
+                lg.grad_weight, lg.grad_bias = gw, gb
+                keep += [gw, gb]
+            if d["phi"]:
+                P = sum(int(t[0].numel()) for t in src["phi"])
+                tables[li] = torch.zeros(D, P, **f32)
+                lg.grad_phi = tables[li].data_ptr()
+            if d["R"] is not None:
+                lg.grad_rotation = d["R"].data_ptr()
+            keep.append(lg)
+            structs[li] = ctypes.pointer(lg)
+        if B:
+            with torch.cuda.device(dev):
+                want = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), B)
+                minimum = L.zk_flow_backward_min_workspace_bytes(ctypes.byref(self.desc))
+                floor = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), min(B, 1024))
+                ws = E.Workspace.get(dev, want, max(minimum, floor))
+                E.check(
+                    L.zk_flow_backward(
+                        ctypes.byref(self.desc), x2.data_ptr(), D, _ptr(c2), ldc, B, _ptr(g_z), D, _ptr(g_l), _ptr(g_lp),
+                        _ptr(gx), D, _ptr(gc), C, structs, ws.data_ptr(), ws.numel(), E.stream_ptr(dev),
+                    )
+                )  # fmt: skip
+        elif gx is not None:
+            gx.zero_()
+        # split shared-table gradients back into the pieces of the ParameterList
+        for i, (li, kind, k) in enumerate(self._slots):
+            if kind == "phi" and need_p[i]:
+                pieces = self._sources[li]["phi"]
+                col = sum(int(t[0].numel()) for t in pieces[:k])
+                w = int(pieces[k][0].numel())
+                pg[i] = tables[li][:, col : col + w].reshape(pieces[k].shape).contiguous()
+        del keep
+        return gx, gc, pg
 
     def log_prob_host(self, x_host: Tensor, c_host: Tensor | None, device: torch.device, out: Tensor | None = None):
         """End-to-end entry: HOST (pinned) inputs, HOST output; H2D / compute / D2H are

@@ -9,11 +9,7 @@
 #include <new>
 #include <vector>
 
-#include "ar_inverse.cuh"
-#include "bijectors.cuh"
-#include "fused_layer.cuh"
-#include "mlp.cuh"
-#include "mlp_tcgen05.cuh"
+#include "api_internal.cuh"
 
 namespace zk {
 
@@ -44,60 +40,11 @@ int sm_count() {
     return cached[dev];
 }
 
-namespace {
-
-// bump allocator over the caller's workspace (256-byte granules)
-struct Arena {
-    char* base;
-    size_t size, off = 0;
-    bool ok = true;
-    Arena(void* p, size_t n) : base((char*)p), size(n) {}
-    template <typename T>
-    T* take(size_t count) {
-        size_t bytes = align_up(count * sizeof(T), 256);
-        if (off + bytes > size) {
-            ok = false;
-            return nullptr;
-        }
-        T* r = (T*)(base + off);
-        off += bytes;
-        return r;
-    }
-};
-inline size_t a256(size_t bytes) { return align_up(bytes, 256); }
-
-template <typename T>
-zk_status dev_copy_from_host(const T* host, size_t n, T** out) {
-    *out = nullptr;
-    if (n == 0) return ZK_OK;
-    ZK_CUDA(cudaMalloc((void**)out, n * sizeof(T)));
-    ZK_CUDA(cudaMemcpy(*out, host, n * sizeof(T), cudaMemcpyHostToDevice));
-    return ZK_OK;
-}
-
-}  // namespace
 }  // namespace zk
 
 using namespace zk;
 namespace zkapi {}
 using namespace zkapi;
-
-// ===========================================================================
-// layer handle
-// ===========================================================================
-struct zk_layer {
-    int kind = 0, D = 0, C = 0, uni = 0, K = 0, P = 0, passes = 0;
-    float bound = 5.f, slope = 1e-3f;
-    zk_mlp* hyper = nullptr;       // owned
-    float* phi_shared = nullptr;   // device (D, P), owned
-    float* rotation = nullptr;     // device (D, D), owned
-    int64_t* perm = nullptr;       // device (D), owned
-    int64_t* perm_inv = nullptr;   // device (D), owned
-    int* idx_a = nullptr;          // device: constant-split columns (coupling), owned
-    int* idx_b = nullptr;          // device: transformed columns (coupling), owned
-    int n_a = 0, n_b = 0;
-    zk::ArInvPack* inv = nullptr;  // step-ordered weights for the dimension-sequential inverse (owned)
-};
 
 extern "C" {
 
@@ -190,6 +137,8 @@ zk_status zk_mlp_destroy(zk_mlp* m) {
     if (!m) return ZK_OK;
     for (float* p : m->w) cudaFree(p);
     for (float* p : m->b) cudaFree(p);
+    for (uint8_t* p : m->mask) cudaFree(p);
+    for (float* p : m->wt) cudaFree(p);
     tc_destroy(m);
     delete m;
     return ZK_OK;
@@ -225,6 +174,14 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
         const uint8_t* mk = (d->mask ? d->mask[i] : nullptr);
         st = launch_apply_mask(d->weight[i], mk, n, w, 0);
         if (st != ZK_OK) break;
+        uint8_t* mcopy = nullptr;  // kept for the backward pass: dL/dW = mask * dL/d(mask * W)
+        if (mk) {
+            if (cudaMalloc((void**)&mcopy, (size_t)n) != cudaSuccess) { st = fail(ZK_ENOMEM, "mlp_create: cudaMalloc failed"); break; }
+            m->mask.push_back(mcopy);
+            if (cudaMemcpyAsync(mcopy, mk, (size_t)n, cudaMemcpyDeviceToDevice, 0) != cudaSuccess) { st = fail(ZK_ECUDA, "mlp_create: mask copy failed"); break; }
+        } else {
+            m->mask.push_back(nullptr);
+        }
         if (cudaMemsetAsync(b, 0, ((size_t)m->dims[i + 1] + 4) * 4, 0) != cudaSuccess) st = fail(ZK_ECUDA, "mlp_create: bias memset failed");
         if (d->bias && d->bias[i]) {
             if (cudaMemcpyAsync(b, d->bias[i], (size_t)m->dims[i + 1] * 4, cudaMemcpyDeviceToDevice, 0) != cudaSuccess)

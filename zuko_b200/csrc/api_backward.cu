@@ -1,0 +1,407 @@
+// zuko_b200 — C ABI of the backward pass: layer / flow orchestration of the reverse-mode kernels
+// (backward.cu).  Declarations and reference citations: include/zuko_b200.h.
+//
+// Structure of one layer's backward (autoregressive, transforms.py:1005-1007):
+//   A0 = cat(x, c)                                   concat_kernel
+//   h_i = relu(h_{i-1} W_i^T + b_i), phi = last      linear_fp32_kernel, activations KEPT
+//   (gx_direct, gphi) = d bijector(x; phi)           uni_bwd_kernel (gphi overwrites phi)
+//   for i = last..first: gW_i += mask * g^T h_{i-1}  wgrad_fp32_kernel + fixed-order reduce
+//                        gb_i += colsum(g)           colsum_stage1/2
+//                        g = (g W_i) * [h_{i-1} > 0] linear_fp32_kernel on W_i^T + relu_gate_kernel
+//   gx = gx_direct + g[:, :D];  gc += g[:, D:]       input_grad_kernel
+// The flow-level call recomputes the forward chain z_0..z_T with the production forward kernels
+// (fused tcgen05 layer kernel where it applies), then walks the layers in reverse.
+
+#include <mutex>
+
+#include "api_internal.cuh"
+#include "backward.cuh"
+
+using namespace zk;
+namespace zkapi {}
+using namespace zkapi;
+
+namespace zkapi {
+
+namespace {
+
+std::mutex g_bwd_mu;
+
+// transposed pre-masked weights for dgrad, built on first use
+zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
+    zk_mlp* m = const_cast<zk_mlp*>(cm);
+    std::lock_guard<std::mutex> lk(g_bwd_mu);
+    if ((int)m->wt.size() == m->n_linear) return ZK_OK;
+    for (float* p : m->wt) cudaFree(p);
+    m->wt.clear();
+    for (int i = 0; i < m->n_linear; ++i) {
+        float* t = nullptr;
+        ZK_CUDA(cudaMalloc((void**)&t, (size_t)m->dims[i] * m->dims[i + 1] * 4));
+        m->wt.push_back(t);
+        ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], t, st));
+    }
+    ZK_CUDA(cudaStreamSynchronize(st));
+    return ZK_OK;
+}
+
+struct MlpBwdBufs {
+    std::vector<float*> acts;  // acts[i]: input of linear layer i, (B, dims[i])
+    float* out = nullptr;      // (B, dims[n]): conditioner output, later its gradient
+    float* gbuf[2] = {nullptr, nullptr};
+    float* gin = nullptr;      // (B, dims[0])
+    void* scratch = nullptr;
+};
+
+size_t mlp_bwd_scratch(const zk_mlp* m) {
+    size_t s = 0;
+    for (int i = 0; i < m->n_linear; ++i)
+        s = std::max(s, std::max(wgrad_scratch_bytes(m->dims[i + 1], m->dims[i]), colsum_scratch_bytes(m->dims[i + 1])));
+    return a256(s);
+}
+
+size_t mlp_bwd_ws(const zk_mlp* m, int64_t B) {
+    size_t s = 0;
+    for (int i = 0; i <= m->n_linear; ++i) s += a256((size_t)B * m->dims[i] * 4);  // acts + out
+    if (m->n_linear > 1) s += 2 * a256((size_t)B * m->max_hidden * 4);
+    s += a256((size_t)B * m->dims[0] * 4);  // gin
+    return s + mlp_bwd_scratch(m);
+}
+
+bool mlp_bwd_carve(const zk_mlp* m, int64_t B, Arena& ar, MlpBwdBufs& b) {
+    b.acts.resize(m->n_linear);
+    for (int i = 0; i < m->n_linear; ++i) b.acts[i] = ar.take<float>((size_t)B * m->dims[i]);
+    b.out = ar.take<float>((size_t)B * m->dims[m->n_linear]);
+    if (m->n_linear > 1) {
+        b.gbuf[0] = ar.take<float>((size_t)B * m->max_hidden);
+        b.gbuf[1] = ar.take<float>((size_t)B * m->max_hidden);
+    }
+    b.gin = ar.take<float>((size_t)B * m->dims[0]);
+    b.scratch = ar.take<char>(mlp_bwd_scratch(m));
+    return ar.ok;
+}
+
+// forward with every activation kept (fp32 CUDA-core path); acts[0] must be filled
+zk_status mlp_forward_save(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, cudaStream_t st) {
+    const int n = m->n_linear;
+    for (int i = 0; i < n; ++i) {
+        float* dst = (i < n - 1) ? b.acts[i + 1] : b.out;
+        ZK_TRY(launch_linear_fp32(b.acts[i], m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i], m->b[i],
+                                  B, m->dims[i + 1], i < n - 1, dst, m->dims[i + 1], st));
+    }
+    return ZK_OK;
+}
+
+// b.out holds dL/d(out) on entry; on exit b.gin = dL/d(input) when want_gin
+zk_status mlp_backward(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, bool want_gin,
+                       const zk_layer_grads* grads, cudaStream_t st) {
+    const int n = m->n_linear;
+    const float* g = b.out;
+    for (int i = n - 1; i >= 0; --i) {
+        const int N = m->dims[i + 1], K = m->dims[i];
+        if (grads && grads->grad_weight && grads->grad_weight[i])
+            ZK_TRY(launch_wgrad_fp32(g, N, b.acts[i], K, B, N, K, m->mask[i], grads->grad_weight[i], b.scratch, st));
+        if (grads && grads->grad_bias && grads->grad_bias[i])
+            ZK_TRY(launch_colsum_add(g, N, B, N, grads->grad_bias[i], b.scratch, st));
+        if (i > 0 || want_gin) {
+            float* dst = (i == 0) ? b.gin : b.gbuf[i & 1];
+            // g (B, N) x W (N, K) = "linear" with the transposed weights (K, N)
+            ZK_TRY(launch_linear_fp32(g, N, N, nullptr, 0, N, m->wt[i], nullptr, B, K, false, dst, K, st));
+            if (i > 0) ZK_TRY(launch_relu_gate(dst, b.acts[i], B * (int64_t)K, st));
+            g = dst;
+        }
+    }
+    return ZK_OK;
+}
+
+size_t layer_bwd_ws(const zk_layer* l, int64_t B) {
+    if (!l || B <= 0) return 0;
+    const size_t table = a256((size_t)B * l->D * l->P * 4) + a256(colsum_scratch_bytes(std::max(1, l->D * l->P)));
+    switch (l->kind) {
+        case ZK_LAYER_AUTOREGRESSIVE:
+        case ZK_LAYER_COUPLING:
+            return mlp_bwd_ws(l->hyper, B) + 1024;
+        case ZK_LAYER_ELEMENTWISE:
+            return (l->hyper ? mlp_bwd_ws(l->hyper, B) : 0) + table + 1024;
+        case ZK_LAYER_ROTATION:
+            return a256(wgrad_scratch_bytes(l->D, l->D)) + 1024;
+        default:
+            return 0;
+    }
+}
+
+zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, const float* c,
+                              int64_t ldc, int64_t B, const float* gy, int64_t ldgy, const float* gl,
+                              float* gx, int64_t ldgx, float* gc, int64_t ldgc,
+                              const zk_layer_grads* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (B == 0) return ZK_OK;
+    ZK_REQUIRE(l->C == 0 || c != nullptr, "layer needs a context of %d features", l->C);
+    Arena ar(ws, ws_bytes);
+    UniBwdArgs u;
+    u.univariate = l->uni; u.B = B; u.K = l->K; u.bound = l->bound; u.slope = l->slope;
+    u.x = x; u.ldx = ldx; u.gy = gy; u.ldgy = ldgy; u.gl = gl; u.gx = gx; u.ldgx = ldgx;
+    switch (l->kind) {
+        case ZK_LAYER_AUTOREGRESSIVE:
+        case ZK_LAYER_COUPLING: {
+            const bool coupling = (l->kind == ZK_LAYER_COUPLING);
+            const zk_mlp* m = l->hyper;
+            const int nx = coupling ? l->n_a : l->D;
+            const int nt = coupling ? l->n_b : l->D;  // transformed dims
+            ZK_TRY(mlp_ensure_backward(m, st));
+            MlpBwdBufs b;
+            ZK_REQUIRE(mlp_bwd_carve(m, B, ar, b), "layer_backward: workspace too small");
+            ZK_TRY(launch_concat(x, ldx, coupling ? l->idx_a : nullptr, nx, c, ldc, l->C, B, b.acts[0], st));
+            ZK_TRY(mlp_forward_save(m, b, B, st));
+            u.phi = b.out; u.phi_ld = (int64_t)nt * l->P; u.gphi = b.out; u.D = nt;
+            u.dim_map = coupling ? l->idx_b : nullptr;
+            ZK_TRY(launch_univariate_backward(u, st));  // gx[:, transformed] = direct term
+            const bool per_row_gc = (gc != nullptr && l->C > 0 && ldc != 0);
+            ZK_TRY(mlp_backward(m, b, B, true, grads, st));
+            // coupling: gx[:, idx_a] = gy[:, idx_a] + gin[:, :n_a] (y_a = x_a, transforms.py:1069)
+            ZK_TRY(launch_input_grad(b.gin, nx, l->C, coupling ? l->idx_a : nullptr, B, gx, ldgx,
+                                     coupling ? gy : nullptr, ldgy, per_row_gc ? gc : nullptr, ldgc, st));
+            if (gc != nullptr && l->C > 0 && ldc == 0)  // broadcast context: one summed row
+                ZK_TRY(launch_colsum_add(b.gin + nx, m->dims[0], B, l->C, gc, b.scratch, st));
+            return ZK_OK;
+        }
+        case ZK_LAYER_ELEMENTWISE: {
+            const int DP = l->D * l->P;
+            u.D = l->D;
+            if (!l->hyper) {  // shared (D, P) table (gaussianization.py:74-77)
+                float* rows = ar.take<float>((size_t)B * DP);
+                void* scr = ar.take<char>(colsum_scratch_bytes(DP));
+                ZK_REQUIRE(ar.ok, "layer_backward: workspace too small");
+                u.phi = l->phi_shared; u.phi_ld = 0;
+                u.gphi = (grads && grads->grad_phi) ? rows : nullptr;
+                ZK_TRY(launch_univariate_backward(u, st));
+                if (grads && grads->grad_phi) ZK_TRY(launch_colsum_add(rows, DP, B, DP, grads->grad_phi, scr, st));
+                return ZK_OK;
+            }
+            const zk_mlp* m = l->hyper;
+            ZK_TRY(mlp_ensure_backward(m, st));
+            const int64_t rows = (ldc == 0) ? 1 : B;  // gaussianization.py:89-92: phi = hyper(c)
+            MlpBwdBufs b;
+            ZK_REQUIRE(mlp_bwd_carve(m, rows, ar, b), "layer_backward: workspace too small");
+            float* grows = nullptr;
+            void* scr = nullptr;
+            if (rows == 1) {
+                grows = ar.take<float>((size_t)B * DP);
+                scr = ar.take<char>(colsum_scratch_bytes(DP));
+                ZK_REQUIRE(ar.ok, "layer_backward: workspace too small");
+            }
+            ZK_TRY(launch_concat(nullptr, 0, nullptr, 0, c, ldc, l->C, rows, b.acts[0], st));
+            ZK_TRY(mlp_forward_save(m, b, rows, st));
+            u.phi = b.out;
+            if (rows == 1) {
+                u.phi_ld = 0; u.gphi = grows;
+                ZK_TRY(launch_univariate_backward(u, st));
+                ZK_CUDA(cudaMemsetAsync(b.out, 0, (size_t)DP * 4, st));
+                ZK_TRY(launch_colsum_add(grows, DP, B, DP, b.out, scr, st));
+            } else {
+                u.phi_ld = DP; u.gphi = b.out;
+                ZK_TRY(launch_univariate_backward(u, st));
+            }
+            ZK_TRY(mlp_backward(m, b, rows, gc != nullptr, grads, st));
+            if (gc) {
+                if (rows == 1) ZK_TRY(launch_add(gc, b.gin, l->C, st));
+                else ZK_TRY(launch_input_grad(b.gin, 0, l->C, nullptr, B, nullptr, 0, nullptr, 0, gc, ldgc, st));
+            }
+            return ZK_OK;
+        }
+        case ZK_LAYER_SOFTCLIP:
+            return launch_softclip_backward(x, ldx, gy, ldgy, gl, B, l->D, l->bound, gx, ldgx, st);
+        case ZK_LAYER_PERMUTATION:  // y[:, j] = x[:, order[j]]  =>  gx[:, i] = gy[:, argsort(order)[i]]
+            return launch_permute(gy, ldgy, l->perm_inv, B, l->D, gx, ldgx, st);
+        case ZK_LAYER_ROTATION: {  // y = R x  =>  gx = R^T gy, gR += gy^T x
+            ZK_TRY(launch_rotate(gy, ldgy, l->rotation, 1, B, l->D, gx, ldgx, st));
+            if (grads && grads->grad_rotation) {
+                void* scr = ar.take<char>(wgrad_scratch_bytes(l->D, l->D));
+                ZK_REQUIRE(ar.ok, "layer_backward: workspace too small");
+                ZK_TRY(launch_wgrad_fp32(gy, ldgy, x, ldx, B, l->D, l->D, nullptr, grads->grad_rotation, scr, st));
+            }
+            return ZK_OK;
+        }
+    }
+    return fail(ZK_EUNSUPPORTED, "layer_backward: unknown kind %d", l->kind);
+}
+
+size_t flow_bwd_ws_for(const zk_flow_desc* f, int64_t Bc) {
+    const int D = f->features;
+    size_t layer_max = 0;
+    for (int i = 0; i < f->n_layers; ++i)
+        layer_max = std::max(layer_max, std::max(zk_layer_workspace_bytes(f->layers[i], Bc), layer_bwd_ws(f->layers[i], Bc)));
+    return (size_t)(f->n_layers + 2) * a256((size_t)Bc * D * 4)  // z_1..z_T + two gradient buffers
+           + 2 * a256((size_t)Bc * 4)                            // gl, ladj scratch
+           + layer_max + 1024;
+}
+
+int64_t flow_bwd_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes) {
+    if (flow_bwd_ws_for(f, B) <= ws_bytes) return B;
+    if (flow_bwd_ws_for(f, 1) > ws_bytes) return 0;
+    int64_t lo = 1, hi = B;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        if (flow_bwd_ws_for(f, mid) <= ws_bytes) lo = mid; else hi = mid - 1;
+    }
+    if (lo >= 2048) lo = lo / 1024 * 1024;
+    return lo;
+}
+
+zk_status flow_backward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx, const float* c,
+                              int64_t ldc, int64_t B, const float* gz_in, int64_t ldgz,
+                              const float* gl_in, const float* g_lp, float* grad_x, int64_t ldgx,
+                              float* grad_c, int64_t ldgc, const zk_layer_grads* const* grads,
+                              void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int D = f->features, T = f->n_layers;
+    Arena ar(ws, ws_bytes);
+    std::vector<const float*> z(T + 1);
+    std::vector<int64_t> ldz(T + 1, D);
+    std::vector<float*> zbuf(T + 1, nullptr);
+    z[0] = x;
+    ldz[0] = ldx;
+    for (int i = 1; i <= T; ++i) z[i] = zbuf[i] = ar.take<float>((size_t)B * D);
+    float* gA = ar.take<float>((size_t)B * D);
+    float* gB = ar.take<float>((size_t)B * D);
+    float* gl = ar.take<float>((size_t)B);
+    float* lscr = ar.take<float>((size_t)B);
+    ZK_REQUIRE(ar.ok, "flow_backward: workspace too small");
+    void* lws = ar.base + ar.off;
+    const size_t lws_bytes = ar.size - ar.off;
+    // forward chain with the production kernels, every z_i kept
+    for (int i = 0; i < T; ++i) {
+        const zk_layer* l = f->layers[i];
+        ZK_TRY(layer_forward_impl(l, z[i], ldz[i], l->C ? c : nullptr, ldc, B, zbuf[i + 1], D, lscr, 0, nullptr,
+                                  nullptr, nullptr, lws, lws_bytes, st));
+    }
+    // seed: dL/dz_T and dL/dladj (distributions.py:115-119)
+    ZK_TRY(launch_base_grad(z[T], ldz[T], f->base_loc, f->base_scale, g_lp, gz_in, ldgz, gl_in, B, D, gA, gl, st));
+    const float* cur = gA;
+    int64_t ldcur = D;
+    for (int i = T - 1; i >= 0; --i) {
+        const zk_layer* l = f->layers[i];
+        float* dst = (i == 0 && grad_x) ? grad_x : (cur == gA ? gB : gA);
+        const int64_t ldd = (i == 0 && grad_x) ? ldgx : D;
+        ZK_TRY(layer_backward_impl(l, z[i], ldz[i], l->C ? c : nullptr, ldc, B, cur, ldcur, gl, dst, ldd,
+                                   l->C ? grad_c : nullptr, ldgc, grads ? grads[i] : nullptr, lws, lws_bytes, st));
+        cur = dst;
+        ldcur = ldd;
+    }
+    if (T == 0 && grad_x) ZK_TRY(copy_rows(gA, D, B, D, grad_x, ldgx, st));
+    return ZK_OK;
+}
+
+zk_status uni_backward_entry(int uni, const float* x, int64_t ldx, const float* phi, int64_t phi_ld,
+                             int64_t B, int D, int K, float bound, float slope, const float* gy,
+                             int64_t ldgy, const float* gl, float* gx, int64_t ldgx, float* gphi,
+                             void* ws, size_t ws_bytes, cudaStream_t st) {
+    ZK_REQUIRE(x && phi && B >= 0 && D > 0, "univariate backward: bad arguments");
+    const int P = (uni == ZK_UNI_RQS) ? 3 * K - 1 : 2;
+    UniBwdArgs u;
+    u.univariate = uni; u.K = K; u.bound = bound; u.slope = slope; u.D = D;
+    u.phi = phi; u.phi_ld = phi_ld;
+    if (phi_ld != 0 || gphi == nullptr) {
+        u.x = x; u.ldx = ldx; u.gy = gy; u.ldgy = ldgy; u.gl = gl; u.gx = gx; u.ldgx = ldgx; u.gphi = gphi; u.B = B;
+        return launch_univariate_backward(u, st);
+    }
+    // shared table: per-row gradients go through the workspace in row chunks, then a fixed-order column sum
+    const size_t DP = (size_t)D * P;
+    const size_t scr = a256(colsum_scratch_bytes((int)DP));
+    ZK_REQUIRE(ws && ws_bytes >= scr + a256(DP * 4), "univariate backward: workspace too small");
+    const int64_t fit = std::min<int64_t>(B, (int64_t)((ws_bytes - scr) / (DP * 4)));
+    float* rows = (float*)((char*)ws + scr);
+    for (int64_t i0 = 0; i0 < B; i0 += fit) {
+        const int64_t n = std::min(fit, B - i0);
+        u.x = x + i0 * ldx; u.ldx = ldx; u.gy = gy ? gy + i0 * ldgy : nullptr; u.ldgy = ldgy;
+        u.gl = gl ? gl + i0 : nullptr; u.gx = gx ? gx + i0 * ldgx : nullptr; u.ldgx = ldgx; u.gphi = rows; u.B = n;
+        ZK_TRY(launch_univariate_backward(u, st));
+        ZK_TRY(launch_colsum_add(rows, (int64_t)DP, n, (int)DP, gphi, ws, st));
+    }
+    return ZK_OK;
+}
+
+}  // namespace
+}  // namespace zkapi
+
+extern "C" {
+
+size_t zk_univariate_backward_workspace_bytes(int64_t B, int D, int P, int64_t phi_ld) {
+    if (phi_ld != 0 || B <= 0 || D <= 0 || P <= 0) return 0;
+    return a256(colsum_scratch_bytes(D * P)) + a256((size_t)B * D * P * 4);
+}
+
+zk_status zk_rqs_backward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld, int64_t B,
+                          int D, int K, float bound, float slope, const float* grad_y, int64_t ldgy,
+                          const float* grad_ladj, float* grad_x, int64_t ldgx, float* grad_phi,
+                          void* ws, size_t ws_bytes, zk_stream stream) {
+    return uni_backward_entry(ZK_UNI_RQS, x, ldx, phi, phi_ld, B, D, K, bound, slope, grad_y, ldgy, grad_ladj,
+                              grad_x, ldgx, grad_phi, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+zk_status zk_affine_backward(const float* x, int64_t ldx, const float* phi, int64_t phi_ld, int64_t B,
+                             int D, float slope, const float* grad_y, int64_t ldgy,
+                             const float* grad_ladj, float* grad_x, int64_t ldgx, float* grad_phi,
+                             void* ws, size_t ws_bytes, zk_stream stream) {
+    return uni_backward_entry(ZK_UNI_AFFINE, x, ldx, phi, phi_ld, B, D, 0, 5.f, slope, grad_y, ldgy, grad_ladj,
+                              grad_x, ldgx, grad_phi, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+zk_status zk_softclip_backward(const float* x, int64_t ldx, int64_t B, int D, float bound,
+                               const float* grad_y, int64_t ldgy, const float* grad_ladj,
+                               float* grad_x, int64_t ldgx, zk_stream stream) {
+    return launch_softclip_backward(x, ldx, grad_y, ldgy, grad_ladj, B, D, bound, grad_x, ldgx, (cudaStream_t)stream);
+}
+
+size_t zk_layer_backward_workspace_bytes(const zk_layer* l, int64_t B) { return layer_bwd_ws(l, B); }
+
+zk_status zk_layer_backward(const zk_layer* l, const float* x, int64_t ldx, const float* c, int64_t ldc,
+                            int64_t B, const float* grad_y, int64_t ldgy, const float* grad_ladj,
+                            float* grad_x, int64_t ldgx, float* grad_c, int64_t ldgc,
+                            const zk_layer_grads* grads, void* ws, size_t ws_bytes, zk_stream stream) {
+    ZK_REQUIRE(l && x && grad_y && grad_x, "layer_backward: null argument");
+    ZK_REQUIRE(grad_x != grad_y && grad_x != x, "layer_backward: grad_x must not alias its inputs");
+    ZK_REQUIRE(B >= 0 && ldx >= l->D && ldgy >= l->D && ldgx >= l->D, "layer_backward: bad shape");
+    ZK_REQUIRE(!grad_c || ldc == 0 || ldgc >= l->C, "layer_backward: bad ldgc");
+    ZK_REQUIRE(ws_bytes >= layer_bwd_ws(l, B), "layer_backward: workspace too small (%zu < %zu)", ws_bytes, layer_bwd_ws(l, B));
+    return layer_backward_impl(l, x, ldx, c, ldc, B, grad_y, ldgy, grad_ladj, grad_x, ldgx, l->C ? grad_c : nullptr,
+                               ldgc, grads, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t zk_flow_backward_workspace_bytes(const zk_flow_desc* f, int64_t B) {
+    if (!f || B <= 0) return 1024;
+    return flow_bwd_ws_for(f, B);
+}
+size_t zk_flow_backward_min_workspace_bytes(const zk_flow_desc* f) { return f ? flow_bwd_ws_for(f, 1) : 1024; }
+
+zk_status zk_flow_backward(const zk_flow_desc* f, const float* x, int64_t ldx, const float* c,
+                           int64_t ldc, int64_t B, const float* grad_z, int64_t ldgz,
+                           const float* grad_ladj, const float* grad_log_prob, float* grad_x,
+                           int64_t ldgx, float* grad_c, int64_t ldgc,
+                           const zk_layer_grads* const* grads, void* ws, size_t ws_bytes,
+                           zk_stream stream) {
+    ZK_TRY(flow_check(f));
+    ZK_REQUIRE(x, "flow_backward: null x");
+    ZK_REQUIRE(B >= 0 && ldx >= f->features, "flow_backward: bad shape");
+    ZK_REQUIRE(!grad_z || ldgz >= f->features, "flow_backward: bad ldgz");
+    ZK_REQUIRE(!grad_x || ldgx >= f->features, "flow_backward: bad ldgx");
+    ZK_REQUIRE(f->context == 0 || c, "flow_backward: flow needs a context");
+    ZK_REQUIRE(!grad_c || f->context == 0 || ldc == 0 || ldgc >= f->context, "flow_backward: bad ldgc");
+    ZK_REQUIRE(grad_x != x || !grad_x, "flow_backward: grad_x must not alias x");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = f->context;
+    if (C == 0) grad_c = nullptr;
+    if (grad_c && ldc == 0) ZK_CUDA(cudaMemsetAsync(grad_c, 0, (size_t)C * 4, st));
+    if (B == 0) return ZK_OK;
+    const int64_t Bc = flow_bwd_chunk_rows(f, B, ws_bytes);
+    ZK_REQUIRE(Bc > 0, "flow_backward: workspace too small (%zu < %zu)", ws_bytes, zk_flow_backward_min_workspace_bytes(f));
+    for (int64_t i0 = 0; i0 < B; i0 += Bc) {
+        const int64_t n = std::min(Bc, B - i0);
+        float* gc = grad_c ? (ldc == 0 ? grad_c : grad_c + i0 * ldgc) : nullptr;
+        if (gc && ldc != 0) ZK_CUDA(cudaMemset2DAsync(gc, (size_t)ldgc * 4, 0, (size_t)C * 4, (size_t)n, st));
+        ZK_TRY(flow_backward_chunk(f, x + i0 * ldx, ldx, c ? c + i0 * ldc : nullptr, ldc, n,
+                                   grad_z ? grad_z + i0 * ldgz : nullptr, ldgz, grad_ladj ? grad_ladj + i0 : nullptr,
+                                   grad_log_prob ? grad_log_prob + i0 : nullptr, grad_x ? grad_x + i0 * ldgx : nullptr,
+                                   ldgx, gc, ldgc, grads, ws, ws_bytes, st));
+    }
+    return ZK_OK;
+}
+
+}  // extern "C"

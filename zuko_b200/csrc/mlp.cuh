@@ -10,6 +10,8 @@ struct zk_mlp {
     std::vector<int> dims;       // n_linear + 1
     std::vector<float*> w;       // device, pre-masked fp32 (dims[i+1], dims[i]) row-major (owned)
     std::vector<float*> b;       // device fp32 (dims[i+1]) (owned; zeros when the layer has no bias)
+    std::vector<uint8_t*> mask;  // device bool bytes (dims[i+1], dims[i]) or nullptr = dense (owned): d(mask*W)/dW
+    std::vector<float*> wt;      // device, w[i] transposed (dims[i], dims[i+1]) for dgrad; built on first backward (owned)
     int gemm_mode = ZK_GEMM_FP32;  // resolved path
     int max_hidden = 0;
     // tcgen05 path: packed bf16 hi/lo weights (owned), see mlp_tcgen05.cu

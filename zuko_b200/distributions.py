@@ -132,7 +132,7 @@ class NormalizingFlow(Distribution):
             fused = t._fused(base.loc.shape[0])
             if fused is not None:
                 call, ctx = fused
-                fc = (_ops.FlowCall(call._handles, call.D, call.C, base.loc, base.scale), ctx)
+                fc = (_ops.FlowCall(call._handles, call.D, call.C, base.loc, base.scale, sources=call._sources, keep=call._keep), ctx)
         self.__dict__["_fc"] = fc
         return fc
 

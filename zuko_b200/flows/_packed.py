@@ -49,6 +49,19 @@ def resolve_univariate(univariate: Callable, shapes: Sequence[Size]) -> dict:
     )
 
 
+class OwnedLayer:
+    """Owns one ``zk_layer`` handle; destroys it when the last reference goes away."""
+
+    def __init__(self, handle: ctypes.c_void_p) -> None:
+        self.handle = handle
+
+    def __del__(self) -> None:
+        try:
+            E.lib().zk_layer_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class PackedLayerMixin:
     """Gives a lazy layer a cached ``zk_layer`` handle, rebuilt when any tensor it was
     packed from changes (data pointer / version / device) — optimizer steps,
@@ -73,7 +86,9 @@ class PackedLayerMixin:
             (t.data_ptr(), t._version, t.device, t.dtype) if torch.is_tensor(t) else t for t in self._layer_tensors()
         )
 
-    def _zk_layer(self) -> ctypes.c_void_p:
+    def _zk_layer_ref(self) -> OwnedLayer:
+        """The packed handle as a reference-counted owner: calls that outlive a re-pack (an
+        autograd graph held across an optimizer step) keep the handle they were built with."""
         sig = self._layer_signature()
         cached = self.__dict__.get("_zk_cache")
         if cached is not None and cached[0] == sig:
@@ -83,13 +98,26 @@ class PackedLayerMixin:
         h = ctypes.c_void_p()
         E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
         del keep
-        self.__dict__["_zk_cache"] = (sig, h)
-        return h
+        ref = OwnedLayer(h)
+        self.__dict__["_zk_cache"] = (sig, ref)
+        return ref
+
+    def _zk_layer(self) -> ctypes.c_void_p:
+        return self._zk_layer_ref().handle
 
     def _zk_release(self) -> None:
-        cached = self.__dict__.pop("_zk_cache", None)
-        if cached is not None:
-            E.lib().zk_layer_destroy(cached[1])
+        self.__dict__.pop("_zk_cache", None)  # the handle is destroyed with its last reference
+
+    def _grad_source(self) -> dict:
+        """Tensors the engine's parameter gradients of this layer belong to (see _ops.FlowCall)."""
+        hyper = getattr(self, "hyper", None)
+        if hyper is not None:
+            lins = hyper._linears()
+            return {"weights": [m.weight for m in lins], "biases": [m.bias for m in lins]}
+        phi = getattr(self, "phi", None)
+        if phi is not None:
+            return {"phi": list(phi)}
+        return {}
 
     def __del__(self) -> None:
         try:

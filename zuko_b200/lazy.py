@@ -111,6 +111,12 @@ class _Unconditional(Partial):
         return tuple(sig)
 
     def _build(self):
+        if torch.is_grad_enabled() and any(
+            torch.is_tensor(v) and v.requires_grad for v in list(self.args) + list(self.kwargs.values())
+        ):
+            # the object may hold tensors computed from the arguments (e.g. R = exp(A - A^T)): its
+            # autograd graph belongs to this forward call, so it is not cached
+            return Partial.forward(self)
         sig = self._tensor_signature()
         cached = self.__dict__.get("_built")
         if cached is not None and cached[0] == sig:

@@ -129,8 +129,6 @@ def _elementwise(phi: Tensor, x: Tensor, P: int):
     onto the engine's (B, D=1) layout.  Returns (x2 (N,1), phi2, phi_ld, shape)."""
     E.require_cuda(x, "input")
     E.require_cuda(phi, "parameters")
-    if x.requires_grad or phi.requires_grad:
-        raise NotImplementedError("zuko_b200: the engine is forward-only (no autograd through the bijectors yet)")
     batch = phi.shape[:-1]
     shape = torch.broadcast_shapes(x.shape, batch)
     x2 = x.expand(shape).reshape(-1, 1).contiguous()
@@ -138,6 +136,85 @@ def _elementwise(phi: Tensor, x: Tensor, P: int):
         return x2, phi.reshape(1, P).contiguous(), 0, shape
     phi2 = phi.expand(*shape, P).reshape(-1, P).contiguous()
     return x2, phi2, P, shape
+
+
+def _uni_forward(kind: int, K: int, bound: float, slope: float, x2: Tensor, phi: Tensor | None, ld: int):
+    """(y, ladj) of a univariate bijector on the (N, 1) layout; kind 0 = softclip."""
+    x2 = x2.detach()
+    y = torch.empty_like(x2)
+    ladj = torch.empty(x2.shape[0], device=x2.device, dtype=torch.float32)
+    L, st, N = E.lib(), E.stream_ptr(x2.device), x2.shape[0]
+    with torch.cuda.device(x2.device):
+        if kind == E.ZK_UNI_RQS:
+            E.check(L.zk_rqs_forward(x2.data_ptr(), 1, phi.detach().data_ptr(), ld, N, 1, K, bound, slope, y.data_ptr(), 1, ladj.data_ptr(), 0, st))
+        elif kind == E.ZK_UNI_AFFINE:
+            E.check(L.zk_affine_forward(x2.data_ptr(), 1, phi.detach().data_ptr(), ld, N, 1, slope, y.data_ptr(), 1, ladj.data_ptr(), 0, st))
+        else:
+            E.check(L.zk_softclip_forward(x2.data_ptr(), 1, N, 1, bound, y.data_ptr(), 1, ladj.data_ptr(), 0, st))
+    return y, ladj
+
+
+class _UniFunction(torch.autograd.Function):
+    """Autograd seam of the explicit-parameter bijectors: backward = ``zk_rqs_backward`` /
+    ``zk_affine_backward`` / ``zk_softclip_backward`` (reverse mode of transforms.py:469-567,
+    426-446, 299-316)."""
+
+    @staticmethod
+    def forward(ctx, kind, K, bound, slope, ld, x2, phi):  # noqa: ANN001
+        ctx.cfg = (kind, K, bound, slope, ld)
+        ctx.has_phi = phi is not None
+        ctx.save_for_backward(*([x2, phi] if phi is not None else [x2]))
+        return _uni_forward(kind, K, bound, slope, x2, phi, ld)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, gl):  # noqa: ANN001
+        kind, K, bound, slope, ld = ctx.cfg
+        x2 = ctx.saved_tensors[0]
+        phi = ctx.saved_tensors[1] if ctx.has_phi else None
+        need_x, need_phi = ctx.needs_input_grad[5], ctx.has_phi and ctx.needs_input_grad[6]
+        gy, gl = gy.to(torch.float32).contiguous(), gl.to(torch.float32).contiguous()
+        N = x2.shape[0]
+        gx = torch.empty_like(x2) if need_x else None
+        gphi = None
+        L, st = E.lib(), E.stream_ptr(x2.device)
+        with torch.cuda.device(x2.device):
+            if kind == 0:
+                if need_x:
+                    E.check(L.zk_softclip_backward(x2.data_ptr(), 1, N, 1, bound, gy.data_ptr(), 1, gl.data_ptr(), gx.data_ptr(), 1, st))
+                return None, None, None, None, None, gx, None
+            P = phi.shape[-1]
+            if need_phi:
+                gphi = torch.zeros_like(phi)  # (N, P) per-sample, or the (1, P) table (accumulated into)
+            need = L.zk_univariate_backward_workspace_bytes(N, 1, P, ld) if need_phi else 0
+            ws = E.Workspace.get(x2.device, need, min(need, 64 << 20)) if need else None
+            args = (gy.data_ptr(), 1, gl.data_ptr(), None if gx is None else gx.data_ptr(), 1,
+                    None if gphi is None else gphi.data_ptr(), None if ws is None else ws.data_ptr(),
+                    0 if ws is None else ws.numel(), st)  # fmt: skip
+            if kind == E.ZK_UNI_RQS:
+                E.check(L.zk_rqs_backward(x2.data_ptr(), 1, phi.data_ptr(), ld, N, 1, K, bound, slope, *args))
+            else:
+                E.check(L.zk_affine_backward(x2.data_ptr(), 1, phi.data_ptr(), ld, N, 1, slope, *args))
+        return None, None, None, None, None, gx, gphi
+
+
+def _uni_call(kind: int, K: int, bound: float, slope: float, x2: Tensor, phi: Tensor | None, ld: int):
+    if torch.is_grad_enabled() and (x2.requires_grad or (phi is not None and phi.requires_grad)):
+        return _UniFunction.apply(kind, K, bound, slope, ld, x2, phi)
+    return _uni_forward(kind, K, bound, slope, x2, phi, ld)
+
+
+_warned_inverse = False
+
+
+def _no_grad_inverse(*tensors: Tensor) -> None:
+    """The inverse direction has no backward pass yet: results are detached (warned once)."""
+    global _warned_inverse
+    if not _warned_inverse and torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        _warned_inverse = True
+        import warnings
+
+        warnings.warn("zuko_b200: the inverse of a bijector is not differentiable in this version; the result is detached.", stacklevel=3)
 
 
 class MonotonicRQSTransform(EngineTransform):
@@ -162,17 +239,13 @@ class MonotonicRQSTransform(EngineTransform):
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
         P = 3 * self.bins - 1
         x2, phi, ld, shape = _elementwise(self.phi, x, P)
-        y = torch.empty_like(x2)
-        ladj = torch.empty(x2.shape[0], device=x2.device, dtype=torch.float32)
-        with torch.cuda.device(x2.device):
-            E.check(E.lib().zk_rqs_forward(x2.data_ptr(), 1, phi.data_ptr(), ld, x2.shape[0], 1, self.bins,
-                                           self.bound, self.slope, y.data_ptr(), 1, ladj.data_ptr(), 0,
-                                           E.stream_ptr(x2.device)))  # fmt: skip
+        y, ladj = _uni_call(E.ZK_UNI_RQS, self.bins, self.bound, self.slope, x2, phi, ld)
         return y.reshape(shape), ladj.reshape(shape)
 
     def _inverse(self, y: Tensor) -> Tensor:
         P = 3 * self.bins - 1
-        y2, phi, ld, shape = _elementwise(self.phi, y, P)
+        _no_grad_inverse(y, self.phi)
+        y2, phi, ld, shape = _elementwise(self.phi.detach(), y.detach(), P)
         x = torch.empty_like(y2)
         with torch.cuda.device(y2.device):
             E.check(E.lib().zk_rqs_inverse(y2.data_ptr(), 1, phi.data_ptr(), ld, y2.shape[0], 1, self.bins,
@@ -197,15 +270,12 @@ class MonotonicAffineTransform(EngineTransform):
 
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
         x2, phi, ld, shape = _elementwise(self.phi, x, 2)
-        y = torch.empty_like(x2)
-        ladj = torch.empty(x2.shape[0], device=x2.device, dtype=torch.float32)
-        with torch.cuda.device(x2.device):
-            E.check(E.lib().zk_affine_forward(x2.data_ptr(), 1, phi.data_ptr(), ld, x2.shape[0], 1, self.slope,
-                                              y.data_ptr(), 1, ladj.data_ptr(), 0, E.stream_ptr(x2.device)))  # fmt: skip
+        y, ladj = _uni_call(E.ZK_UNI_AFFINE, 0, 5.0, self.slope, x2, phi, ld)
         return y.reshape(shape), ladj.reshape(shape)
 
     def _inverse(self, y: Tensor) -> Tensor:
-        y2, phi, ld, shape = _elementwise(self.phi, y, 2)
+        _no_grad_inverse(y, self.phi)
+        y2, phi, ld, shape = _elementwise(self.phi.detach(), y.detach(), 2)
         x = torch.empty_like(y2)
         with torch.cuda.device(y2.device):
             E.check(E.lib().zk_affine_inverse(y2.data_ptr(), 1, phi.data_ptr(), ld, y2.shape[0], 1, self.slope,
@@ -228,15 +298,13 @@ class SoftclipTransform(EngineTransform):
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
         E.require_cuda(x, "input")
         x2 = x.reshape(-1, 1).contiguous()
-        y = torch.empty_like(x2)
-        ladj = torch.empty(x2.shape[0], device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
-            E.check(E.lib().zk_softclip_forward(x2.data_ptr(), 1, x2.shape[0], 1, self.bound, y.data_ptr(), 1,
-                                                ladj.data_ptr(), 0, E.stream_ptr(x.device)))  # fmt: skip
+        y, ladj = _uni_call(0, 0, self.bound, 1e-3, x2, None, 0)
         return y.reshape(x.shape), ladj.reshape(x.shape)
 
     def _inverse(self, y: Tensor) -> Tensor:
         E.require_cuda(y, "input")
+        _no_grad_inverse(y)
+        y = y.detach()
         y2 = y.reshape(-1, 1).contiguous()
         x = torch.empty_like(y2)
         with torch.cuda.device(y.device):
@@ -253,7 +321,20 @@ class SoftclipTransform(EngineTransform):
 # --------------------------------------------------------------------------- #
 
 
-class PermutationTransform(EngineTransform):
+class _VectorLayer(EngineTransform):
+    """A parameter-free / explicit-parameter map on feature vectors that the engine knows as a
+    ``zk_layer``: evaluated as a one-layer flow call, which also gives it the autograd seam."""
+
+    def _single(self, D: int) -> _ops.FlowCall:
+        ref = _simple_layer_handle(self, D)
+        cache = self.__dict__.setdefault("_single_calls", {})
+        if D not in cache or cache[D][0] is not ref:
+            src = self._grad_source() if hasattr(self, "_grad_source") else {}
+            cache[D] = (ref, _ops.FlowCall([ref.handle], D, 0, None, None, sources=[src], keep=[ref]))
+        return cache[D][1]
+
+
+class PermutationTransform(_VectorLayer):
     """``y = x[..., order]`` — a bit-exact gather (zuko/transforms.py:1182-1214)."""
 
     domain = constraints.real_vector
@@ -271,22 +352,11 @@ class PermutationTransform(EngineTransform):
             order = str(order[:5] + [...] + order[-5:]).replace("Ellipsis", "...")
         return f"{type(self).__name__}({order})"
 
-    def _gather(self, x: Tensor, order: Tensor) -> Tensor:
-        E.require_cuda(x, "input")
-        D = order.shape[0]
-        x2 = x.reshape(-1, D).contiguous()
-        y = torch.empty_like(x2)
-        order = order.to(device=x.device, dtype=torch.int64).contiguous()
-        with torch.cuda.device(x.device):
-            E.check(E.lib().zk_permute(x2.data_ptr(), D, order.data_ptr(), x2.shape[0], D, y.data_ptr(), D,
-                                       E.stream_ptr(x.device)))  # fmt: skip
-        return y.reshape(x.shape)
-
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
-        return self._gather(x, self.order), torch.zeros_like(x[..., 0])
+        return self._single(self.order.shape[0]).forward(x, None)
 
     def _inverse(self, y: Tensor) -> Tensor:
-        return self._gather(y, torch.argsort(self.order))
+        return self._single(self.order.shape[0]).inverse(y, None)
 
     def _layer_desc(self, D: int):
         host = self.order.detach().to("cpu", torch.int64).contiguous()
@@ -294,7 +364,7 @@ class PermutationTransform(EngineTransform):
         return E.LayerDesc(kind=E.ZK_LAYER_PERMUTATION, features=D, slope=1e-3, bound=1.0, order=arr), [arr]
 
 
-class RotationTransform(EngineTransform):
+class RotationTransform(_VectorLayer):
     """``y = R x`` with ``R = exp(A - A^T)`` orthogonal (zuko/transforms.py:1217-1244).
     ``matrix_exp`` of the (D, D) generator is one-time torch plumbing; the batched
     product runs in ``zk_rotate``."""
@@ -306,28 +376,21 @@ class RotationTransform(EngineTransform):
         super().__init__()
         if A.dim() != 2:
             raise NotImplementedError("zuko_b200: batched rotation generators are not supported")
-        A = A.detach()
+        # R carries its autograd history: the engine returns dL/dR and torch chains through matrix_exp
         self.R = torch.linalg.matrix_exp(A - A.mT).contiguous()
 
-    def _apply(self, x: Tensor, transpose: int) -> Tensor:
-        E.require_cuda(x, "input")
-        E.require_cuda(self.R, "rotation matrix")
-        D = self.R.shape[0]
-        x2 = x.reshape(-1, D).contiguous()
-        y = torch.empty_like(x2)
-        with torch.cuda.device(x.device):
-            E.check(E.lib().zk_rotate(x2.data_ptr(), D, self.R.data_ptr(), transpose, x2.shape[0], D,
-                                      y.data_ptr(), D, E.stream_ptr(x.device)))  # fmt: skip
-        return y.reshape(x.shape)
+    def _grad_source(self) -> dict:
+        return {"R": self.R} if self.R.requires_grad else {}
 
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
-        return self._apply(x, 0), torch.zeros_like(x[..., 0])
+        return self._single(self.R.shape[0]).forward(x, None)
 
     def _inverse(self, y: Tensor) -> Tensor:
-        return self._apply(y, 1)
+        return self._single(self.R.shape[0]).inverse(y, None)
 
     def _layer_desc(self, D: int):
-        return E.LayerDesc(kind=E.ZK_LAYER_ROTATION, features=D, slope=1e-3, bound=1.0, rotation=self.R.data_ptr()), [self.R]
+        R = self.R.detach()
+        return E.LayerDesc(kind=E.ZK_LAYER_ROTATION, features=D, slope=1e-3, bound=1.0, rotation=R.data_ptr()), [R]
 
 
 # --------------------------------------------------------------------------- #
@@ -350,11 +413,28 @@ class _PackedLayerTransform(EngineTransform):
     def _layer_handle(self, D: int | None = None):
         return self._owner._zk_layer()
 
+    def _layer_ref(self, D: int | None = None):
+        return self._owner._zk_layer_ref()
+
+    def _grad_source(self) -> dict:
+        return self._owner._grad_source()
+
+    def _single(self) -> _ops.FlowCall:
+        """This layer alone as a flow-level call (gives it the autograd seam of _ops.FlowCall)."""
+        ref = self._layer_ref()
+        cached = self.__dict__.get("_single_call")
+        if cached is None or cached[0] is not ref:
+            call = _ops.FlowCall([ref.handle], self.features, self._owner.context, None, None,
+                                 sources=[self._grad_source()], keep=[ref])  # fmt: skip
+            cached = (ref, call)
+            self.__dict__["_single_call"] = cached
+        return cached[1]
+
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
-        return _ops.layer_forward(self._layer_handle(), self.features, x, self._c)
+        return self._single().forward(x, self._c)
 
     def _inverse(self, y: Tensor) -> Tensor:
-        return _ops.layer_inverse(self._layer_handle(), self.features, y, self._c)
+        return self._single().inverse(y, self._c)
 
     def __repr__(self) -> str:
         return f"{type(self).__name__}()"
@@ -394,7 +474,7 @@ def _simple_layer_handle(t: Transform, D: int):
         E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
         cache[key] = _OwnedLayer(h)
         del keep
-    return cache[key].handle
+    return cache[key]
 
 
 class _OwnedLayer:
@@ -452,7 +532,7 @@ class ComposedTransform(EngineTransform):
             return self.__dict__[key]
         call = None
         ctx = None
-        handles = []
+        handles, refs, sources = [], [], []
         ok = self.domain_dim == 1 and self.codomain_dim == 1
         C = 0
         for t in self.transforms if ok else ():
@@ -466,14 +546,17 @@ class ComposedTransform(EngineTransform):
                         break
                     ctx = t._c
                     C = t._owner.context
-                handles.append(t._layer_handle())
+                refs.append(t._layer_ref())
+                sources.append(t._grad_source())
             elif hasattr(t, "_layer_desc"):
-                handles.append(_simple_layer_handle(t, D))
+                refs.append(_simple_layer_handle(t, D))
+                sources.append(t._grad_source() if hasattr(t, "_grad_source") else {})
             else:
                 ok = False
                 break
         if ok:
-            call = (_ops.FlowCall(handles, D, C, None, None), ctx)
+            handles = [r.handle for r in refs]
+            call = (_ops.FlowCall(handles, D, C, None, None, sources=sources, keep=refs), ctx)
         self.__dict__[key] = call
         return call
 
