@@ -57,7 +57,7 @@ def measured_peaks() -> dict:
 
 class ClockSampler:
     """Samples SM clocks / throttle reasons of one GPU WHILE the timed region runs: an NVML
-    polling thread (2 ms period, so even a 40 ms region gets samples); `nvidia-smi -lms` is the
+    polling thread (10 ms period by default, ZK_BENCH_CLOCK_PERIOD_MS); `nvidia-smi -lms` is the
     fallback when NVML cannot be initialised."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -68,6 +68,8 @@ class ClockSampler:
         self.index, self.rows, self.proc, self.thread = index, [], None, None
         self.stop = threading.Event()
         self.source = None
+        self.mode = os.environ.get("ZK_BENCH_CLOCKS", "nvml")  # nvml | smi | off
+        self.period = float(os.environ.get("ZK_BENCH_CLOCK_PERIOD_MS", "10")) * 1e-3
 
     def _nvml_handle(self):
         import pynvml as N
@@ -91,20 +93,44 @@ class ClockSampler:
                 self.rows.append([sm, smax, [n for n, b in zip(self.NAMES, bits) if r & b]])
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
-    def __enter__(self):
+    def prepare(self):
+        """NVML initialisation + one full round of queries, BEFORE the warm-up: the first NVML
+        calls of a process (and of a fresh box) take tens of milliseconds inside the driver and
+        must not land in the timed region."""
+        self._nvml = None
+        if self.mode != "nvml":
+            return self
         try:
             N, h = self._nvml_handle()
+            N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self._nvml = (N, h)
+        except Exception:
+            self._nvml = None
+        return self
+
+    def __enter__(self):
+        if self.mode == "off":
+            return self
+        try:
+            if self.mode == "smi":
+                raise RuntimeError("nvidia-smi requested")
+            N, h = getattr(self, "_nvml", None) or self._nvml_handle()
             self.thread = threading.Thread(target=self._poll_nvml, args=(N, h), daemon=True)
             self.thread.start()
             self.source = "nvml"
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 0.2:  # first sample landed
+                time.sleep(0.001)
             return self
         except Exception:
             self.thread = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(max(5, int(self.period * 1e3)))],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
             self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
@@ -276,14 +302,19 @@ def run_ours(args) -> None:
             ref = spec.log_prob(xs_host[0][:n].numpy(), cs_host[0][:n].numpy())
             parity = {"rows": n, "max_rel_err_vs_fp64_oracle": float(np.max(np.abs(ours - ref) / np.maximum(np.abs(ref), 1.0)))}
 
-        for i in range(max(args.warmup, 3)):
+        clk = ClockSampler(local).prepare()
+        # warm-up: at least W (>= 3) steps and never fewer than 50 (~0.25 s; the same count on every
+        # rank — each step holds a collective), so that clocks / power state have settled and every
+        # lazy initialisation (allocator, NVML, module loading) is behind us
+        warm_steps = max(args.warmup, 3, 50)
+        for i in range(warm_steps):
             step(i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         launches0 = E.lib().zk_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
+        with clk:
             torch.cuda.synchronize()
             e0.record()
             for i in range(args.steps):
@@ -337,7 +368,7 @@ def run_ours(args) -> None:
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{rows} rows of the workload, oracle fp32 C port with OpenMP, {sec:.1f} s"}  # fmt: skip
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "warmup_steps_run": warm_steps,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (conditioner GEMMs: %s)" % gemm_mode_name(flow), "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,

@@ -183,10 +183,18 @@ def oracle_named_grads(flow, layer_grads) -> dict:
     return out
 
 
-def assert_param_grads(named: dict, gg: dict, prefix: str, rtol: float, what: str = ""):
+def grad_bar(gg: dict, prefix: str, name: str, rtol: float, ref32_factor: float) -> float:
+    """Parity bar of one gradient tensor: ``max(rtol, ref32_factor * e32)`` where e32 is the
+    reference's OWN fp32-vs-fp64 deviation on that tensor (stored by make_golden_grad.py), the
+    same calibration the forward parity rule uses (assert_log_prob_parity)."""
+    key = f"{prefix}err32/{name}"
+    return max(rtol, ref32_factor * float(gg[key])) if (ref32_factor and key in gg) else rtol
+
+
+def assert_param_grads(named: dict, gg: dict, prefix: str, rtol: float, what: str = "", ref32_factor: float = 0.0):
     """Compares a name -> flat-gradient dict with the golden gradients (full or sampled).
     Error is measured relative to the largest entry of each tensor's golden gradient
-    (`|ours - ref| <= rtol * max|ref|`), the natural scale of a summed-over-batch gradient."""
+    (`|ours - ref| <= bar * max|ref|`), the natural scale of a summed-over-batch gradient."""
     checked = 0
     for key in gg:
         if key.startswith(prefix + "pg/"):
@@ -201,7 +209,8 @@ def assert_param_grads(named: dict, gg: dict, prefix: str, rtol: float, what: st
             ours = ours[grad_sample_idx(ours.size)]
         scale = max(float(np.abs(ref).max()), 1e-30)
         err = float(np.abs(ours - ref).max()) / scale
-        assert err <= rtol, f"{what}: d/d{name}: max err {err:.3e} of max|grad| {scale:.3e} (bar {rtol:.1e})"
+        bar = grad_bar(gg, prefix, name, rtol, ref32_factor)
+        assert err <= bar, f"{what}: d/d{name}: max err {err:.3e} of max|grad| {scale:.3e} (bar {bar:.1e})"
         checked += 1
     assert checked > 0, f"{what}: golden file holds no parameter gradients under {prefix}"
     return checked

@@ -91,13 +91,28 @@ def grad_case(name: str, build, rows: int, *, seed=0, full=True, w_scale=1.0):
     gz = gen(9002, B, D).double()
     gl = gen(9003, B).double()
     info = {"rows": np.int64(rows), "g": g.numpy(), "gz": gz.numpy(), "gl": gl.numpy()}
-    info.update(grads_of(f64, x, c, lambda f, xx, cc: (g * f(cc).log_prob(xx)).sum(), full, "lp/"))
+    def l1(f, xx, cc):
+        return (g.to(xx.dtype) * f(cc).log_prob(xx)).sum()
 
     def l2(f, xx, cc):
         z, ladj = f(cc).transform.call_and_ladj(xx)
-        return (gz * z).sum() + (gl * ladj).sum()
+        return (gz.to(xx.dtype) * z).sum() + (gl.to(xx.dtype) * ladj).sum()
 
+    info.update(grads_of(f64, x, c, l1, full, "lp/"))
     info.update(grads_of(f64, x, c, l2, full, "tr/"))
+    # the reference's OWN fp32 deviation from its fp64 gradients, per tensor, relative to the
+    # largest fp64 entry: calibrates the parity bar of the fp32 engine (like log_prob32 / log_prob64
+    # do for the forward pass)
+    c32 = None if c is None else c.float()
+    for prefix, fn in (("lp/", l1), ("tr/", l2)):
+        g32 = grads_of(flow, x.float(), c32, fn, True, "")
+        g64 = grads_of(f64, x, c, fn, True, "")
+        for k, v64 in g64.items():
+            if k.startswith("pg_norm/"):
+                continue
+            scale = max(float(np.abs(v64).max()), 1e-30)
+            key = k[3:] if k.startswith("pg/") else k
+            info[f"{prefix}err32/{key}"] = np.float64(np.abs(g32[k].astype(np.float64) - v64).max() / scale)
     np.savez_compressed(OUT / f"grad_{name}.npz", **info)
     print(f"grad_{name}: rows={rows} D={D} |gx|max={np.abs(info['lp/gx']).max():.3e}")
 

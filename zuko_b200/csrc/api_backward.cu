@@ -53,7 +53,7 @@ struct MlpBwdBufs {
 };
 
 size_t mlp_bwd_scratch(const zk_mlp* m) {
-    size_t s = 0;
+    size_t s = colsum_scratch_bytes(m->dims[0]);  // broadcast-context column sum of the input gradient
     for (int i = 0; i < m->n_linear; ++i)
         s = std::max(s, std::max(wgrad_scratch_bytes(m->dims[i + 1], m->dims[i]), colsum_scratch_bytes(m->dims[i + 1])));
     return a256(s);
