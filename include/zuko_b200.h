@@ -285,6 +285,11 @@ zk_status zk_flow_backward(const zk_flow_desc* flow, const float* x, int64_t ldx
                            const zk_layer_grads* const* grads, void* workspace,
                            size_t workspace_bytes, zk_stream stream);
 
+/* 1 (default): the conditioner GEMMs of the backward pass (forward recompute, dgrad, wgrad) of a
+ * handle packed for tcgen05 run on the tensor cores (split-bf16, fp32 accumulate); 0: fp32 FMA on
+ * CUDA cores (exact-order arbitration path).  Returns the previous value. */
+int zk_set_tc_backward(int on);
+
 /* Transcendental arithmetic of the bijector kernels: 1 (default) = MUFU rcp / ex2 / lg2
  * approximations, 0 = IEEE division + expf / logf.  Process-wide; returns the previous
  * value.  Both settings meet the 1e-5 parity bar on the BASELINE configs (tests/). */

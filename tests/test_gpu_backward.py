@@ -205,6 +205,36 @@ def test_chunked_backward_and_determinism(device):
     close(full[1][:n], ogc, 2e-5, "gc vs oracle")
 
 
+@pytest.mark.parametrize("name,B", [("cfg2_nsf", 6000), ("cfg5_nsf", 2500), ("cfg3_maf", 3000), ("cfg4_nsf", 1500)])
+def test_tensor_core_and_fp32_backward_agree(device, name, B):
+    """The tcgen05 split-bf16 backward (forward recompute, dgrad, batch-sliced wgrad) against the
+    fp32 CUDA-core backward of the same handle on a batch large enough for several batch slices,
+    and both against the gradient oracle on the leading rows."""
+    flow = build_flow(name).to(device)
+    D = flow.base.loc.shape[0]
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, D, generator=gen).numpy()
+    C = flow.transform.transforms[0].context
+    c = torch.randn(B, C, generator=gen).numpy() if C else None
+    gg = {"g": torch.randn(B, generator=gen).numpy()}
+    tc = _flow_grads(flow, x, c, "lp", gg, device)
+    prev = E.lib().zk_set_tc_backward(0)
+    try:
+        f32 = _flow_grads(flow, x, c, "lp", gg, device)
+    finally:
+        E.lib().zk_set_tc_backward(prev)
+    close(tc[0], f32[0], 2e-5, f"{name} gx tc vs fp32")
+    if c is not None:
+        close(tc[1], f32[1], 2e-5, f"{name} gc tc vs fp32")
+    assert set(tc[2]) == set(f32[2])
+    for k in f32[2]:
+        close(tc[2][k], f32[2][k], 5e-5, f"{name} d/d{k} tc vs fp32")
+    n = 64
+    spec = O.flowspec_from_module(build_flow(name))
+    ogx, _, _ = OG.flow_backward(spec, x[:n], None if c is None else c[:n], g_log_prob=gg["g"][:n])
+    close(tc[0][:n], ogx, 5e-5, f"{name} gx vs oracle")
+
+
 def test_training_step_decreases_nll(device):
     """README.md:43-49: a few Adam steps through the engine's backward reduce the NLL, and the
     packed weights follow the optimizer (re-pack on version change)."""

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "zk_launch_count": (c_int64, []),
     "zk_set_fast_math": (c_int, [c_int]),
     "zk_set_fused_layers": (c_int, [c_int]),
+    "zk_set_tc_backward": (c_int, [c_int]),
     "zk_debug_timeline": (None, [c_void_p]),
     "zk_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "zk_rqs_forward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_float, c_float, _P, c_int64, _P, c_int, _P]),

@@ -16,6 +16,7 @@
 
 #include "api_internal.cuh"
 #include "backward.cuh"
+#include "tc_common.cuh"
 
 using namespace zk;
 namespace zkapi {}
@@ -26,6 +27,7 @@ namespace zkapi {
 namespace {
 
 std::mutex g_bwd_mu;
+std::atomic<int> g_tc_backward{1};
 
 // transposed pre-masked weights for dgrad, built on first use
 zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
@@ -40,6 +42,7 @@ zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
         m->wt.push_back(t);
         ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], t, st));
     }
+    if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr) ZK_TRY(tc_pack_backward(m, st));
     ZK_CUDA(cudaStreamSynchronize(st));
     return ZK_OK;
 }
@@ -113,13 +116,148 @@ zk_status mlp_backward(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, bool wan
     return ZK_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// conditioner backward on the tensor cores (handles packed for tcgen05): every GEMM-shaped piece —
+// forward recompute with saved activations, dgrad, wgrad — is linear_tc_kernel (split-bf16, fp32
+// accumulation in TMEM); see the block comment at the end of mlp_tcgen05.cu.
+// ---------------------------------------------------------------------------
+struct TcBwdPlan {
+    int n = 0;
+    std::vector<int> Kp;       // pad64(dims[i]), i = 0..n
+    std::vector<int> S, Bs, slice_m;  // per linear layer: batch slices of the wgrad GEMM
+    int max_hidden_kp = 0;
+    size_t gT = 0, aT = 0, partial = 0, scratch = 0;
+};
+
+TcBwdPlan tc_plan(const zk_mlp* m, int64_t B) {
+    TcBwdPlan p;
+    p.n = m->n_linear;
+    for (int i = 0; i <= p.n; ++i) p.Kp.push_back(pad64(m->dims[i]));
+    for (int i = 1; i < p.n; ++i) p.max_hidden_kp = std::max(p.max_hidden_kp, p.Kp[i]);
+    p.scratch = colsum_scratch_bytes(m->dims[0]);
+    for (int i = 0; i < p.n; ++i) {
+        const int N = m->dims[i + 1], K = m->dims[i];
+        const int sm = (N + 127) / 128 * 128;
+        const int64_t tiles = (int64_t)(sm / 128) * ((K + 255) / 256);
+        int64_t S = ceil_div(2 * 148, tiles);
+        S = std::max<int64_t>(1, std::min<int64_t>(S, B / 512));
+        const int Bs = pad64((int)ceil_div(B, S));
+        p.S.push_back((int)S);
+        p.Bs.push_back(Bs);
+        p.slice_m.push_back(sm);
+        p.gT = std::max(p.gT, (size_t)4 * S * sm * Bs);
+        p.aT = std::max(p.aT, (size_t)4 * S * p.Kp[i] * Bs);
+        p.partial = std::max(p.partial, (size_t)4 * S * sm * K);
+        p.scratch = std::max(p.scratch, std::max(colsum_scratch_bytes(N), colsum_planes_scratch_bytes(N)));
+    }
+    return p;
+}
+
+bool mlp_uses_tc(const zk_mlp* m) { return m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr; }
+
+size_t tc_bwd_ws(const zk_mlp* m, int64_t B) {
+    const TcBwdPlan p = tc_plan(m, B);
+    size_t s = 2 * a256((size_t)B * m->dims[0] * 4);  // A0 (fp32 cat) + gin
+    for (int i = 0; i < p.n; ++i) s += a256((size_t)B * p.Kp[i] * 4);  // saved activation planes
+    s += a256((size_t)B * m->dims[p.n] * 4);                            // phi / gphi (fp32)
+    s += a256((size_t)B * p.Kp[p.n] * 4);                               // planes of gphi
+    if (p.n > 1) s += 2 * a256((size_t)B * p.max_hidden_kp * 4);        // dgrad ping-pong planes
+    return s + a256(p.gT) + a256(p.aT) + a256(p.partial) + a256(p.scratch);
+}
+
+struct TcBwdBufs {
+    float* a0 = nullptr;
+    float* gin = nullptr;
+    std::vector<__nv_bfloat16*> P;  // saved activation planes, [2][B][Kp[i]]
+    float* out = nullptr;           // phi, then gphi
+    __nv_bfloat16* G = nullptr;     // planes of gphi
+    __nv_bfloat16* gbuf[2] = {nullptr, nullptr};
+    __nv_bfloat16* gT = nullptr;
+    __nv_bfloat16* aT = nullptr;
+    float* partial = nullptr;
+    void* scratch = nullptr;
+};
+
+bool tc_bwd_carve(const zk_mlp* m, const TcBwdPlan& p, int64_t B, Arena& ar, TcBwdBufs& b) {
+    b.a0 = ar.take<float>((size_t)B * m->dims[0]);
+    b.gin = ar.take<float>((size_t)B * m->dims[0]);
+    b.P.resize(p.n);
+    for (int i = 0; i < p.n; ++i) b.P[i] = ar.take<__nv_bfloat16>((size_t)2 * B * p.Kp[i]);
+    b.out = ar.take<float>((size_t)B * m->dims[p.n]);
+    b.G = ar.take<__nv_bfloat16>((size_t)2 * B * p.Kp[p.n]);
+    if (p.n > 1) {
+        b.gbuf[0] = ar.take<__nv_bfloat16>((size_t)2 * B * p.max_hidden_kp);
+        b.gbuf[1] = ar.take<__nv_bfloat16>((size_t)2 * B * p.max_hidden_kp);
+    }
+    b.gT = (__nv_bfloat16*)ar.take<char>(p.gT);
+    b.aT = (__nv_bfloat16*)ar.take<char>(p.aT);
+    b.partial = (float*)ar.take<char>(p.partial);
+    b.scratch = ar.take<char>(p.scratch);
+    return ar.ok;
+}
+
+// b.a0 = cat(x, c) must be filled; leaves phi in b.out and every layer input in b.P
+zk_status tc_forward_save(const zk_mlp* m, const TcBwdPlan& p, const TcBwdBufs& b, int64_t B, cudaStream_t st) {
+    const TcPack* pk = tc_pack_of(m);
+    ZK_TRY(launch_split_planes(b.a0, m->dims[0], m->dims[0], nullptr, 0, 0, B, p.Kp[0], b.P[0], st));
+    for (int i = 0; i < p.n; ++i) {
+        const bool last = (i == p.n - 1);
+        TcGemmArgs g;
+        g.a_planes = b.P[i]; g.M = B; g.Kp = p.Kp[i]; g.mapW = &pk->layers[i].mapW; g.N = m->dims[i + 1];
+        g.bias = m->b[i]; g.relu = last ? 0 : 1; g.n_terms = pk->n_terms;
+        if (last) { g.out_f32 = b.out; g.ldo = m->dims[p.n]; }
+        else { g.out_planes = b.P[i + 1]; g.Np = p.Kp[i + 1]; }
+        ZK_TRY(tc_gemm(g, st));
+    }
+    return ZK_OK;
+}
+
+// b.out holds dL/d(out) (fp32); on exit b.gin = dL/d(input) when want_gin
+zk_status tc_mlp_backward(const zk_mlp* m, const TcBwdPlan& p, const TcBwdBufs& b, int64_t B, bool want_gin,
+                          const zk_layer_grads* grads, cudaStream_t st) {
+    const TcPack* pk = tc_pack_of(m);
+    const int n = p.n;
+    ZK_TRY(launch_split_planes(b.out, m->dims[n], m->dims[n], nullptr, 0, 0, B, p.Kp[n], b.G, st));
+    const __nv_bfloat16* g = b.G;  // planes [2][B][Kp[i + 1]] of dL/d(output of layer i)
+    for (int i = n - 1; i >= 0; --i) {
+        const int N = m->dims[i + 1], K = m->dims[i];
+        if (grads && grads->grad_weight && grads->grad_weight[i]) {
+            const int S = p.S[i], Bs = p.Bs[i], sm = p.slice_m[i];
+            if (i == n - 1) ZK_TRY(launch_transpose_split_f32(b.out, N, B, N, S, sm, Bs, b.gT, st));
+            else ZK_TRY(launch_transpose_planes(g, B, p.Kp[i + 1], S, sm, Bs, b.gT, st));
+            ZK_TRY(launch_transpose_planes(b.P[i], B, p.Kp[i], S, p.Kp[i], Bs, b.aT, st));
+            CUtensorMap mapAT;
+            ZK_TRY(make_plane_map(&mapAT, b.aT, (int64_t)S * p.Kp[i], Bs, 256));
+            TcGemmArgs w;
+            w.a_planes = b.gT; w.M = (int64_t)S * sm; w.Kp = Bs; w.mapW = &mapAT; w.N = K;
+            w.out_f32 = b.partial; w.ldo = K; w.slice_m = sm; w.w_slice_rows = p.Kp[i]; w.n_terms = pk->n_terms;
+            ZK_TRY(tc_gemm(w, st));
+            ZK_TRY(launch_wgrad_reduce_sliced(b.partial, S, sm, N, K, m->mask[i], grads->grad_weight[i], st));
+        }
+        if (grads && grads->grad_bias && grads->grad_bias[i]) {
+            if (i == n - 1) ZK_TRY(launch_colsum_add(b.out, N, B, N, grads->grad_bias[i], b.scratch, st));
+            else ZK_TRY(launch_colsum_planes_add(g, B, p.Kp[i + 1], N, grads->grad_bias[i], b.scratch, st));
+        }
+        if (i > 0 || want_gin) {
+            TcGemmArgs d;
+            d.a_planes = g; d.M = B; d.Kp = p.Kp[i + 1]; d.mapW = &pk->bwd[i].mapW; d.N = K; d.n_terms = pk->n_terms;
+            if (i == 0) { d.out_f32 = b.gin; d.ldo = K; }
+            else { d.out_planes = b.gbuf[i & 1]; d.Np = p.Kp[i]; d.gate = b.P[i]; }
+            ZK_TRY(tc_gemm(d, st));
+            g = b.gbuf[i & 1];
+        }
+    }
+    return ZK_OK;
+}
+
 size_t layer_bwd_ws(const zk_layer* l, int64_t B) {
     if (!l || B <= 0) return 0;
     const size_t table = a256((size_t)B * l->D * l->P * 4) + a256(colsum_scratch_bytes(std::max(1, l->D * l->P)));
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE:
         case ZK_LAYER_COUPLING:
-            return mlp_bwd_ws(l->hyper, B) + 1024;
+            return (mlp_uses_tc(l->hyper) ? std::max(tc_bwd_ws(l->hyper, B), mlp_bwd_ws(l->hyper, B)) : mlp_bwd_ws(l->hyper, B)) + 1024;
         case ZK_LAYER_ELEMENTWISE:
             return (l->hyper ? mlp_bwd_ws(l->hyper, B) : 0) + table + 1024;
         case ZK_LAYER_ROTATION:
@@ -147,14 +285,31 @@ zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, co
             const int nx = coupling ? l->n_a : l->D;
             const int nt = coupling ? l->n_b : l->D;  // transformed dims
             ZK_TRY(mlp_ensure_backward(m, st));
+            u.phi_ld = (int64_t)nt * l->P; u.D = nt;
+            u.dim_map = coupling ? l->idx_b : nullptr;
+            const bool per_row_gc = (gc != nullptr && l->C > 0 && ldc != 0);
+            if (mlp_uses_tc(m) && g_tc_backward.load()) {
+                // tensor-core path: forward recompute, dgrad and wgrad on linear_tc_kernel
+                const TcBwdPlan plan = tc_plan(m, B);
+                TcBwdBufs tb;
+                ZK_REQUIRE(tc_bwd_carve(m, plan, B, ar, tb), "layer_backward: workspace too small");
+                ZK_TRY(launch_concat(x, ldx, coupling ? l->idx_a : nullptr, nx, c, ldc, l->C, B, tb.a0, st));
+                ZK_TRY(tc_forward_save(m, plan, tb, B, st));
+                u.phi = tb.out; u.gphi = tb.out;
+                ZK_TRY(launch_univariate_backward(u, st));
+                ZK_TRY(tc_mlp_backward(m, plan, tb, B, true, grads, st));
+                ZK_TRY(launch_input_grad(tb.gin, nx, l->C, coupling ? l->idx_a : nullptr, B, gx, ldgx,
+                                         coupling ? gy : nullptr, ldgy, per_row_gc ? gc : nullptr, ldgc, st));
+                if (gc != nullptr && l->C > 0 && ldc == 0)
+                    ZK_TRY(launch_colsum_add(tb.gin + nx, m->dims[0], B, l->C, gc, tb.scratch, st));
+                return ZK_OK;
+            }
             MlpBwdBufs b;
             ZK_REQUIRE(mlp_bwd_carve(m, B, ar, b), "layer_backward: workspace too small");
             ZK_TRY(launch_concat(x, ldx, coupling ? l->idx_a : nullptr, nx, c, ldc, l->C, B, b.acts[0], st));
             ZK_TRY(mlp_forward_save(m, b, B, st));
-            u.phi = b.out; u.phi_ld = (int64_t)nt * l->P; u.gphi = b.out; u.D = nt;
-            u.dim_map = coupling ? l->idx_b : nullptr;
+            u.phi = b.out; u.gphi = b.out;
             ZK_TRY(launch_univariate_backward(u, st));  // gx[:, transformed] = direct term
-            const bool per_row_gc = (gc != nullptr && l->C > 0 && ldc != 0);
             ZK_TRY(mlp_backward(m, b, B, true, grads, st));
             // coupling: gx[:, idx_a] = gy[:, idx_a] + gin[:, :n_a] (y_a = x_a, transforms.py:1069)
             ZK_TRY(launch_input_grad(b.gin, nx, l->C, coupling ? l->idx_a : nullptr, B, gx, ldgx,
@@ -322,6 +477,8 @@ zk_status uni_backward_entry(int uni, const float* x, int64_t ldx, const float* 
 }  // namespace zkapi
 
 extern "C" {
+
+int zk_set_tc_backward(int on) { return g_tc_backward.exchange(on ? 1 : 0); }
 
 size_t zk_univariate_backward_workspace_bytes(int64_t B, int D, int P, int64_t phi_ld) {
     if (phi_ld != 0 || B <= 0 || D <= 0 || P <= 0) return 0;

@@ -56,6 +56,10 @@ struct TcParams {
     int64_t ldo;
     __nv_bfloat16* out_planes;  // [2][M][Np]
     int Np;                     // padded width of the next layer's K
+    // backward pass (tc_gemm): ReLU gate and batch-sliced weight operand
+    const __nv_bfloat16* gate;  // [M][Np] hi plane of a ReLU output: out = gate > 0 ? out : 0 (planes output only)
+    int slice_m;                // > 0: rows [s * slice_m, (s + 1) * slice_m) of A pair with W rows s * w_slice_rows + n
+    int w_slice_rows;
 };
 
 // ---------------------------------------------------------------------------
@@ -111,15 +115,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int m0 = (t / p.n_chunks) * BM;
                 const int n0 = (t % p.n_chunks) * BN;
+                // split-K wgrad: the batch slice this M tile belongs to selects the W rows
+                const int wr = n0 + (p.slice_m > 0 ? (m0 / p.slice_m) * p.w_slice_rows : 0);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], bytes);
                     tma_load_3d(st, &mapA, &full_bar[stage], kb * BK, m0, 0);                      // A hi
-                    tma_load_3d(st + 2 * A_TILE_BYTES, &mapW, &full_bar[stage], kb * BK, n0, 0);   // W hi
+                    tma_load_3d(st + 2 * A_TILE_BYTES, &mapW, &full_bar[stage], kb * BK, wr, 0);   // W hi
                     if (p.n_terms == 3) {
                         tma_load_3d(st + A_TILE_BYTES, &mapA, &full_bar[stage], kb * BK, m0, 1);   // A lo
-                        tma_load_3d(st + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapW, &full_bar[stage], kb * BK, n0, 1);  // W lo
+                        tma_load_3d(st + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapW, &full_bar[stage], kb * BK, wr, 1);  // W lo
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -187,7 +193,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c0 + j;
-                    float f = __uint_as_float(r[j]) + ((n < p.N) ? __ldg(p.bias + n) : 0.f);
+                    float f = __uint_as_float(r[j]) + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
                     if (p.relu) f = fmaxf(f, 0.f);
                     v[j] = (n < p.N) ? f : 0.f;  // padded columns feed the next layer as exact zeros
                 }
@@ -205,6 +211,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             if (j < lim) dst[j] = v[j];
                     }
                 } else {
+                    if (p.gate != nullptr) {  // d relu: zero where the forward activation was not positive
+                        const uint4* gp = reinterpret_cast<const uint4*>(p.gate + (int64_t)row * p.Np + n0 + c0);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 gv = __ldg(gp + q4);
+                            const uint32_t w4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint32_t b0 = w4[u] & 0xffffu, b1 = w4[u] >> 16;
+                                const int j = q4 * 8 + u * 2;
+                                if (!((b0 & 0x7fffu) != 0u && (b0 & 0x8000u) == 0u)) v[j] = 0.f;
+                                if (!((b1 & 0x7fffu) != 0u && (b1 & 0x8000u) == 0u)) v[j + 1] = 0.f;
+                            }
+                        }
+                    }
                     // split into bf16 hi / lo planes (K-major operand of the next layer)
                     __nv_bfloat16* hi = p.out_planes + (int64_t)row * p.Np + n0 + c0;
                     __nv_bfloat16* lo = hi + (int64_t)p.M * p.Np;
@@ -327,6 +348,7 @@ void tc_destroy(zk_mlp* m) {
     TcPack* pk = (TcPack*)m->tc;
     if (!pk) return;
     for (auto& l : pk->layers) cudaFree(l.w);
+    for (auto& l : pk->bwd) cudaFree(l.w);
     for (auto* q : pk->fused.w) cudaFree(q);
     for (auto* q : pk->fused.bias) cudaFree(q);
     cudaFree(pk->fused.sched);
@@ -424,6 +446,7 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
         p.ldo = ldo;
         p.out_planes = last ? nullptr : hid[i & 1];
         p.Np = last ? 0 : pk->layers[i + 1].Kp;
+        p.gate = nullptr; p.slice_m = 0; p.w_slice_rows = 0;
         if (!last) {
             // the next layer reads columns [0, Np): they are all written when the chunks cover Np
             ZK_REQUIRE(p.n_chunks * BN >= p.Np, "tc_forward: internal padding error");
@@ -436,5 +459,200 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
     }
     return ZK_OK;
 }
+
+// ===========================================================================
+// backward pass on the tensor cores: the same GEMM kernel drives
+//   forward-with-saved-activations, dgrad (A = g planes, W = transposed weights, ReLU gate in the
+//   epilogue) and wgrad (A = g^T, W = act^T, both batch-major; the batch is cut into S slices that
+//   become extra M tiles, each pairing with its own rows of the W operand; fp32 partials are
+//   reduced in a fixed order by wgrad_reduce_sliced_kernel).
+// ===========================================================================
+namespace {
+
+// bf16 planes [2][M][Kp]  ->  [2][S][Rp][Bs]: out[pl][s][r][j] = in[pl][s*Bs + j][r] (0 beyond M / Kp)
+__global__ void transpose_planes_kernel(const __nv_bfloat16* in, int64_t M, int Kp, int S, int Rp, int Bs,
+                                        __nv_bfloat16* out) {
+    __shared__ uint16_t tile[32][34];
+    const int pl = blockIdx.z;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;  // position along S*Bs
+    const int r0 = blockIdx.y * 32;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(in) + (int64_t)pl * M * Kp;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(out) + (int64_t)pl * S * Rp * Bs;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t b = b0 + j;  // batch index (slices are contiguous in b)
+        const int r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (b < M && r < Kp) ? src[b * Kp + r] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j;
+        const int64_t b = b0 + threadIdx.x;
+        if (r < Rp && b < (int64_t)S * Bs) {
+            const int64_t s = b / Bs, jj = b - s * Bs;
+            dst[(s * Rp + r) * Bs + jj] = tile[threadIdx.x][j];
+        }
+    }
+}
+
+// fp32 (M, N) row-major (stride ld)  ->  bf16 hi/lo planes [2][S][Rp][Bs], transposed
+__global__ void transpose_split_f32_kernel(const float* in, int64_t ld, int64_t M, int N, int S, int Rp, int Bs,
+                                           __nv_bfloat16* out) {
+    __shared__ float tile[32][33];
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t b = b0 + j;
+        const int r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (b < M && r < N) ? in[b * ld + r] : 0.f;
+    }
+    __syncthreads();
+    const int64_t plane = (int64_t)S * Rp * Bs;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j;
+        const int64_t b = b0 + threadIdx.x;
+        if (r < Rp && b < (int64_t)S * Bs) {
+            const int64_t s = b / Bs, jj = b - s * Bs;
+            const float v = tile[threadIdx.x][j];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const int64_t o = (s * Rp + r) * Bs + jj;
+            out[o] = h;
+            out[plane + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
+// gw (N, K) += mask ? sum_s partial[(s * slice_m + n) * K + k] : 0
+__global__ void wgrad_reduce_sliced_kernel(const float* partial, int S, int slice_m, int N, int K,
+                                           const uint8_t* mask, float* gw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    if (mask && !mask[i]) return;
+    const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += partial[((int64_t)s * slice_m + n) * K + k];
+    gw[i] += t;
+}
+
+// column sums of (hi + lo) planes [2][M][Np] over a row slice (stage 1 of the fixed-order reduction)
+__global__ void colsum_planes_stage1(const __nv_bfloat16* planes, int64_t M, int Np, int N, int64_t rows_per_slice,
+                                     float* partial) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const int64_t lo_r = (int64_t)blockIdx.y * rows_per_slice;
+    const int64_t hi_r = min(M, lo_r + rows_per_slice);
+    const __nv_bfloat16* hi = planes;
+    const __nv_bfloat16* lo = planes + M * (int64_t)Np;
+    float acc = 0.f;
+    if (col < N)
+        for (int64_t r = lo_r + ty; r < hi_r; r += 8)
+            acc += __bfloat162float(hi[r * Np + col]) + __bfloat162float(lo[r * Np + col]);
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][tx];
+        partial[(int64_t)blockIdx.y * N + col] = t;
+    }
+}
+__global__ void colsum_planes_stage2(const float* partial, int S, int N, float* out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float t = 0.f;
+    for (int z = 0; z < S; ++z) t += partial[(int64_t)z * N + n];
+    out[n] += t;
+}
+
+}  // namespace
+
+zk_status launch_split_planes(const float* x, int64_t ldx, int dx, const float* c, int64_t ldc, int dc,
+                              int64_t M, int Kp, __nv_bfloat16* out, cudaStream_t st) {
+    if (M == 0) return ZK_OK;
+    const int64_t n = M * (Kp / 8);
+    split_input_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, ldx, dx, c, ldc, dc, M, Kp, out);
+    return check_launch("split_input_kernel");
+}
+
+zk_status launch_transpose_planes(const __nv_bfloat16* in, int64_t M, int Kp, int S, int Rp, int Bs,
+                                  __nv_bfloat16* out, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 32), (unsigned)ceil_div(Rp, 32), 2);
+    transpose_planes_kernel<<<grid, dim3(32, 8), 0, st>>>(in, M, Kp, S, Rp, Bs, out);
+    return check_launch("transpose_planes_kernel");
+}
+
+zk_status launch_transpose_split_f32(const float* in, int64_t ld, int64_t M, int N, int S, int Rp, int Bs,
+                                     __nv_bfloat16* out, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 32), (unsigned)ceil_div(Rp, 32), 1);
+    transpose_split_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, M, N, S, Rp, Bs, out);
+    return check_launch("transpose_split_f32_kernel");
+}
+
+zk_status launch_wgrad_reduce_sliced(const float* partial, int S, int slice_m, int N, int K, const uint8_t* mask,
+                                     float* gw, cudaStream_t st) {
+    wgrad_reduce_sliced_kernel<<<(unsigned)ceil_div((int64_t)N * K, 256), 256, 0, st>>>(partial, S, slice_m, N, K, mask, gw);
+    return check_launch("wgrad_reduce_sliced_kernel");
+}
+
+size_t colsum_planes_scratch_bytes(int N) { return (size_t)64 * N * 4; }
+zk_status launch_colsum_planes_add(const __nv_bfloat16* planes, int64_t M, int Np, int N, float* out, void* scratch,
+                                   cudaStream_t st) {
+    if (M == 0) return ZK_OK;
+    int64_t S = std::min<int64_t>(64, ceil_div(M, 256));
+    const int64_t rows = ceil_div(M, S);
+    S = ceil_div(M, rows);
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)S);
+    colsum_planes_stage1<<<grid, 256, 0, st>>>(planes, M, Np, N, rows, (float*)scratch);
+    ZK_TRY(check_launch("colsum_planes_stage1"));
+    colsum_planes_stage2<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)scratch, (int)S, N, out);
+    return check_launch("colsum_planes_stage2");
+}
+
+zk_status tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
+    ZK_REQUIRE(a.a_planes && a.mapW && a.M > 0 && a.N > 0 && a.Kp > 0 && a.Kp % BK == 0, "tc_gemm: bad arguments");
+    ZK_REQUIRE((a.out_f32 != nullptr) != (a.out_planes != nullptr), "tc_gemm: exactly one output kind");
+    ZK_REQUIRE(a.M < ((int64_t)1 << 31) - BM, "tc_gemm: too many rows for one launch");
+    CUtensorMap mapA;
+    ZK_TRY(make_plane_map(&mapA, a.a_planes, a.M, a.Kp, BM));
+    TcParams p;
+    p.M = (int)a.M; p.N = a.N; p.Kp = a.Kp;
+    p.n_chunks = (a.N + BN - 1) / BN;
+    p.n_terms = a.n_terms;
+    p.relu = a.relu;
+    p.bias = a.bias;
+    p.out_f32 = a.out_f32; p.ldo = a.ldo;
+    p.out_planes = a.out_planes; p.Np = a.Np;
+    p.gate = a.gate; p.slice_m = a.slice_m; p.w_slice_rows = a.w_slice_rows;
+    if (a.out_planes) ZK_REQUIRE(p.n_chunks * BN >= p.Np && a.Np % 64 == 0, "tc_gemm: internal padding error");
+    if (a.slice_m) ZK_REQUIRE(a.slice_m % BM == 0, "tc_gemm: slice_m must be a multiple of %d", BM);
+    const int64_t tiles = ceil_div(a.M, BM) * p.n_chunks;
+    const int grid = (int)std::min<int64_t>(tiles, sm_count());
+    linear_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(mapA, *a.mapW, p);
+    return check_launch("linear_tc_kernel");
+}
+
+// transposed weights as bf16 planes for dgrad: wt[i] is (K_i, N_i) fp32 row-major
+zk_status tc_pack_backward(zk_mlp* m, cudaStream_t st) {
+    TcPack* pk = (TcPack*)m->tc;
+    ZK_REQUIRE(pk, "tc_pack_backward: handle has no tensor-core pack");
+    if ((int)pk->bwd.size() == m->n_linear) return ZK_OK;
+    ZK_REQUIRE((int)m->wt.size() == m->n_linear, "tc_pack_backward: transposed weights missing");
+    for (auto& l : pk->bwd) cudaFree(l.w);
+    pk->bwd.clear();
+    for (int i = 0; i < m->n_linear; ++i) {
+        TcLayer L;
+        L.K = m->dims[i + 1];  // contraction over the layer's outputs
+        L.N = m->dims[i];
+        L.Kp = pad64(L.K);
+        if (cudaMalloc((void**)&L.w, (size_t)2 * L.N * L.Kp * 2) != cudaSuccess) return fail(ZK_ENOMEM, "tc_pack_backward: cudaMalloc failed");
+        pk->bwd.push_back(L);
+        split_weight_kernel<<<(unsigned)ceil_div((int64_t)L.N * L.Kp, 256), 256, 0, st>>>(m->wt[i], L.N, L.K, L.Kp, L.w);
+        ZK_TRY(check_launch("split_weight_kernel"));
+        ZK_TRY(make_plane_map(&pk->bwd.back().mapW, L.w, L.N, L.Kp, BN));
+    }
+    return ZK_OK;
+}
+
+const TcPack* tc_pack_of(const zk_mlp* m) { return (const TcPack*)m->tc; }
 
 }  // namespace zk

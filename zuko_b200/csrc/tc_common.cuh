@@ -143,6 +143,7 @@ struct FusedPack {
 };
 struct TcPack {
     std::vector<TcLayer> layers;
+    std::vector<TcLayer> bwd;  // transposed weights (dgrad): N = in features, K = out features; built on first backward
     int n_terms = 3;
     int max_np = 0;  // widest padded hidden activation
     FusedPack fused;
