@@ -3,6 +3,12 @@
 against gradients that torch.autograd produced on the UNMODIFIED reference in fp64
 (tests/golden/grad_*.npz) and against the gradient oracle (oracle/oracle_grad.py).
 
+Rows on which the flow is not differentiable to working precision (a hidden pre-activation within
+the GEMM's rounding error of the ReLU kink in the fp64 oracle, cases.relu_kink_rows — there a sign
+flip of the last bits changes the gradient by a finite jump; the tcgen05 split-bf16 conditioner and
+the fp32 one each flip a handful of such units, as does the reference's own fp32 path) get zero weight, and the golden sums are corrected by
+the pinned gradient oracle for exactly those rows (gradients are linear in the per-row weights).
+
 Bar: every gradient tensor within ``max(5e-5, 3 * e32)`` of the fp64 golden one, relative to its
 largest entry, where e32 is the reference's own fp32-vs-fp64 deviation on that tensor (stored in
 the golden files; 1e-6..1e-5 on the BASELINE configs).  The stress set (weights x3 => splines
@@ -24,6 +30,7 @@ from cases import (
     grad_inputs,
     load,
     oracle_named_grads,
+    relu_kink_rows,
 )
 from oracle import oracle as O
 from oracle import oracle_grad as OG
@@ -126,17 +133,43 @@ def _flow_grads(flow, x, c, mode, gg, device):
     return cpu(xt.grad), (None if ct is None else cpu(ct.grad)), named_param_grads(flow)
 
 
+def _without_kink_rows(name, gg, x, c, mode):
+    """Gives the rows at a ReLU kink (cases.relu_kink_rows) zero weight: returns the modified weights,
+    the golden gradients corrected by the gradient oracle for those rows, and the row mask."""
+    cpu_flow = build_flow(name)
+    spec = O.flowspec_from_module(cpu_flow)
+    kink = relu_kink_rows(spec, x, c)
+    w = {k: gg[k].copy() for k in ("g", "gz", "gl")}
+    ref = {"gx": gg[f"{mode}/gx"].copy(), "gc": None if c is None else gg[f"{mode}/gc"].copy(), "minus": None}
+    if kink.any():
+        for k in w:
+            w[k][kink] = 0.0
+        ck = c if (c is None or c.ndim == 1) else c[kink]
+        kw = dict(g_log_prob=gg["g"][kink]) if mode == "lp" else dict(g_z=gg["gz"][kink], g_ladj=gg["gl"][kink])
+        _, ogc, lgs = OG.flow_backward(spec, x[kink], ck, **kw)
+        ref["gx"][kink] = 0.0
+        if c is not None:
+            if c.ndim == 1:
+                ref["gc"] = ref["gc"] - ogc
+            else:
+                ref["gc"][kink] = 0.0
+        ref["minus"] = oracle_named_grads(cpu_flow, lgs)
+    return w, ref, kink
+
+
 @pytest.mark.parametrize("mode", ["lp", "tr"])
 @pytest.mark.parametrize("name", GRAD_CASES_FULL + GRAD_CASES_SAMPLED)
 def test_flow_gradients_vs_reference_autograd(device, name, mode):
     gg, x, c = grad_inputs(name)
     flow = build_flow(name).to(device)
     rtol = 1e-2 if name == "nsf6_stress" else 5e-5
-    gx, gc, pg = _flow_grads(flow, x, c, mode, gg, device)
-    close(gx, gg[f"{mode}/gx"], grad_bar(gg, f"{mode}/", "gx", rtol, 3.0), f"{name} d/dx")
+    w, ref, kink = _without_kink_rows(name, gg, x, c, mode)
+    assert kink.mean() <= 0.6, f"{name}: {kink.sum()} of {kink.size} rows at a ReLU kink"
+    gx, gc, pg = _flow_grads(flow, x, c, mode, w, device)
+    close(gx, ref["gx"], grad_bar(gg, f"{mode}/", "gx", rtol, 3.0), f"{name} d/dx")
     if c is not None:
-        close(gc, gg[f"{mode}/gc"], grad_bar(gg, f"{mode}/", "gc", rtol, 3.0), f"{name} d/dc")
-    assert_param_grads(pg, gg, f"{mode}/", rtol, name, ref32_factor=3.0)
+        close(gc, ref["gc"], grad_bar(gg, f"{mode}/", "gc", rtol, 3.0), f"{name} d/dc")
+    assert_param_grads(pg, gg, f"{mode}/", rtol, name, ref32_factor=3.0, minus=ref["minus"])
 
 
 @pytest.mark.parametrize("mode", ["lp", "tr"])
@@ -149,14 +182,15 @@ def test_stress_gradients_exact_order_arithmetic(device, mode):
     for t in flow.transform.transforms:
         t.hyper.gemm_mode = "fp32"
     flow = flow.to(device)
+    w, ref, _ = _without_kink_rows("nsf6_stress", gg, x, c, mode)
     prev = E.lib().zk_set_fast_math(0)
     try:
-        gx, gc, pg = _flow_grads(flow, x, c, mode, gg, device)
+        gx, gc, pg = _flow_grads(flow, x, c, mode, w, device)
     finally:
         E.lib().zk_set_fast_math(prev)
-    close(gx, gg[f"{mode}/gx"], grad_bar(gg, f"{mode}/", "gx", 5e-5, 4.0), "stress d/dx (fp32 mode)")
-    close(gc, gg[f"{mode}/gc"], grad_bar(gg, f"{mode}/", "gc", 5e-5, 4.0), "stress d/dc (fp32 mode)")
-    assert_param_grads(pg, gg, f"{mode}/", 5e-5, "stress (fp32 mode)", ref32_factor=4.0)
+    close(gx, ref["gx"], grad_bar(gg, f"{mode}/", "gx", 5e-5, 4.0), "stress d/dx (fp32 mode)")
+    close(gc, ref["gc"], grad_bar(gg, f"{mode}/", "gc", 5e-5, 4.0), "stress d/dc (fp32 mode)")
+    assert_param_grads(pg, gg, f"{mode}/", 5e-5, "stress (fp32 mode)", ref32_factor=4.0, minus=ref["minus"])
 
 
 def test_log_prob_value_unchanged_by_autograd(device):
@@ -179,6 +213,7 @@ def test_chunked_backward_and_determinism(device):
     gen = torch.Generator().manual_seed(5)
     B = 6000
     x, c, g = torch.randn(B, 16, generator=gen).numpy(), torch.randn(B, 8, generator=gen).numpy(), torch.randn(B, generator=gen).numpy()
+    g[:512][relu_kink_rows(spec, x[:512], c[:512])] = 0.0  # rows compared with the oracle below
     gg = {"g": g}
     full = _flow_grads(flow, x, c, "lp", gg, device)
     again = _flow_grads(flow, x, c, "lp", gg, device)
@@ -217,6 +252,8 @@ def test_tensor_core_and_fp32_backward_agree(device, name, B):
     C = flow.transform.transforms[0].context
     c = torch.randn(B, C, generator=gen).numpy() if C else None
     gg = {"g": torch.randn(B, generator=gen).numpy()}
+    spec = O.flowspec_from_module(build_flow(name))
+    gg["g"][relu_kink_rows(spec, x, c)] = 0.0  # the two arithmetics may sit on different sides of a kink
     tc = _flow_grads(flow, x, c, "lp", gg, device)
     prev = E.lib().zk_set_tc_backward(0)
     try:
@@ -230,7 +267,6 @@ def test_tensor_core_and_fp32_backward_agree(device, name, B):
     for k in f32[2]:
         close(tc[2][k], f32[2][k], 5e-5, f"{name} d/d{k} tc vs fp32")
     n = 64
-    spec = O.flowspec_from_module(build_flow(name))
     ogx, _, _ = OG.flow_backward(spec, x[:n], None if c is None else c[:n], g_log_prob=gg["g"][:n])
     close(tc[0][:n], ogx, 5e-5, f"{name} gx vs oracle")
 
@@ -265,9 +301,10 @@ def test_broadcast_context_and_oracle(device):
     gg, x, c = grad_inputs("nsf35_row")
     assert c.ndim == 1
     flow = build_flow("nsf35_row").to(device)
-    gx, gc, _ = _flow_grads(flow, x, c, "lp", gg, device)
+    w, ref, _ = _without_kink_rows("nsf35_row", gg, x, c, "lp")
+    gx, gc, _ = _flow_grads(flow, x, c, "lp", w, device)
     assert gc.shape == c.shape
-    close(gc, gg["lp/gc"], 5e-5, "d/dc (broadcast row)")
+    close(gc, ref["gc"], 5e-5, "d/dc (broadcast row)")
 
 
 def test_accelerated_reference_style_module_gets_grads(device):
@@ -278,6 +315,7 @@ def test_accelerated_reference_style_module_gets_grads(device):
     gg, x, c = grad_inputs("maf35_batch")
     src = build_flow("maf35_batch").to(device)
     acc = zuko.accelerate(src)
+    w, ref, _ = _without_kink_rows("maf35_batch", gg, x, c, "lp")
     xt, ct = dev_t(x, device), dev_t(c, device)
-    (dev_t(gg["g"], device) * acc(ct).log_prob(xt)).sum().backward()
-    assert_param_grads(named_param_grads(src), gg, "lp/", 5e-5, "accelerate(maf35)")
+    (dev_t(w["g"], device) * acc(ct).log_prob(xt)).sum().backward()
+    assert_param_grads(named_param_grads(src), gg, "lp/", 5e-5, "accelerate(maf35)", minus=ref["minus"])
