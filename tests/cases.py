@@ -220,38 +220,60 @@ def assert_param_grads(named: dict, gg: dict, prefix: str, rtol: float, what: st
     return checked
 
 
-def relu_kink_rows(spec, x, c, tau: float = 1e-5) -> np.ndarray:
-    """Rows of the batch on which the flow is NOT differentiable to working precision: some hidden
-    unit of some conditioner has a pre-activation ``|p| < tau * (sum_k |a_k w_k| + |b|)`` (fp64
-    oracle), i.e. within the rounding error of the split-bf16 GEMM of the ReLU kink (measured on
-    the BASELINE configs by emulating the 3-term bf16 product: median 7e-7, 99.99th percentile
-    1e-5 of that sum; every sign flip observed on the GPU sat below 5e-7).  There the gradient jumps
-    by a finite amount when the pre-activation changes sign, so two correct implementations whose
-    pre-activations differ in the last bits (the reference's own fp32 path included) may return
-    either one-sided gradient.  The gradient parity tests give those rows zero weight and correct
-    the golden sums with the (pinned) gradient oracle — gradients are linear in the per-row
-    weights."""
+def relu_kink_rows(spec, x, c, tau: float = 1e-5, tau_knot: float = 5e-5) -> np.ndarray:
+    """Rows of the batch on which the flow is NOT differentiable to working precision (fp64 oracle):
+
+    * ReLU kinks — some hidden unit of some conditioner has a pre-activation
+      ``|p| < tau * (sum_k |a_k w_k| + |b|)``, i.e. within the rounding error of the split-bf16 GEMM
+      of zero (measured on the BASELINE configs by emulating the 3-term bf16 product: median 7e-7,
+      99.99th percentile 1e-5 of that sum; every sign flip observed on the GPU sat below 5e-7);
+    * spline knots — some input of a rational-quadratic spline lies within ``tau_knot`` of one of its
+      knots: the spline is C1, so d(ladj)/dx and d(ladj)/d(phi) jump across a knot (the engine's
+      layer inputs carry ~1e-5 of forward error, the knots ~1e-6).
+
+    There the gradient jumps by a finite amount, so two correct implementations whose intermediates
+    differ in the last bits (the reference's own fp32 path included) may return either one-sided
+    gradient.  The gradient parity tests give those rows zero weight and correct the golden sums
+    with the (pinned) gradient oracle — gradients are linear in the per-row weights."""
     x = np.asarray(x, np.float64)
     B = x.shape[0]
     bad = np.zeros(B, dtype=bool)
     z = x
     for layer in spec.layers:
         cond = layer.hyper
+        phi = None
+        zt = z  # inputs of the univariate bijector
         if cond is not None:
             cc = None if c is None else (np.broadcast_to(c, (B, np.asarray(c).shape[-1])) if np.asarray(c).ndim == 1 else np.asarray(c, np.float64))
             if layer.kind == "autoregressive":
                 h = z if cc is None else np.concatenate([z, cc], -1)
             elif layer.kind == "coupling":
                 za = z[:, np.nonzero(layer.mask)[0]]
+                zt = z[:, np.nonzero(~layer.mask)[0]]
                 h = za if cc is None else np.concatenate([za, cc], -1)
             else:
                 h = cc
             n = len(cond.weights)
-            for i in range(n - 1):
+            for i in range(n):
                 W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
                 bias = 0.0 if cond.biases[i] is None else cond.biases[i]
                 pre = h @ W.T + bias
+                if i == n - 1:
+                    phi = pre
+                    break
                 bad |= (np.abs(pre) < tau * (np.abs(h) @ np.abs(W).T + np.abs(bias))).any(-1)
                 h = np.maximum(pre, 0.0)
+        elif layer.kind == "elementwise":
+            phi = np.broadcast_to(np.asarray(layer.phi, np.float64), (B, *np.asarray(layer.phi).shape))
+        if phi is not None and layer.univariate == "rqs":
+            P = 3 * layer.bins - 1
+            X, _, _ = O_rqs_knots(phi.reshape(B, zt.shape[1], P), layer.bins, layer.bound, layer.slope)
+            bad |= (np.abs(zt[..., None] - X).min(-1) < tau_knot).any(-1)
         z, _ = layer.forward(z, c, np.float64)
     return bad
+
+
+def O_rqs_knots(phi, bins, bound, slope):
+    from oracle import oracle as O
+
+    return O.rqs_knots(phi, bins, bound, slope)

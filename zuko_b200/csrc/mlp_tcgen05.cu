@@ -469,54 +469,70 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
 // ===========================================================================
 namespace {
 
-// bf16 planes [2][M][Kp]  ->  [2][S][Rp][Bs]: out[pl][s][r][j] = in[pl][s*Bs + j][r] (0 beyond M / Kp)
-__global__ void transpose_planes_kernel(const __nv_bfloat16* in, int64_t M, int Kp, int S, int Rp, int Bs,
-                                        __nv_bfloat16* out) {
-    __shared__ uint16_t tile[32][34];
+// bf16 planes [2][M][Kp]  ->  [2][S][Rp][Bs]: out[pl][s][r][j] = in[pl][s*Bs + j][r] (0 beyond M / Kp).
+// 64 x 64 tiles, 32-bit (bf16 pair) accesses on both sides: every warp reads and writes 128
+// contiguous bytes per row.  Bs is a multiple of 64, so a tile never straddles two batch slices.
+__global__ void __launch_bounds__(256)
+transpose_planes_kernel(const __nv_bfloat16* in, int64_t M, int Kp, int S, int Rp, int Bs, __nv_bfloat16* out) {
+    __shared__ uint16_t tile[64][66];
     const int pl = blockIdx.z;
-    const int64_t b0 = (int64_t)blockIdx.x * 32;  // position along S*Bs
-    const int r0 = blockIdx.y * 32;
+    const int64_t b0 = (int64_t)blockIdx.x * 64;  // position along S*Bs (slices are contiguous in b)
+    const int r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const uint16_t* src = reinterpret_cast<const uint16_t*>(in) + (int64_t)pl * M * Kp;
     uint16_t* dst = reinterpret_cast<uint16_t*>(out) + (int64_t)pl * S * Rp * Bs;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        const int64_t b = b0 + j;  // batch index (slices are contiguous in b)
-        const int r = r0 + threadIdx.x;
-        tile[j][threadIdx.x] = (b < M && r < Kp) ? src[b * Kp + r] : (uint16_t)0;
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
+        const int64_t b = b0 + j;
+        const int r = r0 + 2 * tx;  // Kp is even (multiple of 64): a pair is in range together
+        uint32_t w = 0u;
+        if (b < M && r < Kp) w = *reinterpret_cast<const uint32_t*>(src + b * Kp + r);
+        tile[j][2 * tx] = (uint16_t)(w & 0xffffu);
+        tile[j][2 * tx + 1] = (uint16_t)(w >> 16);
     }
     __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += 8) {
+    const int64_t s = b0 / Bs, jj0 = b0 - s * Bs;
+    if (s >= S) return;
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
         const int r = r0 + j;
-        const int64_t b = b0 + threadIdx.x;
-        if (r < Rp && b < (int64_t)S * Bs) {
-            const int64_t s = b / Bs, jj = b - s * Bs;
-            dst[(s * Rp + r) * Bs + jj] = tile[threadIdx.x][j];
+        if (r < Rp) {
+            const uint32_t w = (uint32_t)tile[2 * tx][j] | ((uint32_t)tile[2 * tx + 1][j] << 16);
+            *reinterpret_cast<uint32_t*>(dst + (s * Rp + r) * Bs + jj0 + 2 * tx) = w;
         }
     }
 }
 
-// fp32 (M, N) row-major (stride ld)  ->  bf16 hi/lo planes [2][S][Rp][Bs], transposed
-__global__ void transpose_split_f32_kernel(const float* in, int64_t ld, int64_t M, int N, int S, int Rp, int Bs,
-                                           __nv_bfloat16* out) {
-    __shared__ float tile[32][33];
-    const int64_t b0 = (int64_t)blockIdx.x * 32;
-    const int r0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) {
+// fp32 (M, N) row-major (stride ld)  ->  bf16 hi/lo planes [2][S][Rp][Bs], transposed (same tiling)
+__global__ void __launch_bounds__(256)
+transpose_split_f32_kernel(const float* in, int64_t ld, int64_t M, int N, int S, int Rp, int Bs, __nv_bfloat16* out) {
+    __shared__ float tile[64][65];
+    const int64_t b0 = (int64_t)blockIdx.x * 64;
+    const int r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
         const int64_t b = b0 + j;
-        const int r = r0 + threadIdx.x;
-        tile[j][threadIdx.x] = (b < M && r < N) ? in[b * ld + r] : 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + tx + 32 * h;
+            tile[j][tx + 32 * h] = (b < M && r < N) ? in[b * ld + r] : 0.f;
+        }
     }
     __syncthreads();
+    const int64_t s = b0 / Bs, jj0 = b0 - s * Bs;
+    if (s >= S) return;
     const int64_t plane = (int64_t)S * Rp * Bs;
-    for (int j = threadIdx.y; j < 32; j += 8) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
         const int r = r0 + j;
-        const int64_t b = b0 + threadIdx.x;
-        if (r < Rp && b < (int64_t)S * Bs) {
-            const int64_t s = b / Bs, jj = b - s * Bs;
-            const float v = tile[threadIdx.x][j];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const int64_t o = (s * Rp + r) * Bs + jj;
-            out[o] = h;
-            out[plane + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (r < Rp) {
+            uint32_t hi, lo;
+            split2_bf16(tile[2 * tx][j], tile[2 * tx + 1][j], hi, lo);
+            const int64_t o = (s * Rp + r) * Bs + jj0 + 2 * tx;
+            *reinterpret_cast<uint32_t*>(dst + o) = hi;
+            *reinterpret_cast<uint32_t*>(dst + plane + o) = lo;
         }
     }
 }
@@ -533,27 +549,36 @@ __global__ void wgrad_reduce_sliced_kernel(const float* partial, int S, int slic
     gw[i] += t;
 }
 
-// column sums of (hi + lo) planes [2][M][Np] over a row slice (stage 1 of the fixed-order reduction)
-__global__ void colsum_planes_stage1(const __nv_bfloat16* planes, int64_t M, int Np, int N, int64_t rows_per_slice,
-                                     float* partial) {
-    __shared__ float sm[8][33];
+// column sums of (hi + lo) planes [2][M][Np] over a row slice (stage 1 of the fixed-order reduction);
+// a thread owns two adjacent columns (one 32-bit load per plane), a warp reads 128 contiguous bytes
+__global__ void __launch_bounds__(256)
+colsum_planes_stage1(const __nv_bfloat16* planes, int64_t M, int Np, int N, int64_t rows_per_slice, float* partial) {
+    __shared__ float sm[8][66];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + tx;
+    const int col = blockIdx.x * 64 + 2 * tx;  // Np is even: col + 1 < Np whenever col < Np
     const int64_t lo_r = (int64_t)blockIdx.y * rows_per_slice;
     const int64_t hi_r = min(M, lo_r + rows_per_slice);
-    const __nv_bfloat16* hi = planes;
-    const __nv_bfloat16* lo = planes + M * (int64_t)Np;
-    float acc = 0.f;
-    if (col < N)
-        for (int64_t r = lo_r + ty; r < hi_r; r += 8)
-            acc += __bfloat162float(hi[r * Np + col]) + __bfloat162float(lo[r * Np + col]);
-    sm[ty][tx] = acc;
+    const uint16_t* hi = reinterpret_cast<const uint16_t*>(planes);
+    const uint16_t* lo = hi + M * (int64_t)Np;
+    float a0 = 0.f, a1 = 0.f;
+    if (col < Np)
+        for (int64_t r = lo_r + ty; r < hi_r; r += 8) {
+            const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + r * Np + col);
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(lo + r * Np + col);
+            a0 += __uint_as_float(h << 16) + __uint_as_float(l << 16);
+            a1 += __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
+        }
+    sm[ty][2 * tx] = a0;
+    sm[ty][2 * tx + 1] = a1;
     __syncthreads();
-    if (ty == 0 && col < N) {
-        float t = 0.f;
+    if (ty < 2) {
+        const int c = blockIdx.x * 64 + 2 * tx + ty;
+        if (c < N) {
+            float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][tx];
-        partial[(int64_t)blockIdx.y * N + col] = t;
+            for (int k = 0; k < 8; ++k) t += sm[k][2 * tx + ty];
+            partial[(int64_t)blockIdx.y * N + c] = t;
+        }
     }
 }
 __global__ void colsum_planes_stage2(const float* partial, int S, int N, float* out) {
@@ -576,15 +601,15 @@ zk_status launch_split_planes(const float* x, int64_t ldx, int dx, const float* 
 
 zk_status launch_transpose_planes(const __nv_bfloat16* in, int64_t M, int Kp, int S, int Rp, int Bs,
                                   __nv_bfloat16* out, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 32), (unsigned)ceil_div(Rp, 32), 2);
-    transpose_planes_kernel<<<grid, dim3(32, 8), 0, st>>>(in, M, Kp, S, Rp, Bs, out);
+    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 64), (unsigned)ceil_div(Rp, 64), 2);
+    transpose_planes_kernel<<<grid, 256, 0, st>>>(in, M, Kp, S, Rp, Bs, out);
     return check_launch("transpose_planes_kernel");
 }
 
 zk_status launch_transpose_split_f32(const float* in, int64_t ld, int64_t M, int N, int S, int Rp, int Bs,
                                      __nv_bfloat16* out, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 32), (unsigned)ceil_div(Rp, 32), 1);
-    transpose_split_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld, M, N, S, Rp, Bs, out);
+    dim3 grid((unsigned)ceil_div((int64_t)S * Bs, 64), (unsigned)ceil_div(Rp, 64), 1);
+    transpose_split_f32_kernel<<<grid, 256, 0, st>>>(in, ld, M, N, S, Rp, Bs, out);
     return check_launch("transpose_split_f32_kernel");
 }
 
@@ -594,14 +619,14 @@ zk_status launch_wgrad_reduce_sliced(const float* partial, int S, int slice_m, i
     return check_launch("wgrad_reduce_sliced_kernel");
 }
 
-size_t colsum_planes_scratch_bytes(int N) { return (size_t)64 * N * 4; }
+size_t colsum_planes_scratch_bytes(int N) { return (size_t)256 * N * 4; }
 zk_status launch_colsum_planes_add(const __nv_bfloat16* planes, int64_t M, int Np, int N, float* out, void* scratch,
                                    cudaStream_t st) {
     if (M == 0) return ZK_OK;
-    int64_t S = std::min<int64_t>(64, ceil_div(M, 256));
+    int64_t S = std::min<int64_t>(256, ceil_div(M, 256));
     const int64_t rows = ceil_div(M, S);
     S = ceil_div(M, rows);
-    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)S);
+    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)S);
     colsum_planes_stage1<<<grid, 256, 0, st>>>(planes, M, Np, N, rows, (float*)scratch);
     ZK_TRY(check_launch("colsum_planes_stage1"));
     colsum_planes_stage2<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)scratch, (int)S, N, out);
