@@ -348,6 +348,11 @@ def run_ours(args) -> None:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_value = world * B / e2e_s.item()
 
+        # ---- training step (forward + backward through the autograd seam), rank 0, 2^18 rows
+        training = None
+        if rank == 0 and not args.no_training_step:
+            training = time_training_step(flow, xs[0], cs[0], rows=min(B, 1 << 18), iters=3)
+
         # ---- per-kernel timing in isolation (CUDA events), rank 0
         kernels, roofline = [], None
         if rank == 0:
@@ -376,11 +381,37 @@ def run_ours(args) -> None:
             "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4, "d2h_bytes_per_step": B * 4,
                                              "steps": e2e_steps, "api": "FlowCall.log_prob_host -> zk_flow_log_prob_host (pinned host buffers)"},
             "gpu_launches": int(launches), "mean_nll": nll_value, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "parity": parity,
+            "cpu_baseline": cpu, "parity": parity, "training_step": training,
         }  # fmt: skip
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_training_step(flow, x, c, rows: int, iters: int) -> dict:
+    """`loss = -flow(c).log_prob(x).mean(); loss.backward()` (README.md:43-49 of the reference) on
+    `rows` rows: ONE zk_flow_log_prob + ONE zk_flow_backward call per step, CUDA events."""
+    from zuko_b200 import _engine as E
+
+    x, c = x[:rows], c[:rows]
+
+    def one():
+        for p in flow.parameters():
+            p.grad = None
+        (-flow(c).log_prob(x).mean()).backward()
+
+    with torch.enable_grad():
+        for _ in range(2):
+            one()
+        n0 = E.lib().zk_launch_count()
+        ms = cuda_time_ms(one, iters)
+        launches = (E.lib().zk_launch_count() - n0) / iters
+    dims = [D + C, *H, D * P]
+    flops = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * rows * T
+    return {"workload": WORKLOAD.replace("log_prob", "training step (log_prob forward + backward)"), "rows": rows,
+            "ms_per_step": ms, "samples_per_s": rows / (ms * 1e-3), "gpu_launches_per_step": launches,
+            "algorithmic_tflops": 4 * flops / (ms * 1e-3) / 1e12,
+            "note": "forward + recompute + dgrad + wgrad = 4 x the dense conditioner FLOPs; backward GEMMs on linear_tc_kernel (tcgen05 split-bf16)"}  # fmt: skip
 
 
 def gemm_mode_name(flow) -> str:
@@ -472,6 +503,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = size it to ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training-step", action="store_true", help="skip the forward+backward timing (extra object)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
