@@ -33,19 +33,38 @@ ZK_HD float dsc(float v, float a) {
     return 1.0f / (d * d);
 }
 
+// soft clip u = v / (1 + |v| a) and its derivative d = 1 / (1 + |v| a)^2 from ONE reciprocal
+ZK_HD void sc_parts(float v, float a, float& u, float& d) {
+    const float r = 1.0f / fmaf(fabsf(v), a, 1.0f);
+    u = v * r;
+    d = r * r;
+}
+
 // One (sample, dim) pair of MonotonicRQSTransform.call_and_ladj, reverse mode.
 //   p   : the pair's P = 3K-1 raw parameters (widths, heights, derivatives)
 //   gy  : dL/dy, gl : dL/dladj (of this pair's log-derivative)
 //   gx  : dL/dx (direct dependence only), gp : dL/dp (P values; may alias p)
+// With a compile-time K (KT > 0) the softmax numerators and soft-clip derivatives of the 2K width /
+// height parameters are computed once and kept in registers (1 reciprocal + 1 exp per parameter);
+// the run-time-K variant recomputes them per sweep with the same arithmetic (bit-identical results).
 template <int KT>
 ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float gl, float bound,
                              float aw, float ad, float& gx, float* gp) {
     const int K = KT > 0 ? KT : Krt;
     const int P = 3 * K - 1;
+    constexpr int KA = KT > 0 ? KT : 1;
+    float ew[KA], eh[KA], dw[KA], dh[KA];
     float sw = 0.f, sh = 0.f;
     for (int k = 0; k < K; ++k) {
-        sw += expf(sc(p[k], aw));
-        sh += expf(sc(p[K + k], aw));
+        float u0, d0_, u1, d1_;
+        sc_parts(p[k], aw, u0, d0_);
+        sc_parts(p[K + k], aw, u1, d1_);
+        const float e0 = expf(u0), e1 = expf(u1);
+        if constexpr (KT > 0) {
+            ew[k] = e0; eh[k] = e1; dw[k] = d0_; dh[k] = d1_;
+        }
+        sw += e0;
+        sh += e1;
     }
     const float gxs = 2.f * bound / sw;  // numerator -> width
     const float gys = 2.f * bound / sh;
@@ -54,8 +73,17 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     int kb = 0;
     float x0 = -bound, y0 = -bound, ewk = 0.f, ehk = 0.f, cwk = 0.f, chk = 0.f;
     for (int j = 0; j < K; ++j) {
-        const float e0 = expf(sc(p[j], aw));
-        const float e1 = expf(sc(p[K + j], aw));
+        float e0, e1;
+        if constexpr (KT > 0) {
+            e0 = ew[j];
+            e1 = eh[j];
+        } else {
+            float u, d;
+            sc_parts(p[j], aw, u, d);
+            e0 = expf(u);
+            sc_parts(p[K + j], aw, u, d);
+            e1 = expf(u);
+        }
         const bool take = (j == 0) || (xl < x);
         if (take) {
             kb = j; x0 = xl; y0 = yl; ewk = e0; ehk = e1; cwk = cw; chk = ch;
@@ -72,10 +100,11 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
         return;
     }
     const float dx = ewk * gxs, dy = ehk * gys;
-    const float r0 = (kb > 0) ? p[2 * K + kb - 1] : 0.f;
-    const float r1 = (kb < K - 1) ? p[2 * K + kb] : 0.f;
-    const float d0 = (kb > 0) ? expf(sc(r0, ad)) : 1.f;  // pad (1, 1) with 0 -> exp(0) = 1
-    const float d1 = (kb < K - 1) ? expf(sc(r1, ad)) : 1.f;
+    float ur0 = 0.f, dr0 = 0.f, ur1 = 0.f, dr1 = 0.f;  // soft-clipped derivatives of the bin's two knots
+    if (kb > 0) sc_parts(p[2 * K + kb - 1], ad, ur0, dr0);
+    if (kb < K - 1) sc_parts(p[2 * K + kb], ad, ur1, dr1);
+    const float d0 = (kb > 0) ? expf(ur0) : 1.f;  // pad (1, 1) with 0 -> exp(0) = 1
+    const float d1 = (kb < K - 1) ? expf(ur1) : 1.f;
     const float rdx = 1.f / dx;
     const float s = dy * rdx;
     const float z = (x - x0) * rdx;
@@ -109,20 +138,24 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     // sum_j W_j dL/dW_j, divided by 2B
     const float dotw = (Gx0 * (cwk * gxs) + Gdx * dx) / (2.f * bound);
     const float doth = (Gy0 * (chk * gys) + Gdy * dy) / (2.f * bound);
+    const float gd0 = Gd0 * d0 * dr0, gd1 = Gd1 * d1 * dr1;  // gradients of the two raw derivative parameters
     for (int i = 0; i < K; ++i) {
-        const float rw = p[i], rh = p[K + i];
+        float e0, e1, c0, c1;
+        if constexpr (KT > 0) {
+            e0 = ew[i]; e1 = eh[i]; c0 = dw[i]; c1 = dh[i];
+        } else {
+            float u;
+            sc_parts(p[i], aw, u, c0);
+            e0 = expf(u);
+            sc_parts(p[K + i], aw, u, c1);
+            e1 = expf(u);
+        }
         const float selw = (i < kb ? Gx0 : 0.f) + (i == kb ? Gdx : 0.f);
         const float selh = (i < kb ? Gy0 : 0.f) + (i == kb ? Gdy : 0.f);
-        gp[i] = expf(sc(rw, aw)) * gxs * (selw - dotw) * dsc(rw, aw);
-        gp[K + i] = expf(sc(rh, aw)) * gys * (selh - doth) * dsc(rh, aw);
+        gp[i] = e0 * gxs * (selw - dotw) * c0;
+        gp[K + i] = e1 * gys * (selh - doth) * c1;
     }
-    for (int j = 0; j < K - 1; ++j) {
-        const float rr = p[2 * K + j];
-        float v = 0.f;
-        if (j == kb - 1) v += Gd0 * d0;
-        if (j == kb) v += Gd1 * d1;
-        gp[2 * K + j] = v * dsc(rr, ad);
-    }
+    for (int j = 0; j < K - 1; ++j) gp[2 * K + j] = (j == kb - 1 ? gd0 : 0.f) + (j == kb ? gd1 : 0.f);
 }
 
 // MonotonicAffineTransform (transforms.py:435-446): p = (shift, unconstrained log-scale)
