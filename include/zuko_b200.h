@@ -47,6 +47,11 @@ typedef void* zk_stream; /* cudaStream_t */
 /* univariate bijector applied per (sample, dim) */
 #define ZK_UNI_AFFINE 1 /* MonotonicAffineTransform, zuko/transforms.py:412-446; phi = (shift, scale) */
 #define ZK_UNI_RQS 2    /* MonotonicRQSTransform,    zuko/transforms.py:449-567; phi = (w[K], h[K], d[K-1]) */
+#define ZK_UNI_CRQS 3   /* CircularRQSTransform = CircularShiftTransform(bound) then RQS(bound), zuko/flows/spline.py:65-72
+                           (layers only: NCSF; `bound` of the layer is pi) */
+/* base distribution of a flow */
+#define ZK_BASE_DIAG_NORMAL 0 /* DiagNormal(loc, scale)    zuko/distributions.py:337-363 */
+#define ZK_BASE_BOX_UNIFORM 1 /* BoxUniform(lower, upper)  zuko/distributions.py:366-396; base_loc = lower, base_scale = upper */
 
 /* layer kinds (elements of a ComposedTransform, zuko/transforms.py:59-160) */
 #define ZK_LAYER_AUTOREGRESSIVE 1 /* flows/autoregressive.py:24-218 + transforms.py:966-1007 */
@@ -106,6 +111,14 @@ zk_status zk_permute(const float* x, int64_t ldx, const int64_t* order, int64_t 
  * row-major, = matrix_exp(A - A^T) built by the caller — transforms.py:1235-1241. */
 zk_status zk_rotate(const float* x, int64_t ldx, const float* R, int transpose, int64_t B, int D,
                     float* y, int64_t ldy, zk_stream stream);
+/* CircularShiftTransform(bound): y = remainder(x, 2 bound) - bound (torch.remainder semantics), its own
+ * inverse, ladj 0 — transforms.py:319-351. */
+zk_status zk_circular_shift(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y,
+                            int64_t ldy, zk_stream stream);
+/* BoxUniform(lower, upper).log_prob(z) + ladj — distributions.py:366-396, torch/distributions/uniform.py:
+ * -sum_d log(upper_d - lower_d) when lower <= z < upper in every dim, -inf otherwise; ladj may be NULL. */
+zk_status zk_box_uniform_log_prob(const float* z, int64_t ldz, const float* lower, const float* upper,
+                                  const float* ladj, int64_t B, int D, float* out, zk_stream stream);
 /* DiagNormal(loc, scale).log_prob(z) + ladj — distributions.py:115-119,337-363;
  * loc/scale DEVICE (D) or both NULL for the standard normal; ladj may be NULL. */
 zk_status zk_diag_normal_log_prob(const float* z, int64_t ldz, const float* loc, const float* scale,
@@ -184,8 +197,9 @@ typedef struct {
     const zk_layer* const* layers; /* host array of handles, applied first to last in the forward direction */
     int features;
     int context;
-    const float* base_loc;   /* DEVICE (D) or NULL (0) */
-    const float* base_scale; /* DEVICE (D) or NULL (1) */
+    const float* base_loc;   /* DEVICE (D) or NULL (0)   — BoxUniform: lower bounds (required) */
+    const float* base_scale; /* DEVICE (D) or NULL (1)   — BoxUniform: upper bounds (required) */
+    int base_kind;           /* ZK_BASE_* */
 } zk_flow_desc;
 
 /* bytes of workspace that let a batch of B rows run in a single chunk; any

@@ -236,6 +236,26 @@ def rotate(x, R, transpose: bool = False, dtype=np.float64):
     return y
 
 
+def circular_shift(x, bound=1.0, dtype=np.float64):
+    """CircularShiftTransform — transforms.py:344-348: remainder(x, 2B) - B (numpy's remainder has
+    torch.remainder's sign convention)."""
+    x = _c(x, dtype)
+    two_b = np.asarray(2 * bound, dtype=dtype)
+    return (np.remainder(x, two_b) - np.asarray(bound, dtype=dtype)).astype(dtype)
+
+
+def box_uniform_log_prob(z, lower, upper, ladj=None, dtype=np.float64):
+    """BoxUniform(lower, upper).log_prob(z) + ladj — distributions.py:366-396,
+    torch/distributions/uniform.py: log(lower <= z) + log(z < upper) - log(upper - lower)."""
+    z = _c(z, dtype)
+    lo, hi = _c(lower, dtype), _c(upper, dtype)
+    inside = ((lo <= z) & (z < hi)).all(-1)
+    out = np.full(z.shape[0], -np.inf, dtype=dtype)
+    const = -np.log(hi - lo).sum()
+    out[inside] = const + (0.0 if ladj is None else np.asarray(ladj, dtype)[inside])
+    return out
+
+
 def permute(x, order, inverse: bool = False):
     """PermutationTransform — transforms.py:1207-1211 (bit-exact gather)."""
     order = np.asarray(order, dtype=np.int64)
@@ -295,7 +315,7 @@ class Layer:
     kind: str
     features: int = 0
     context: int = 0
-    univariate: str = "affine"  # 'affine' | 'rqs'
+    univariate: str = "affine"  # 'affine' | 'rqs' | 'crqs' (circular shift by `bound`, then RQS over [-bound, bound])
     bins: int = 0
     bound: float = 5.0
     slope: float = 1e-3
@@ -311,11 +331,17 @@ class Layer:
     def _uni_fwd(self, x, phi, dtype):
         if self.univariate == "rqs":
             return rqs_forward(x, phi, self.bins, self.bound, self.slope, dtype)
+        if self.univariate == "crqs":
+            # CircularRQSTransform — flows/spline.py:65-72: CircularShiftTransform(bound) (transforms.py:
+            # 344-345, ladj 0) followed by MonotonicRQSTransform(bound=bound)
+            return rqs_forward(circular_shift(x, self.bound, dtype), phi, self.bins, self.bound, self.slope, dtype)
         return affine_forward(x, phi, self.slope, dtype)
 
     def _uni_inv(self, y, phi, dtype):
         if self.univariate == "rqs":
             return rqs_inverse(y, phi, self.bins, self.bound, self.slope, dtype)
+        if self.univariate == "crqs":  # ComposedTransform.inv: RQS^-1 then the shift (its own inverse)
+            return circular_shift(rqs_inverse(y, phi, self.bins, self.bound, self.slope, dtype), self.bound, dtype)
         return affine_inverse(y, phi, self.slope, dtype)
 
     # -- forward: returns (y, ladj summed over the event dim) -----------------
@@ -395,8 +421,14 @@ class FlowSpec:
     """Flow(transforms, DiagNormal(loc, scale)) — lazy.py:131-172."""
 
     layers: list
-    loc: np.ndarray
-    scale: np.ndarray
+    loc: np.ndarray  # DiagNormal loc, or BoxUniform lower when base == "uniform"
+    scale: np.ndarray  # DiagNormal scale, or BoxUniform upper
+    base: str = "normal"  # 'normal' | 'uniform'
+
+    def _base_log_prob(self, z, ladj, dtype):
+        if self.base == "uniform":
+            return box_uniform_log_prob(z, self.loc, self.scale, ladj, dtype)
+        return diag_normal_log_prob(z, self.loc, self.scale, ladj, dtype)
 
     def forward(self, x, c=None, dtype=np.float64):
         """ComposedTransform.call_and_ladj — transforms.py:141-150."""
@@ -417,7 +449,7 @@ class FlowSpec:
     def log_prob(self, x, c=None, dtype=np.float64):
         """NormalizingFlow.log_prob — distributions.py:115-119."""
         z, ladj = self.forward(x, c, dtype)
-        return diag_normal_log_prob(z, self.loc, self.scale, ladj, dtype)
+        return self._base_log_prob(z, ladj, dtype)
 
     def inverse_and_log_prob(self, z, c=None, dtype=np.float64):
         """NormalizingFlow.rsample_and_log_prob for a GIVEN z — distributions.py:129-138:
@@ -426,7 +458,7 @@ class FlowSpec:
         z = _c(z, dtype)
         x = self.inverse(z, c, dtype)
         _, ladj = self.forward(x, c, dtype)
-        return x, diag_normal_log_prob(z, self.loc, self.scale, ladj, dtype)
+        return x, self._base_log_prob(z, ladj, dtype)
 
 
 # --------------------------------------------------------------------------- #
@@ -461,6 +493,9 @@ def _univariate_info(t):
     uni = t.univariate
     kw = getattr(uni, "keywords", {}) or {}
     slope = float(kw.get("slope", 1e-3))
+    fname = getattr(getattr(uni, "func", uni), "__name__", "")
+    if len(shapes) == 3 and fname == "CircularRQSTransform":
+        return "crqs", int(shapes[0][0]), slope
     if len(shapes) == 3:
         return "rqs", int(shapes[0][0]), slope
     if shapes == [(), ()]:
@@ -475,7 +510,8 @@ def layer_from_module(t) -> Layer:
         in_f = t.hyper[0].weight.shape[1]
         D = t.hyper[-1].weight.shape[0] // t.total
         return Layer("autoregressive", features=D, context=in_f - D, univariate=uni, bins=bins,
-                     slope=slope, passes=int(t.passes), hyper=conditioner_from_module(t.hyper))  # fmt: skip
+                     slope=slope, passes=int(t.passes), hyper=conditioner_from_module(t.hyper),
+                     bound=float(np.pi) if uni == "crqs" else 5.0)  # fmt: skip
     if name == "GeneralCouplingTransform":
         uni, bins, slope = _univariate_info(t)
         mask = _np(t.mask).astype(bool)
@@ -519,6 +555,10 @@ def flowspec_from_module(flow) -> FlowSpec:
     layers = [layer_from_module(t) for t in (tr.transforms if hasattr(tr, "transforms") else [tr])]
     base = flow.base
     kw, args = base.kwargs, list(base.args)
+    if getattr(base.f, "__name__", "") == "BoxUniform":  # flows/spline.py:111-116
+        lower = _np(kw["lower"] if "lower" in kw else args[0]).astype(np.float64)
+        upper = _np(kw["upper"] if "upper" in kw else args[-1]).astype(np.float64)
+        return FlowSpec(layers, lower, upper, base="uniform")
     loc = _np(kw["loc"] if "loc" in kw else args[0]).astype(np.float64)
     scale = _np(kw["scale"] if "scale" in kw else args[-1]).astype(np.float64)
     return FlowSpec(layers, loc, scale)

@@ -253,6 +253,8 @@ def _uni_backward(layer: O.Layer, x, phi, gy, gl_row):
     gl = np.broadcast_to(np.asarray(gl_row, F)[:, None], x.shape)  # ladj.sum(-1): transforms.py:210-214
     if layer.univariate == "rqs":
         return rqs_backward(x, phi, gy, gl, layer.bins, layer.bound, layer.slope)
+    if layer.univariate == "crqs":  # the circular shift is a translation almost everywhere: d/dx = 1
+        return rqs_backward(O.circular_shift(x, layer.bound), phi, gy, gl, layer.bins, layer.bound, layer.slope)
     return affine_backward(x, phi, gy, gl, layer.slope)
 
 
@@ -264,7 +266,7 @@ def layer_backward(layer: O.Layer, x, c, gy, gl):
     gl = np.asarray(gl, F)
     B, D = x.shape
     cc = _ctx_rows(c, B)
-    P = 3 * layer.bins - 1 if layer.univariate == "rqs" else 2
+    P = 3 * layer.bins - 1 if layer.univariate in ("rqs", "crqs") else 2
     if layer.kind == "autoregressive":
         inp = x if cc is None else np.concatenate([x, cc], -1)  # flows/autoregressive.py:209
         phi = _cond_forward(layer.hyper, inp).reshape(B, D, P)
@@ -316,8 +318,10 @@ def flow_backward(spec: O.FlowSpec, x, c=None, g_log_prob=None, g_z=None, g_ladj
     gl = np.zeros(B, F) if g_ladj is None else np.asarray(g_ladj, F).copy()
     if g_log_prob is not None:
         glp = np.asarray(g_log_prob, F)
-        # base.log_prob(z) + ladj (distributions.py:115-119; torch normal.py:87-102)
-        g = g + glp[:, None] * (-(zs[-1] - spec.loc) / spec.scale**2)
+        # base.log_prob(z) + ladj (distributions.py:115-119; torch normal.py:87-102); a BoxUniform base
+        # has a constant density on its support: no d/dz term
+        if spec.base != "uniform":
+            g = g + glp[:, None] * (-(zs[-1] - spec.loc) / spec.scale**2)
         gl = gl + glp
     gc = None
     grads = [None] * len(spec.layers)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 import zuko_b200 as zuko
-from zuko_b200.flows import MAF, NICE, NSF, ElementWiseTransform, GeneralCouplingTransform, MaskedAutoregressiveTransform
+from zuko_b200.flows import MAF, NCSF, NICE, NSF, ElementWiseTransform, GeneralCouplingTransform, MaskedAutoregressiveTransform
 from zuko_b200.lazy import Flow, UnconditionalDistribution, UnconditionalTransform
 from zuko_b200.transforms import MonotonicRQSTransform, PermutationTransform, RotationTransform, SoftclipTransform
 
@@ -31,6 +31,7 @@ FLOW_CASES = {
     "maf5_randperm": (7, lambda: MAF(5, 2, randperm=True, hidden_features=[24])),
     "nsf1_elementwise": (0, lambda: NSF(1, 3, hidden_features=[16])),
     "nsf6_stress": (0, lambda: NSF(6, 3, transforms=3, hidden_features=[64, 64])),
+    "ncsf34": (0, lambda: NCSF(3, 4, hidden_features=[32, 32])),
 }
 SMALL_CASES = [k for k in FLOW_CASES if not k.startswith(("cfg2", "cfg3", "cfg4", "cfg5"))]
 BIG_CASES = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
@@ -136,7 +137,7 @@ def assert_log_prob_parity(ours, g: dict, rtol: float = 1e-5):
 # --------------------------------------------------------------------------- #
 
 GRAD_CASES_FULL = ["cfg1_maf", "nsf35_row", "maf35_batch", "nice35", "nsf5_passes2", "maf5_randperm",
-                   "nsf1_elementwise", "nsf6_stress", "composed", "composed_uncond"]  # fmt: skip
+                   "nsf1_elementwise", "nsf6_stress", "composed", "composed_uncond", "ncsf34"]  # fmt: skip
 GRAD_CASES_SAMPLED = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
 GRAD_SAMPLE = 2048
 
@@ -265,9 +266,15 @@ def relu_kink_rows(spec, x, c, tau: float = 1e-5, tau_knot: float = 5e-5) -> np.
                 h = np.maximum(pre, 0.0)
         elif layer.kind == "elementwise":
             phi = np.broadcast_to(np.asarray(layer.phi, np.float64), (B, *np.asarray(layer.phi).shape))
-        if phi is not None and layer.univariate == "rqs":
+        if phi is not None and layer.univariate in ("rqs", "crqs"):
             P = 3 * layer.bins - 1
             X, _, _ = O_rqs_knots(phi.reshape(B, zt.shape[1], P), layer.bins, layer.bound, layer.slope)
+            if layer.univariate == "crqs":  # the spline sees the circularly shifted input; the shift itself
+                from oracle import oracle as _O  # jumps where remainder wraps (x = 2 k bound)
+
+                bad |= (np.abs(np.remainder(zt, 2 * layer.bound)) < tau_knot).any(-1)
+                bad |= (np.abs(np.remainder(zt, 2 * layer.bound) - 2 * layer.bound) < tau_knot).any(-1)
+                zt = _O.circular_shift(zt, layer.bound)
             bad |= (np.abs(zt[..., None] - X).min(-1) < tau_knot).any(-1)
         z, _ = layer.forward(z, c, np.float64)
     return bad

@@ -77,7 +77,7 @@ def flow_case(name, build, B, ctx, *, seed=0, store=False, x_scale=1.0, w_scale=
             for n, p in flow.named_parameters():
                 p.mul_(w_scale)
         info["w_scale"] = np.float64(w_scale)
-    D = flow.base.loc.shape[0]
+    D = (flow.base.loc if hasattr(flow.base, "loc") else flow.base.lower).shape[0]  # NCSF: BoxUniform base
     x = gen(1234, B, D, scale=x_scale)
     c = None
     t0 = flow.transform.transforms[0]

@@ -349,6 +349,28 @@ def test_host_buffer_entry_point(device):
     assert abs(total - ref.double().sum().item()) < 1e-6 * abs(total)
 
 
+def test_circular_shift_and_box_uniform(device):
+    """CircularShiftTransform (transforms.py:319-351) and BoxUniform.log_prob (distributions.py:366-396)
+    against the reference's golden vectors: the shift is bit-exact in fp32."""
+    from zuko_b200.distributions import BoxUniform
+    from zuko_b200.transforms import CircularShiftTransform
+
+    UN = load("units_ncsf")
+    x = dev_t(UN["circ_x"], device)
+    for tag, b in (("circ1", 1.0), ("circpi", float(np.pi))):
+        t = CircularShiftTransform(bound=b)
+        y, ladj = t.call_and_ladj(x)
+        assert np.array_equal(y.cpu().numpy(), UN[f"{tag}_y32"]) and float(ladj.abs().max()) == 0.0
+        assert np.array_equal(t.inv(x).cpu().numpy(), UN[f"{tag}_y32"])
+    box = BoxUniform(dev_t(UN["box_lower"], device), dev_t(UN["box_upper"], device))
+    lp = cpu(box.log_prob(dev_t(UN["box_z"], device)))
+    ref = UN["box_lp64"]
+    assert np.array_equal(np.isinf(lp), np.isinf(ref))
+    assert rel_err(lp[np.isfinite(ref)], ref[np.isfinite(ref)]) < 1e-6
+    s = box.sample((1000,))
+    assert s.shape == (1000, 3) and bool(((s >= box.lower) & (s < box.upper)).all())
+
+
 def test_parameter_update_repacks(device):
     """The packed weights are a cache keyed on (data_ptr, version): an in-place update (an
     optimizer step) must be seen by the next call."""

@@ -131,3 +131,25 @@ def test_inverse_and_log_prob_consistent():
     spec = O.flowspec_from_module(build_flow("nsf35_row", g))
     x, lp = spec.inverse_and_log_prob(g["zin"], g["c"])
     np.testing.assert_allclose(lp, spec.log_prob(x, g["c"]), rtol=1e-12, atol=1e-12)
+
+
+# --------------------------------------------------------------------------- #
+# circular spline flow pieces (NCSF): CircularShiftTransform, BoxUniform
+# --------------------------------------------------------------------------- #
+
+UN = load("units_ncsf")
+
+
+@pytest.mark.parametrize("tag,bound", [("circ1", 1.0), ("circpi", float(np.pi))])
+def test_circular_shift(tag, bound):
+    x = UN["circ_x"]
+    np.testing.assert_allclose(O.circular_shift(x, bound), UN[f"{tag}_y64"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(O.circular_shift(x, bound), UN[f"{tag}_xinv64"], rtol=1e-12, atol=1e-12)  # its own inverse
+    np.testing.assert_array_equal(O.circular_shift(x, bound, dtype=np.float32), UN[f"{tag}_y32"])  # fp32: bit-exact
+
+
+def test_box_uniform_log_prob():
+    lp = O.box_uniform_log_prob(UN["box_z"], UN["box_lower"], UN["box_upper"])
+    ref = UN["box_lp64"]
+    assert np.array_equal(np.isinf(lp), np.isinf(ref)) and np.isinf(ref).any() and np.isfinite(ref).any()
+    np.testing.assert_allclose(lp[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-12)

@@ -21,7 +21,8 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libzuko_b200.so"
 
 # status codes (include/zuko_b200.h)
 ZK_OK, ZK_EINVAL, ZK_EUNSUPPORTED, ZK_ECUDA, ZK_ENOMEM = range(5)
-ZK_UNI_AFFINE, ZK_UNI_RQS = 1, 2
+ZK_UNI_AFFINE, ZK_UNI_RQS, ZK_UNI_CRQS = 1, 2, 3
+ZK_BASE_DIAG_NORMAL, ZK_BASE_BOX_UNIFORM = 0, 1
 (
     ZK_LAYER_AUTOREGRESSIVE,
     ZK_LAYER_COUPLING,
@@ -86,6 +87,7 @@ class FlowDesc(ctypes.Structure):
         ("context", c_int),
         ("base_loc", c_void_p),
         ("base_scale", c_void_p),
+        ("base_kind", c_int),
     ]
 
 
@@ -108,6 +110,8 @@ _SIGNATURES = {
     "zk_softclip_inverse": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
     "zk_permute": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, _P]),
     "zk_rotate": (c_int, [_P, c_int64, _P, c_int, c_int64, c_int, _P, c_int64, _P]),
+    "zk_circular_shift": (c_int, [_P, c_int64, c_int64, c_int, c_float, _P, c_int64, _P]),
+    "zk_box_uniform_log_prob": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, _P, _P]),
     "zk_diag_normal_log_prob": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, _P, _P]),
     "zk_mlp_create": (c_int, [POINTER(MlpDesc), POINTER(c_void_p)]),
     "zk_mlp_destroy": (c_int, [_P]),

@@ -118,8 +118,9 @@ class FlowCall:
     _warned_inverse = False
 
     def __init__(self, handles: Sequence, D: int, C: int, loc: Tensor | None, scale: Tensor | None,
-                 sources: Sequence[dict] | None = None, keep: Sequence | None = None) -> None:  # fmt: skip
+                 sources: Sequence[dict] | None = None, keep: Sequence | None = None, base_kind: int = 0) -> None:  # fmt: skip
         self.D, self.C = D, C
+        self.base_kind = base_kind  # E.ZK_BASE_*: DiagNormal(loc, scale) or BoxUniform(lower=loc, upper=scale)
         self._handles = list(handles)
         # per layer: the tensors its parameter gradients belong to ({"weights", "biases"} of the
         # conditioner, {"phi"} shared table pieces, {"R"} rotation matrix) — see _FlowFunction
@@ -142,7 +143,7 @@ class FlowCall:
         if self._loc is not None:
             E.require_cuda(self._loc, "base loc")
             E.require_cuda(self._scale, "base scale")
-        self.desc = E.FlowDesc(len(handles), self._arr, D, C, _ptr(self._loc), _ptr(self._scale))
+        self.desc = E.FlowDesc(len(handles), self._arr, D, C, _ptr(self._loc), _ptr(self._scale), base_kind)
 
     def _ws(self, device, B: int):
         L = E.lib()

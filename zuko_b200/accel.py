@@ -44,6 +44,9 @@ from .lazy import (
 # constructors a reference `Unconditional*` / `univariate=` hook may name -> engine classes
 _ENGINE_CALLABLES = {
     "DiagNormal": _D.DiagNormal,
+    "BoxUniform": _D.BoxUniform,
+    "CircularRQSTransform": _T.CircularRQSTransform,
+    "CircularShiftTransform": _T.CircularShiftTransform,
     "MonotonicAffineTransform": _T.MonotonicAffineTransform,
     "MonotonicRQSTransform": _T.MonotonicRQSTransform,
     "SoftclipTransform": _T.SoftclipTransform,

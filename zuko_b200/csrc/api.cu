@@ -125,6 +125,14 @@ zk_status zk_rotate(const float* x, int64_t ldx, const float* R, int transpose, 
                     float* y, int64_t ldy, zk_stream stream) {
     return launch_rotate(x, ldx, R, transpose, B, D, y, ldy, (cudaStream_t)stream);
 }
+zk_status zk_circular_shift(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y, int64_t ldy,
+                            zk_stream stream) {
+    return launch_circular_shift(x, ldx, B, D, bound, y, ldy, (cudaStream_t)stream);
+}
+zk_status zk_box_uniform_log_prob(const float* z, int64_t ldz, const float* lower, const float* upper,
+                                  const float* ladj, int64_t B, int D, float* out, zk_stream stream) {
+    return launch_box_uniform(z, ldz, lower, upper, ladj, B, D, out, (cudaStream_t)stream);
+}
 zk_status zk_diag_normal_log_prob(const float* z, int64_t ldz, const float* loc, const float* scale,
                                   const float* ladj, int64_t B, int D, float* out, zk_stream stream) {
     return launch_diag_normal(z, ldz, loc, scale, ladj, B, D, out, (cudaStream_t)stream);
@@ -265,13 +273,17 @@ zk_status zk_layer_destroy(zk_layer* l) {
 
 static zk_status layer_create_impl(const zk_layer_desc* d, zk_layer* l) {
     l->kind = d->kind; l->D = d->features; l->C = d->context; l->uni = d->univariate;
+    if (l->uni == ZK_UNI_CRQS) {  // circular spline = shift + RQS over [-bound, bound] (flows/spline.py:65-72)
+        l->uni = ZK_UNI_RQS;
+        l->circ = true;
+    }
     l->K = d->bins; l->bound = d->bound; l->slope = d->slope; l->passes = d->passes;
     ZK_REQUIRE(l->D >= 1, "layer_create: features=%d", l->D);
     ZK_REQUIRE(l->C >= 0, "layer_create: context=%d", l->C);
     const bool has_uni = (l->kind == ZK_LAYER_AUTOREGRESSIVE || l->kind == ZK_LAYER_COUPLING ||
                           l->kind == ZK_LAYER_ELEMENTWISE);
     if (has_uni) {
-        ZK_REQUIRE(l->uni == ZK_UNI_AFFINE || l->uni == ZK_UNI_RQS, "layer_create: univariate=%d", l->uni);
+        ZK_REQUIRE(l->uni == ZK_UNI_AFFINE || l->uni == ZK_UNI_RQS, "layer_create: univariate=%d", d->univariate);
         if (l->uni == ZK_UNI_RQS) ZK_REQUIRE(l->K >= 1 && l->K <= 1024, "layer_create: bins=%d", l->K);
         ZK_REQUIRE(l->slope > 0.f && l->slope < 1.f, "layer_create: slope=%g", (double)l->slope);
         l->P = (l->uni == ZK_UNI_RQS) ? 3 * l->K - 1 : 2;
@@ -427,11 +439,11 @@ zk_status layer_forward_impl(const zk_layer* l, const float* x, int64_t ldx, con
     UniArgs a;
     a.univariate = l->uni; a.B = B; a.K = l->K; a.bound = l->bound; a.slope = l->slope;
     a.ladj = ladj; a.accumulate = accumulate; a.log_prob = log_prob; a.base_loc = loc;
-    a.base_scale = scale; a.fast_math = g_fast_math.load() != 0;
+    a.base_scale = scale; a.fast_math = g_fast_math.load() != 0; a.circular = l->circ;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:1005-1007 + flows/autoregressive.py:207-215
-            if (g_fused.load() && fused_layer_supported(l->hyper, l->uni, l->K, l->D, l->C)) {
+            if (g_fused.load() && !l->circ && fused_layer_supported(l->hyper, l->uni, l->K, l->D, l->C)) {
                 // ONE kernel: conditioner GEMMs + bijector + ladj; neither the hidden
                 // activations nor phi touch HBM
                 FusedLayerArgs f;
@@ -502,12 +514,12 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
     Arena ar(ws, ws_bytes);
     UniArgs a;
     a.univariate = l->uni; a.inverse = true; a.B = B; a.K = l->K; a.bound = l->bound;
-    a.slope = l->slope; a.fast_math = g_fast_math.load() != 0;
+    a.slope = l->slope; a.fast_math = g_fast_math.load() != 0; a.circular = l->circ;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:994-1000: x = zeros_like(y); for _ in range(passes): x = meta(x).inv(y)
             if (l->inv && g_fused.load())  // same fixed point, every weight visited once (ar_inverse.cu)
-                return launch_ar_inverse(l->inv, y, ldy, c, ldc, B, x, ldx, l->bound, l->slope, g_fast_math.load() != 0, st);
+                return launch_ar_inverse(l->inv, y, ldy, c, ldc, B, x, ldx, l->bound, l->slope, g_fast_math.load() != 0, l->circ, st);
             float* phi = ar.take<float>((size_t)B * l->D * l->P);
             ZK_REQUIRE(ar.ok, "layer_inverse: workspace too small");
             if (ldx == l->D) {
@@ -599,6 +611,8 @@ zk_status flow_check(const zk_flow_desc* f) {
     ZK_REQUIRE(f->n_layers >= 0 && (f->n_layers == 0 || f->layers), "flow: bad layer list");
     ZK_REQUIRE(f->features >= 1 && f->context >= 0, "flow: bad features/context");
     ZK_REQUIRE((f->base_loc == nullptr) == (f->base_scale == nullptr), "flow: base loc/scale must both be set or null");
+    ZK_REQUIRE(f->base_kind == ZK_BASE_DIAG_NORMAL || f->base_kind == ZK_BASE_BOX_UNIFORM, "flow: unknown base kind %d", f->base_kind);
+    ZK_REQUIRE(f->base_kind != ZK_BASE_BOX_UNIFORM || f->base_loc, "flow: a BoxUniform base needs lower / upper bounds");
     for (int i = 0; i < f->n_layers; ++i) {
         const zk_layer* l = f->layers[i];
         ZK_REQUIRE(l, "flow: layer %d is null", i);
@@ -626,7 +640,7 @@ zk_status flow_forward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx,
         const zk_layer* l = f->layers[i];
         const bool last = (i == T - 1);
         const float* cc = l->C ? c : nullptr;
-        if (last && log_prob && layer_can_fuse_base(l)) {
+        if (last && log_prob && layer_can_fuse_base(l) && f->base_kind == ZK_BASE_DIAG_NORMAL) {
             ZK_TRY(layer_forward_impl(l, cur, ldcur, cc, ldc, B, nullptr, 0, ladj, i > 0, log_prob,
                                       f->base_loc, f->base_scale, lws, lws_bytes, st));
             fused = true;
@@ -643,8 +657,12 @@ zk_status flow_forward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx,
         ZK_TRY(launch_fill(ladj, B, 0.f, st));
         if (z) ZK_TRY(copy_rows(x, ldx, B, D, z, ldz, st));
     }
-    if (log_prob && !fused)
-        ZK_TRY(launch_diag_normal(cur, ldcur, f->base_loc, f->base_scale, ladj, B, D, log_prob, st));
+    if (log_prob && !fused) {
+        if (f->base_kind == ZK_BASE_BOX_UNIFORM)
+            ZK_TRY(launch_box_uniform(cur, ldcur, f->base_loc, f->base_scale, ladj, B, D, log_prob, st));
+        else
+            ZK_TRY(launch_diag_normal(cur, ldcur, f->base_loc, f->base_scale, ladj, B, D, log_prob, st));
+    }
     return ZK_OK;
 }
 

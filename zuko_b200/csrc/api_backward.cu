@@ -275,7 +275,7 @@ zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, co
     ZK_REQUIRE(l->C == 0 || c != nullptr, "layer needs a context of %d features", l->C);
     Arena ar(ws, ws_bytes);
     UniBwdArgs u;
-    u.univariate = l->uni; u.B = B; u.K = l->K; u.bound = l->bound; u.slope = l->slope;
+    u.univariate = l->uni; u.B = B; u.K = l->K; u.bound = l->bound; u.slope = l->slope; u.circular = l->circ;
     u.x = x; u.ldx = ldx; u.gy = gy; u.ldgy = ldgy; u.gl = gl; u.gx = gx; u.ldgx = ldgx;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE:
@@ -428,7 +428,10 @@ zk_status flow_backward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx
                                   nullptr, nullptr, lws, lws_bytes, st));
     }
     // seed: dL/dz_T and dL/dladj (distributions.py:115-119)
-    ZK_TRY(launch_base_grad(z[T], ldz[T], f->base_loc, f->base_scale, g_lp, gz_in, ldgz, gl_in, B, D, gA, gl, st));
+    if (f->base_kind == ZK_BASE_BOX_UNIFORM)  // constant density on the support: no d/dz term
+        ZK_TRY(launch_base_grad_flat(g_lp, gz_in, ldgz, gl_in, B, D, gA, gl, st));
+    else
+        ZK_TRY(launch_base_grad(z[T], ldz[T], f->base_loc, f->base_scale, g_lp, gz_in, ldgz, gl_in, B, D, gA, gl, st));
     const float* cur = gA;
     int64_t ldcur = D;
     for (int i = T - 1; i >= 0; --i) {

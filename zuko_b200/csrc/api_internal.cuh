@@ -50,6 +50,7 @@ inline zk_status dev_copy_from_host(const T* host, size_t n, T** out) {
 struct zk_layer {
     int kind = 0, D = 0, C = 0, uni = 0, K = 0, P = 0, passes = 0;
     float bound = 5.f, slope = 1e-3f;
+    bool circ = false;             // ZK_UNI_CRQS: CircularShiftTransform(bound) in front of the spline
     zk_mlp* hyper = nullptr;       // owned
     float* phi_shared = nullptr;   // device (D, P), owned
     float* rotation = nullptr;     // device (D, D), owned

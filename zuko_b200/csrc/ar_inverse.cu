@@ -61,6 +61,7 @@ struct InvParams {
     float* x; int64_t ldx;
     int64_t B;
     float bound, aw, ad;
+    int circ;  // circular RQS (NCSF): CircularShiftTransform(bound) applied to the solved dimension
 };
 
 // acc[j] += sum_k state[k][tid] * w[k][j]  over one 8-row tile (weights broadcast from smem)
@@ -162,6 +163,7 @@ __global__ void ar_inverse_kernel(const InvParams p) {
                 if constexpr (UNI == ZK_UNI_RQS) {
                     Bin b = rqs_select<KT, FAST, true>(phi, KT, yv, p.bound, p.aw, p.ad);
                     xv = rqs_inverse_eval<FAST>(b, yv);
+                    if (p.circ) xv = circ_shift(xv, p.bound);  // inverse of flows/spline.py:68-71
                 } else {
                     const float ls = softclip<FAST>(phi[1], p.ad);
                     xv = zdiv<FAST>(yv - phi[0], zexp<FAST>(ls));
@@ -337,7 +339,7 @@ bool ar_inverse_threads(const ArInvPack* pk, int* threads, size_t* smem) {
 }
 
 zk_status launch_ar_inverse(const ArInvPack* pk, const float* y, int64_t ldy, const float* c, int64_t ldc, int64_t B,
-                            float* x, int64_t ldx, float bound, float slope, bool fast, cudaStream_t st) {
+                            float* x, int64_t ldx, float bound, float slope, bool fast, bool circular, cudaStream_t st) {
     if (B == 0) return ZK_OK;
     int T = 0;
     size_t smem = 0;
@@ -349,6 +351,7 @@ zk_status launch_ar_inverse(const ArInvPack* pk, const float* y, int64_t ldy, co
     for (size_t i = 0; i < pk->sec_off.size(); ++i) p.sec_off[i] = pk->sec_off[i];
     p.y = y; p.ldy = ldy; p.c = c; p.ldc = ldc; p.x = x; p.ldx = ldx; p.B = B;
     p.bound = bound;
+    p.circ = circular ? 1 : 0;
     const float absL = fabsf(logf(slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;

@@ -15,6 +15,6 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
 void ar_inverse_free(ArInvPack* pk);
 bool ar_inverse_threads(const ArInvPack* pk, int* threads, size_t* smem);
 zk_status launch_ar_inverse(const ArInvPack* pk, const float* y, int64_t ldy, const float* c, int64_t ldc, int64_t B,
-                            float* x, int64_t ldx, float bound, float slope, bool fast, cudaStream_t stream);
+                            float* x, int64_t ldx, float bound, float slope, bool fast, bool circular, cudaStream_t stream);
 
 }  // namespace zk

@@ -26,7 +26,15 @@ struct UniBwdParams {
     int64_t B; int D; int K; int P;
     float bound, aw, ad;
     int rows_per_tile;
+    int circ;
 };
+
+__device__ __forceinline__ float circ_shift_b(float x, float bound) {  // bijector_math.cuh:circ_shift
+    const float m = 2.f * bound;
+    float r = fmodf(x, m);
+    if (r != 0.f && r < 0.f) r += m;
+    return r - bound;
+}
 
 // thread = (sample row, dim) pair; the tile's parameter block is staged in shared memory, every
 // pair rewrites its P slots with the parameter gradients, and the tile is written back with
@@ -56,7 +64,8 @@ __global__ void __launch_bounds__(kBwdThreads) uni_bwd_kernel(const UniBwdParams
         const int row = p / D;
         const int d = p - row * D;
         const int col = a.dim_map ? a.dim_map[d] : d;
-        const float xv = a.x[(r0 + row) * a.ldx + col];
+        float xv = a.x[(r0 + row) * a.ldx + col];
+        if (UNI == ZK_UNI_RQS && a.circ) xv = circ_shift_b(xv, a.bound);
         const float gyv = a.gy ? a.gy[(r0 + row) * a.ldgy + col] : 0.f;
         const float glv = a.gl ? a.gl[r0 + row] : 0.f;
         const float* pp = s_phi + (shared_tbl ? d * P : p * P);
@@ -291,6 +300,7 @@ zk_status launch_univariate_backward(const UniBwdArgs& a, cudaStream_t stream) {
     p.x = a.x; p.ldx = a.ldx; p.phi = a.phi; p.phi_ld = a.phi_ld; p.gy = a.gy; p.ldgy = a.ldgy;
     p.gl = a.gl; p.gx = a.gx; p.ldgx = a.ldgx; p.gphi = a.gphi; p.dim_map = a.dim_map; p.B = a.B;
     p.D = a.D; p.K = a.K; p.P = P; p.bound = a.bound;
+    p.circ = (a.circular && a.univariate == ZK_UNI_RQS) ? 1 : 0;
     const float absL = fabsf(logf(a.slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
@@ -332,6 +342,16 @@ zk_status launch_base_grad(const float* z, int64_t ldz, const float* loc, const 
     if (B == 0) return ZK_OK;
     base_grad_kernel<<<(unsigned)ceil_div(B * D, 256), 256, 0, st>>>(z, ldz, loc, scale, g_lp, gz_in, ldgz_in, gl_in, B, D, gz, gl);
     return check_launch("base_grad_kernel");
+}
+
+zk_status launch_base_grad_flat(const float* g_lp, const float* gz_in, int64_t ldgz_in, const float* gl_in,
+                                int64_t B, int D, float* gz, float* gl, cudaStream_t st) {
+    ZK_REQUIRE(B >= 0 && D > 0 && gz && gl, "base grad: bad arguments");
+    if (B == 0) return ZK_OK;
+    base_grad_kernel<<<(unsigned)ceil_div(B * D, 256), 256, 0, st>>>(nullptr, 0, nullptr, nullptr, nullptr, gz_in, ldgz_in, gl_in, B, D, gz, gl);
+    ZK_TRY(check_launch("base_grad_kernel"));
+    if (g_lp) return launch_add(gl, g_lp, B, st);
+    return ZK_OK;
 }
 
 zk_status launch_concat(const float* x, int64_t ldx, const int* cols, int nx, const float* c,

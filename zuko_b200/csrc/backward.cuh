@@ -31,6 +31,7 @@ struct UniBwdArgs {
     int64_t B = 0;
     int D = 0, K = 0;
     float bound = 5.f, slope = 1e-3f;
+    bool circular = false;  // RQS: CircularShiftTransform(bound) in front (d shift / dx = 1)
 };
 zk_status launch_univariate_backward(const UniBwdArgs& a, cudaStream_t stream);
 
@@ -44,7 +45,10 @@ zk_status launch_softclip_backward(const float* x, int64_t ldx, const float* gy,
 zk_status launch_base_grad(const float* z, int64_t ldz, const float* loc, const float* scale,
                            const float* g_lp, const float* gz_in, int64_t ldgz_in,
                            const float* gl_in, int64_t B, int D, float* gz, float* gl,
-                           cudaStream_t stream);
+                           cudaStream_t stream);  // loc == scale == nullptr with g_lp: standard normal; see `flat_base`
+// same seed for a base whose density is constant on its support (BoxUniform): d log p / dz = 0
+zk_status launch_base_grad_flat(const float* g_lp, const float* gz_in, int64_t ldgz_in, const float* gl_in,
+                                int64_t B, int D, float* gz, float* gl, cudaStream_t stream);
 
 // out (B, nx + nc) = cat(x[:, cols] (or x[:, :nx] when cols == null), c)  (autoregressive.py:209)
 zk_status launch_concat(const float* x, int64_t ldx, const int* cols, int nx, const float* c,

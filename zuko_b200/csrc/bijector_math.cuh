@@ -63,6 +63,15 @@ __device__ __forceinline__ float softclip(float v, float a) {
     return zdiv<FAST>(v, fmaf(fabsf(v), a, 1.0f));
 }
 
+// CircularShiftTransform: remainder(x, 2B) - B with torch.remainder's sign convention
+// (transforms.py:344-348; result of the remainder in [0, 2B))
+__device__ __forceinline__ float circ_shift(float x, float bound) {
+    const float m = 2.f * bound;
+    float r = fmodf(x, m);
+    if (r != 0.f && r < 0.f) r += m;
+    return r - bound;
+}
+
 // ---------------------------------------------------------------------------
 // RQS: select the bin and its six knot values in one sweep over the K bins.
 // p points at this pair's P = 3K-1 raw parameters in shared memory:

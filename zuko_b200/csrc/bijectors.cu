@@ -43,6 +43,7 @@ struct UniParams {
     int64_t B; int D; int K; int P;
     float bound, aw, ad;
     int rows_per_tile;
+    int circ;      // RQS: circular shift by `bound` before the spline (forward) / after it (inverse)
     int use_bulk;  // host-side verdict: alignment rules for cp.async.bulk hold for full tiles
 };
 
@@ -92,16 +93,18 @@ __global__ void __launch_bounds__(kUniThreads) uni_kernel(const UniParams a) {
             row = p / D;
             d = p - row * D;
             const int col = a.dim_map ? a.dim_map[d] : d;
-            const float xv = a.x[(r0 + row) * a.ldx + col];
+            float xv = a.x[(r0 + row) * a.ldx + col];
             const float* pp = s_phi + (shared_tbl ? d * P : p * P);
             float yv;
             if constexpr (UNI == ZK_UNI_RQS) {
                 if constexpr (!INVERSE) {
+                    if (a.circ) xv = circ_shift(xv, a.bound);  // flows/spline.py:68-71
                     Bin b = rqs_select<KT, FAST, false>(pp, a.K, xv, a.bound, a.aw, a.ad);
                     rqs_forward_eval<FAST>(b, xv, yv, lj);
                 } else {
                     Bin b = rqs_select<KT, FAST, true>(pp, a.K, xv, a.bound, a.aw, a.ad);
                     yv = rqs_inverse_eval<FAST>(b, xv);
+                    if (a.circ) yv = circ_shift(yv, a.bound);
                 }
             } else {  // affine, transforms.py:435-446: phi = (shift, unconstrained log-scale)
                 const float shift = pp[0];
@@ -197,6 +200,7 @@ zk_status launch_univariate(const UniArgs& a, cudaStream_t stream) {
     p.y = a.y; p.ldy = a.ldy; p.ladj = a.ladj; p.accumulate = a.accumulate;
     p.log_prob = a.log_prob; p.base_loc = a.base_loc; p.base_scale = a.base_scale;
     p.dim_map = a.dim_map; p.B = a.B; p.D = a.D; p.K = a.K; p.P = P; p.bound = a.bound;
+    p.circ = (a.circular && a.univariate == ZK_UNI_RQS) ? 1 : 0;
     const float absL = fabsf(logf(a.slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
@@ -269,6 +273,31 @@ __global__ void rotate_kernel(const float* x, int64_t ldx, const float* R, int t
     for (int j = 0; j < D; ++j)
         acc = fmaf(transpose ? sR[j * D + o] : sR[o * D + j], x[r * ldx + j], acc);
     y[r * ldy + o] = acc;
+}
+
+// CircularShiftTransform, transforms.py:344-348
+__global__ void circular_shift_kernel(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y, int64_t ldy) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    y[r * ldy + d] = circ_shift(x[r * ldx + d], bound);
+}
+
+// BoxUniform.log_prob (+ ladj): Independent(Uniform(lower, upper), 1) — torch/distributions/uniform.py:
+// log(lower <= z) + log(z < upper) - log(upper - lower), summed over the event dim
+__global__ void box_uniform_kernel(const float* z, int64_t ldz, const float* lower, const float* upper,
+                                   const float* ladj, int64_t B, int D, float* out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    float acc = 0.f;
+    bool inside = true;
+    for (int d = 0; d < D; ++d) {
+        const float v = z[r * ldz + d];
+        inside = inside && (lower[d] <= v) && (v < upper[d]);
+        acc -= logf(upper[d] - lower[d]);
+    }
+    out[r] = inside ? acc + (ladj ? ladj[r] : 0.f) : -CUDART_INF_F;
 }
 
 // DiagNormal.log_prob (+ ladj), one thread per sample row
@@ -371,6 +400,22 @@ zk_status launch_diag_normal(const float* z, int64_t ldz, const float* loc, cons
     if (B == 0) return ZK_OK;
     diag_normal_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(z, ldz, loc, scale, ladj, B, D, out);
     return check_launch("diag_normal_kernel");
+}
+
+zk_status launch_circular_shift(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y,
+                                int64_t ldy, cudaStream_t st) {
+    ZK_REQUIRE(B >= 0 && D > 0 && x && y && bound > 0.f, "circular shift: bad arguments");
+    if (B == 0) return ZK_OK;
+    circular_shift_kernel<<<(unsigned)ceil_div(B * D, 256), 256, 0, st>>>(x, ldx, B, D, bound, y, ldy);
+    return check_launch("circular_shift_kernel");
+}
+
+zk_status launch_box_uniform(const float* z, int64_t ldz, const float* lower, const float* upper,
+                             const float* ladj, int64_t B, int D, float* out, cudaStream_t st) {
+    ZK_REQUIRE(B >= 0 && D > 0 && z && out && lower && upper, "box_uniform: bad arguments");
+    if (B == 0) return ZK_OK;
+    box_uniform_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(z, ldz, lower, upper, ladj, B, D, out);
+    return check_launch("box_uniform_kernel");
 }
 
 size_t reduce_scratch_bytes() { return kRedBlocks * sizeof(double); }

@@ -27,6 +27,7 @@ struct UniArgs {
     int K = 0;      // bins (RQS)
     float bound = 5.f;
     float slope = 1e-3f;
+    bool circular = false;  // RQS only: CircularShiftTransform(bound) in front (forward) / behind (inverse)
     bool fast_math = true;  // MUFU rcp/ex2/lg2 fast path (default) vs IEEE div + expf/logf
 };
 
@@ -38,6 +39,10 @@ zk_status launch_permute(const float* x, int64_t ldx, const int64_t* order, int6
                          float* y, int64_t ldy, cudaStream_t stream);
 zk_status launch_rotate(const float* x, int64_t ldx, const float* R, int transpose, int64_t B, int D,
                         float* y, int64_t ldy, cudaStream_t stream);
+zk_status launch_circular_shift(const float* x, int64_t ldx, int64_t B, int D, float bound, float* y,
+                                int64_t ldy, cudaStream_t stream);
+zk_status launch_box_uniform(const float* z, int64_t ldz, const float* lower, const float* upper,
+                             const float* ladj, int64_t B, int D, float* out, cudaStream_t stream);
 zk_status launch_diag_normal(const float* z, int64_t ldz, const float* loc, const float* scale,
                              const float* ladj, int64_t B, int D, float* out, cudaStream_t stream);
 // out[0] = sum_b v[b] in double, fixed-order two-stage reduction; scratch >= reduce_scratch_bytes()

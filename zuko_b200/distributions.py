@@ -7,7 +7,7 @@ random numbers (``torch.randn`` on the device) and owns all memory.
 
 from __future__ import annotations
 
-__all__ = ["DiagNormal", "NormalizingFlow"]
+__all__ = ["BoxUniform", "DiagNormal", "NormalizingFlow"]
 
 from textwrap import indent
 
@@ -83,6 +83,55 @@ class DiagNormal(Distribution):
         return out.reshape(lead)
 
 
+class BoxUniform(Distribution):
+    """Uniform distribution over the box ``lower_i <= x_i < upper_i`` (zuko/distributions.py:366-396 =
+    Independent(Uniform(lower, upper), 1)); the base of ``NCSF`` (flows/spline.py:111-116).
+
+    ``log_prob`` is evaluated by ``zk_box_uniform_log_prob``: ``-sum log(upper - lower)`` inside the
+    box, ``-inf`` outside (torch/distributions/uniform.py)."""
+
+    has_rsample = True
+    arg_constraints = {}
+
+    def __init__(self, lower: Tensor, upper: Tensor, ndims: int = 1) -> None:
+        lower, upper = torch.as_tensor(lower), torch.as_tensor(upper)
+        if ndims != 1 or lower.dim() != 1 or upper.shape != lower.shape:
+            raise NotImplementedError("zuko_b200: BoxUniform supports 1-d lower/upper and ndims=1 only")
+        self.lower, self.upper = lower, upper
+        super().__init__(batch_shape=Size(), event_shape=lower.shape, validate_args=False)
+
+    def __repr__(self) -> str:
+        return f"BoxUniform(lower: {self.lower.shape}, upper: {self.upper.shape})"
+
+    def expand(self, batch_shape: Size, new: Distribution | None = None) -> Distribution:
+        new = self._get_checked_instance(BoxUniform, new)
+        new.lower, new.upper = self.lower, self.upper
+        Distribution.__init__(new, batch_shape=Size(batch_shape), event_shape=self.event_shape, validate_args=False)
+        return new
+
+    def rsample(self, shape: Size = ()) -> Tensor:
+        full = Size(shape) + self.batch_shape + self.event_shape
+        u = torch.rand(full, device=self.lower.device, dtype=self.lower.dtype)  # torch RNG (uniform.py)
+        return self.lower + u * (self.upper - self.lower)
+
+    def sample(self, shape: Size = ()) -> Tensor:
+        with torch.no_grad():
+            return self.rsample(shape)
+
+    def log_prob(self, z: Tensor) -> Tensor:
+        E.require_cuda(z, "input")
+        D = self.lower.shape[0]
+        lead = torch.broadcast_shapes(z.shape[:-1], self.batch_shape)
+        z2 = z.detach().expand(*lead, D).reshape(-1, D).contiguous()
+        out = torch.empty(z2.shape[0], device=z.device, dtype=torch.float32)
+        lo, hi = self.lower.detach().contiguous(), self.upper.detach().contiguous()
+        E.require_cuda(lo, "lower bound")
+        with torch.cuda.device(z.device):
+            E.check(E.lib().zk_box_uniform_log_prob(z2.data_ptr(), D, lo.data_ptr(), hi.data_ptr(), None,
+                                                    z2.shape[0], D, out.data_ptr(), E.stream_ptr(z.device)))  # fmt: skip
+        return out.reshape(lead)
+
+
 class NormalizingFlow(Distribution):
     """Normalizing flow ``p(x) = p_Z(f(x)) |det df/dx|`` (zuko/distributions.py:39-138).
 
@@ -128,11 +177,14 @@ class NormalizingFlow(Distribution):
             return self.__dict__["_fc"]
         fc = None
         t, base = self.transform, self.base
-        if isinstance(t, ComposedTransform) and isinstance(base, DiagNormal) and self.reinterpreted == 0:
-            fused = t._fused(base.loc.shape[0])
+        if isinstance(t, ComposedTransform) and isinstance(base, (DiagNormal, BoxUniform)) and self.reinterpreted == 0:
+            box = isinstance(base, BoxUniform)
+            first, second = (base.lower, base.upper) if box else (base.loc, base.scale)
+            fused = t._fused(first.shape[0])
             if fused is not None:
                 call, ctx = fused
-                fc = (_ops.FlowCall(call._handles, call.D, call.C, base.loc, base.scale, sources=call._sources, keep=call._keep), ctx)
+                fc = (_ops.FlowCall(call._handles, call.D, call.C, first, second, sources=call._sources, keep=call._keep,
+                                    base_kind=E.ZK_BASE_BOX_UNIFORM if box else E.ZK_BASE_DIAG_NORMAL), ctx)  # fmt: skip
         self.__dict__["_fc"] = fc
         return fc
 

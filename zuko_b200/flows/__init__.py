@@ -3,11 +3,12 @@
 from .autoregressive import MAF, MaskedAutoregressiveTransform
 from .coupling import NICE, GeneralCouplingTransform, RealNVP
 from .elementwise import ElementWiseTransform
-from .spline import NSF
+from .spline import NCSF, NSF
 from ..lazy import Flow, UnconditionalDistribution, UnconditionalTransform
 
 __all__ = [
     "MAF",
+    "NCSF",
     "NICE",
     "NSF",
     "ElementWiseTransform",

@@ -12,7 +12,9 @@ import torch
 from torch import Size
 
 from .. import _engine as E
-from ..transforms import MonotonicAffineTransform, MonotonicRQSTransform
+import math
+
+from ..transforms import CircularRQSTransform, MonotonicAffineTransform, MonotonicRQSTransform
 
 
 def resolve_univariate(univariate: Callable, shapes: Sequence[Size]) -> dict:
@@ -43,9 +45,17 @@ def resolve_univariate(univariate: Callable, shapes: Sequence[Size]) -> dict:
         K = shapes[0][0]
         return dict(kind=E.ZK_UNI_RQS, bins=K, bound=float(kwargs.get("bound", 5.0)),
                     slope=float(kwargs.get("slope", 1e-3)), total=3 * K - 1)  # fmt: skip
+    if f is CircularRQSTransform:  # flows/spline.py:65-72: CircularShift(pi) then RQS(bound=pi)
+        if len(shapes) != 3 or shapes[0] != shapes[1] or len(shapes[0]) != 1 or shapes[2] != (shapes[0][0] - 1,):
+            raise ValueError(f"CircularRQSTransform expects shapes [(K,), (K,), (K-1,)], got {shapes}")
+        extra = set(kwargs) - {"slope"}
+        if extra:
+            raise NotImplementedError(f"zuko_b200: unsupported CircularRQSTransform arguments {sorted(extra)}")
+        K = shapes[0][0]
+        return dict(kind=E.ZK_UNI_CRQS, bins=K, bound=math.pi, slope=float(kwargs.get("slope", 1e-3)), total=3 * K - 1)
     raise NotImplementedError(
         f"zuko_b200: univariate transformation {getattr(f, '__name__', f)!r} is not implemented by the engine "
-        "(supported: MonotonicAffineTransform, MonotonicRQSTransform)"
+        "(supported: MonotonicAffineTransform, MonotonicRQSTransform, CircularRQSTransform)"
     )
 
 
@@ -136,6 +146,8 @@ class PackedLayerMixin:
                            bins=u["bins"], bound=u["bound"], slope=u["slope"], passes=getattr(self, "passes", 0))  # fmt: skip
 
     def _describe_base(self) -> str:
+        if self._uni["kind"] == E.ZK_UNI_CRQS:
+            return "CircularRQSTransform(bins=%d)" % self._uni["bins"]
         return "MonotonicRQSTransform(bins=%d)" % self._uni["bins"] if self._uni["kind"] == E.ZK_UNI_RQS else "MonotonicAffineTransform()"
 
 

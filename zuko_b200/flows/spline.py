@@ -2,11 +2,17 @@
 
 from __future__ import annotations
 
-__all__ = ["NSF"]
+__all__ = ["NCSF", "NSF"]
 
 from functools import partial
 
-from ..transforms import MonotonicRQSTransform
+from math import pi
+
+import torch
+
+from ..distributions import BoxUniform
+from ..lazy import UnconditionalDistribution
+from ..transforms import CircularRQSTransform, MonotonicRQSTransform
 from .autoregressive import MAF
 
 
@@ -22,4 +28,24 @@ class NSF(MAF):
             univariate=partial(MonotonicRQSTransform, slope=slope),
             shapes=[(bins,), (bins,), (bins - 1,)],
             **kwargs,
+        )
+
+
+class NCSF(MAF):
+    """Neural circular spline flow (zuko/flows/spline.py:75-117): a :class:`MAF` whose univariate
+    bijector is the circular RQS over ``[-pi, pi[`` and whose base is uniform over that box."""
+
+    def __init__(self, features: int, context: int = 0, bins: int = 8, slope: float = 1e-3, **kwargs) -> None:
+        super().__init__(
+            features=features,
+            context=context,
+            univariate=partial(CircularRQSTransform, slope=slope),
+            shapes=[(bins,), (bins,), (bins - 1,)],
+            **kwargs,
+        )
+        self.base = UnconditionalDistribution(
+            BoxUniform,
+            lower=torch.full((features,), -pi - 1e-5),
+            upper=torch.full((features,), pi + 1e-5),
+            buffer=True,
         )

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 __all__ = [
     "AutoregressiveTransform",
+    "CircularRQSTransform",
+    "CircularShiftTransform",
     "ComposedTransform",
     "CouplingTransform",
     "DependentTransform",
@@ -314,6 +316,56 @@ class SoftclipTransform(EngineTransform):
 
     def _layer_desc(self, D: int):
         return E.LayerDesc(kind=E.ZK_LAYER_SOFTCLIP, features=D, bound=self.bound, slope=1e-3), []
+
+
+class _CircularShiftFunction(torch.autograd.Function):
+    """y = remainder(x, 2B) - B is a translation almost everywhere: dy/dx = 1."""
+
+    @staticmethod
+    def forward(ctx, x2, bound):  # noqa: ANN001
+        y = torch.empty_like(x2)
+        with torch.cuda.device(x2.device):
+            E.check(E.lib().zk_circular_shift(x2.data_ptr(), 1, x2.shape[0], 1, bound, y.data_ptr(), 1, E.stream_ptr(x2.device)))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):  # noqa: ANN001
+        return gy, None
+
+
+class CircularShiftTransform(EngineTransform):
+    """``f(x) = (x mod 2B) - B``: circular shift of ``[-B, B]`` by half a period, its own inverse,
+    ladj 0 (zuko/transforms.py:319-351; evaluated by ``zk_circular_shift``)."""
+
+    def __init__(self, bound: float = 1.0) -> None:
+        super().__init__()
+        self.bound = float(bound)
+        self.domain = constraints.interval(-bound, bound)
+        self.codomain = constraints.interval(-bound, bound)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(bound={self.bound})"
+
+    def _shift(self, x: Tensor) -> Tensor:
+        E.require_cuda(x, "input")
+        x2 = x.reshape(-1, 1).contiguous()
+        return _CircularShiftFunction.apply(x2, self.bound).reshape(x.shape)
+
+    def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        return self._shift(x), torch.zeros_like(x)
+
+    def _inverse(self, y: Tensor) -> Tensor:
+        return self._shift(y)
+
+
+def CircularRQSTransform(*phi: Tensor, slope: float = 1e-3) -> Transform:
+    """Circular rational-quadratic spline: a circular shift of ``[-pi, pi]`` followed by the monotonic
+    RQS over the same interval (zuko/flows/spline.py:65-72).  Inside ``NCSF`` the engine evaluates
+    the pair as one univariate kind (``ZK_UNI_CRQS``)."""
+    return ComposedTransform(
+        CircularShiftTransform(bound=math.pi),
+        MonotonicRQSTransform(*phi, bound=math.pi, slope=slope),
+    )
 
 
 # --------------------------------------------------------------------------- #
