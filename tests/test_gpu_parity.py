@@ -223,7 +223,12 @@ def test_flow_forward_and_inverse_golden(device, name, gemm):
             assert np.all(ex <= np.maximum(2 * rt * np.maximum(np.abs(g["xinv64"]), 1.0), 3 * devx)), ex.max()
         # the reference's own property: t(t.inv(z)) ~ z, atol 1e-4 (tests/test_flows.py:57-61)
         # (the stress set's splines are too sharp for a 1e-4 fp32 round trip: SURVEY §7.4-1b)
-        assert torch.allclose(ti(xi), dev_t(g["zin"], device), atol=1e-2 if "w_scale" in g else 1e-4)
+        zin = dev_t(g["zin"], device)
+        back = ti(xi)
+        if name.startswith("ncsf"):  # circular flow: a bijection of [-pi, pi[ only (flows/spline.py:78-80)
+            rows = (zin.abs() < np.pi - 1e-3).all(-1)
+            zin, back = zin[rows], back[rows]
+        assert torch.allclose(back, zin, atol=1e-2 if "w_scale" in g else 1e-4)
 
 
 def test_stress_set_report(device):

@@ -45,7 +45,7 @@ def test_tcgen05_mlp_vs_oracle(device, shape, hidden, B):
     ref = _oracle_mlp(net, x)
     out = net.to(device)(x.to(device))
     assert E.lib().zk_mlp_gemm_mode(net._handle()) == E.ZK_GEMM_BF16X3
-    out = out.cpu().numpy().astype(np.float64)
+    out = out.detach().cpu().numpy().astype(np.float64)
     scale = np.abs(ref).max()
     err = np.abs(out - ref).max() / scale
     # split-bf16 (3 MMAs, fp32 accumulate): ~2^-16 per product term; bound 3e-5 of the output scale
@@ -53,7 +53,7 @@ def test_tcgen05_mlp_vs_oracle(device, shape, hidden, B):
     # and the fp32 CUDA-core path agrees with both
     net32 = _masked(shape, hidden)
     net32.gemm_mode = "fp32"
-    out32 = net32.to(device)(x.to(device)).cpu().numpy().astype(np.float64)
+    out32 = net32.to(device)(x.to(device)).detach().cpu().numpy().astype(np.float64)
     assert np.abs(out32 - ref).max() / scale < 2e-6
 
 
@@ -62,7 +62,7 @@ def test_bf16x1_is_available_but_inexact(device):
     net.gemm_mode = "bf16x1"
     x = torch.randn(4096, 24, generator=torch.Generator().manual_seed(1))
     ref = _oracle_mlp(net, x)
-    out = net.to(device)(x.to(device)).cpu().numpy().astype(np.float64)
+    out = net.to(device)(x.to(device)).detach().cpu().numpy().astype(np.float64)
     err = np.abs(out - ref).max() / np.abs(ref).max()
     assert 1e-4 < err < 3e-2, err  # single bf16 MMA: ~2^-8 per operand
 
@@ -79,7 +79,7 @@ def test_flow_parity_on_tensor_cores(device, name):
     c = None if "c" not in g else torch.from_numpy(g["c"]).to(device)
     lp = flow(c).log_prob(torch.from_numpy(g["x"]).to(device))
     assert E.lib().zk_mlp_gemm_mode(flow.transform.transforms[0].hyper._handle()) == E.ZK_GEMM_BF16X3
-    assert_log_prob_parity(lp.cpu().numpy(), g, rtol=1e-5)
+    assert_log_prob_parity(lp.detach().cpu().numpy(), g, rtol=1e-5)
 
 
 def test_auto_mode_picks_tensor_cores_for_wide_layers(device):
@@ -138,8 +138,8 @@ def test_fused_layer_matches_unfused_and_oracle(device, unfused, name, B):
     lp_u = unfused(lambda: flow(cd).log_prob(xd))
     z_u, ladj_u = unfused(lambda: flow(cd).transform.call_and_ladj(xd))
     ref = spec.log_prob(x.numpy(), None if c is None else c.numpy())
-    assert rel_err(lp_f.cpu().numpy(), ref) < 1e-5
-    assert rel_err(lp_u.cpu().numpy(), ref) < 1e-5
+    assert rel_err(lp_f.detach().cpu().numpy(), ref) < 1e-5
+    assert rel_err(lp_u.detach().cpu().numpy(), ref) < 1e-5
     # same arithmetic (split-bf16 GEMMs, same bijector math): fused and unfused agree to rounding
     assert torch.allclose(lp_f, lp_u, rtol=2e-6, atol=2e-5)
     assert torch.allclose(z_f, z_u, rtol=1e-5, atol=1e-5)
