@@ -44,13 +44,18 @@ ZK_HD void sc_parts(float v, float a, float& u, float& d) {
 //   p   : the pair's P = 3K-1 raw parameters (widths, heights, derivatives)
 //   gy  : dL/dy, gl : dL/dladj (of this pair's log-derivative)
 //   gx  : dL/dx (direct dependence only), gp : dL/dp (P values; may alias p)
-// With a compile-time K (KT > 0) the softmax numerators and soft-clip derivatives of the 2K width /
-// height parameters are computed once and kept in registers (1 reciprocal + 1 exp per parameter);
-// the run-time-K variant recomputes them per sweep with the same arithmetic (bit-identical results).
-template <int KT>
+// The softmax numerators / soft-clip derivatives of the 2K width / height parameters are recomputed
+// in each of the three sweeps (1 reciprocal + 1 exp per parameter and sweep).  Keeping them in
+// registers instead (kCacheNumerators) was measured SLOWER on B200: 92 instead of 64 registers per
+// thread at K = 8 halves the resident warps of this latency-bound kernel (1.04 ms vs 0.62 ms per
+// 2^18 x 16 pairs); the code path is kept for reference, both give bit-identical results.
+constexpr bool kCacheNumerators = false;
+
+template <int KT_>
 ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float gl, float bound,
                              float aw, float ad, float& gx, float* gp) {
-    const int K = KT > 0 ? KT : Krt;
+    constexpr int KT = kCacheNumerators ? KT_ : 0;  // 0 = recompute path
+    const int K = KT_ > 0 ? KT_ : Krt;
     const int P = 3 * K - 1;
     constexpr int KA = KT > 0 ? KT : 1;
     float ew[KA], eh[KA], dw[KA], dh[KA];
