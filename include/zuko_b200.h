@@ -67,6 +67,18 @@ typedef void* zk_stream; /* cudaStream_t */
 #define ZK_GEMM_BF16X3 2  /* tcgen05.mma kind::f16, bf16 hi/lo split (3 MMAs), fp32 accumulate in TMEM */
 #define ZK_GEMM_BF16X1 3  /* single bf16 MMA: fast, does NOT meet the 1e-5 parity bar */
 
+/* activation between the linear layers of a conditioner (zuko/nn.py:264-265: `activation()` modules);
+ * torch defaults of each: ELU(alpha=1), GELU(approximate='none'), LeakyReLU(0.01), Softplus(beta=1,
+ * threshold=20).  0 keeps the reference's default (ReLU). */
+#define ZK_ACT_RELU 0
+#define ZK_ACT_ELU 2
+#define ZK_ACT_TANH 3
+#define ZK_ACT_SILU 4
+#define ZK_ACT_GELU 5
+#define ZK_ACT_LEAKY_RELU 6
+#define ZK_ACT_SOFTPLUS 7
+#define ZK_ACT_SIGMOID 8
+
 int zk_version(void);
 const char* zk_last_error(void);
 /* sm count / compute capability of the current device; ZK_ECUDA if none. */
@@ -127,7 +139,7 @@ zk_status zk_diag_normal_log_prob(const float* z, int64_t ldz, const float* loc,
 
 /* ------------------------------------------------------------------------- *
  * Conditioner: MaskedMLP (zuko/nn.py:221-318) or MLP (zuko/nn.py:122-192) with
- * ReLU between layers and none after the last.  Creation applies `mask * W`
+ * an element-wise activation (ReLU by default, ZK_ACT_*) between layers and none after the last.  Creation applies `mask * W`
  * ONCE (the reference redoes it on every call, nn.py:217-218) and packs the
  * weights for the selected GEMM path.
  * ------------------------------------------------------------------------- */
@@ -140,6 +152,7 @@ typedef struct {
     const float* const* bias;    /* host array of DEVICE ptrs, (dims[i+1]); entries may be NULL */
     const uint8_t* const* mask;  /* host array of DEVICE ptrs (bool bytes), or NULL / NULL entries = dense */
     int gemm_mode;               /* ZK_GEMM_* */
+    int activation;              /* ZK_ACT_* between the linear layers (0 = ReLU) */
 } zk_mlp_desc;
 
 zk_status zk_mlp_create(const zk_mlp_desc* desc, zk_mlp** out);

@@ -282,23 +282,54 @@ def diag_normal_log_prob(z, loc, scale, ladj=None, dtype=np.float64):
 # --------------------------------------------------------------------------- #
 
 
+def _sigmoid(v):
+    return 1.0 / (1.0 + np.exp(-v))
+
+
+def _erf(v):
+    from scipy.special import erf
+
+    return erf(v)
+
+
+# torch defaults of the activation modules the reference may put between the linear layers
+# (zuko/nn.py:160-192, 258-318: `activation()`); name -> (f, df/dv at the pre-activation v)
+ACTIVATIONS = {
+    "ReLU": (lambda v: np.maximum(v, 0), lambda v: (v > 0).astype(v.dtype)),
+    "ELU": (lambda v: np.where(v > 0, v, np.expm1(np.minimum(v, 0))), lambda v: np.where(v > 0, 1.0, np.exp(np.minimum(v, 0))).astype(v.dtype)),
+    "Tanh": (np.tanh, lambda v: 1 - np.tanh(v) ** 2),
+    "SiLU": (lambda v: v * _sigmoid(v), lambda v: _sigmoid(v) * (1 + v * (1 - _sigmoid(v)))),
+    "GELU": (lambda v: (0.5 * v * (1 + _erf(v / np.sqrt(2.0)))).astype(v.dtype),
+             lambda v: (0.5 * (1 + _erf(v / np.sqrt(2.0))) + v * np.exp(-0.5 * v * v) / np.sqrt(2 * np.pi)).astype(v.dtype)),
+    "LeakyReLU": (lambda v: np.where(v > 0, v, 0.01 * v).astype(v.dtype), lambda v: np.where(v > 0, 1.0, 0.01).astype(v.dtype)),
+    "Softplus": (lambda v: np.where(v > 20, v, np.log1p(np.exp(np.minimum(v, 20)))).astype(v.dtype),
+                 lambda v: np.where(v > 20, 1.0, _sigmoid(np.minimum(v, 20))).astype(v.dtype)),
+    "Sigmoid": (_sigmoid, lambda v: _sigmoid(v) * (1 - _sigmoid(v))),
+}  # fmt: skip
+
+
 @dataclass
 class Conditioner:
     """Weights of a MaskedMLP (nn.py:221-318) or MLP (nn.py:122-192), as numpy.
-    ``masks[i]`` is None for dense layers."""
+    ``masks[i]`` is None for dense layers; ``activation`` names the module between the layers."""
 
     weights: list
     biases: list
     masks: list
+    activation: str = "ReLU"
 
     def __call__(self, x, c, dtype) -> np.ndarray:
         h = None
         n = len(self.weights)
+        relu = self.activation == "ReLU"
         for i, (W, b, m) in enumerate(zip(self.weights, self.biases, self.masks, strict=True)):
+            hidden = i < n - 1
             if i == 0:
-                h = linear(x, c, W, m, b, relu=(n > 1), dtype=dtype)
+                h = linear(x, c, W, m, b, relu=(hidden and relu), dtype=dtype)
             else:
-                h = linear(h, None, W, m, b, relu=(i < n - 1), dtype=dtype)
+                h = linear(h, None, W, m, b, relu=(hidden and relu), dtype=dtype)
+            if hidden and not relu:
+                h = np.ascontiguousarray(ACTIVATIONS[self.activation][0](h), dtype=dtype)
         return h
 
 
@@ -474,6 +505,7 @@ def _np(t):
 
 def conditioner_from_module(hyper) -> Conditioner:
     Ws, bs, ms = [], [], []
+    act = "ReLU"
     for m in hyper:
         if hasattr(m, "weight"):
             Ws.append(_np(m.weight).astype(np.float64))
@@ -481,9 +513,10 @@ def conditioner_from_module(hyper) -> Conditioner:
             ms.append(_np(m.mask).astype(bool) if hasattr(m, "mask") else None)
         else:
             name = type(m).__name__
-            if name != "ReLU":
+            if name not in ACTIVATIONS:
                 raise NotImplementedError(f"oracle: activation {name}")
-    return Conditioner(Ws, bs, ms)
+            act = name
+    return Conditioner(Ws, bs, ms, act)
 
 
 def _univariate_info(t):

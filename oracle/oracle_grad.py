@@ -196,20 +196,23 @@ def conditioner_backward(cond: O.Conditioner, inp, gout):
     inp (B, in), gout (B, out).  Returns (ginp, CondGrads) — weight gradients are w.r.t. the
     RAW weights, i.e. already multiplied by the mask."""
     n = len(cond.weights)
+    act, dact = O.ACTIVATIONS[cond.activation]
     acts = [np.asarray(inp, F)]
+    pres = []
     for i in range(n):
         W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
         hcur = acts[-1] @ W.T
         if cond.biases[i] is not None:
             hcur = hcur + cond.biases[i]
+        pres.append(hcur)
         if i < n - 1:
-            hcur = np.maximum(hcur, 0.0)
+            hcur = act(hcur)
         acts.append(hcur)
     g = np.asarray(gout, F)
     out = CondGrads([None] * n, [None] * n)
     for i in reversed(range(n)):
         if i < n - 1:
-            g = g * (acts[i + 1] > 0)
+            g = g * dact(pres[i])
         mk = 1.0 if cond.masks[i] is None else cond.masks[i]
         out.weights[i] = (g.T @ acts[i]) * mk
         out.biases[i] = None if cond.biases[i] is None else g.sum(0)
@@ -220,13 +223,14 @@ def conditioner_backward(cond: O.Conditioner, inp, gout):
 def _cond_forward(cond: O.Conditioner, inp):
     h = np.asarray(inp, F)
     n = len(cond.weights)
+    act = O.ACTIVATIONS[cond.activation][0]
     for i in range(n):
         W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
         h = h @ W.T
         if cond.biases[i] is not None:
             h = h + cond.biases[i]
         if i < n - 1:
-            h = np.maximum(h, 0.0)
+            h = act(h)
     return h
 
 

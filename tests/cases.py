@@ -32,7 +32,16 @@ FLOW_CASES = {
     "nsf1_elementwise": (0, lambda: NSF(1, 3, hidden_features=[16])),
     "nsf6_stress": (0, lambda: NSF(6, 3, transforms=3, hidden_features=[64, 64])),
     "ncsf34": (0, lambda: NCSF(3, 4, hidden_features=[32, 32])),
+    # non-ReLU activations (tests/golden/make_golden_act.py)
+    "act_maf_elu": (0, lambda: MAF(5, 2, transforms=2, hidden_features=[32, 32], activation=torch.nn.ELU)),
+    "act_nsf_tanh": (0, lambda: NSF(4, 0, transforms=2, hidden_features=[64, 64], activation=torch.nn.Tanh)),
+    "act_nsf_silu": (0, lambda: NSF(3, 2, transforms=2, hidden_features=[32], activation=torch.nn.SiLU)),
+    "act_maf_gelu": (0, lambda: MAF(4, 0, transforms=2, hidden_features=[64, 64], activation=torch.nn.GELU)),
+    "act_nice_lrelu": (0, lambda: NICE(4, 2, hidden_features=[32], activation=torch.nn.LeakyReLU)),
+    "act_maf_softplus": (0, lambda: MAF(3, 0, transforms=2, hidden_features=[16], activation=torch.nn.Softplus)),
+    "act_maf_sigmoid": (0, lambda: MAF(3, 1, transforms=2, hidden_features=[16, 16], activation=torch.nn.Sigmoid)),
 }
+ACT_CASES = [k for k in FLOW_CASES if k.startswith("act_")]
 SMALL_CASES = [k for k in FLOW_CASES if not k.startswith(("cfg2", "cfg3", "cfg4", "cfg5"))]
 BIG_CASES = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
 
@@ -137,7 +146,7 @@ def assert_log_prob_parity(ours, g: dict, rtol: float = 1e-5):
 # --------------------------------------------------------------------------- #
 
 GRAD_CASES_FULL = ["cfg1_maf", "nsf35_row", "maf35_batch", "nice35", "nsf5_passes2", "maf5_randperm",
-                   "nsf1_elementwise", "nsf6_stress", "composed", "composed_uncond", "ncsf34"]  # fmt: skip
+                   "nsf1_elementwise", "nsf6_stress", "composed", "composed_uncond", "ncsf34", *ACT_CASES]  # fmt: skip
 GRAD_CASES_SAMPLED = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
 GRAD_SAMPLE = 2048
 
@@ -262,8 +271,9 @@ def relu_kink_rows(spec, x, c, tau: float = 1e-5, tau_knot: float = 5e-5) -> np.
                 if i == n - 1:
                     phi = pre
                     break
-                bad |= (np.abs(pre) < tau * (np.abs(h) @ np.abs(W).T + np.abs(bias))).any(-1)
-                h = np.maximum(pre, 0.0)
+                if cond.activation in ("ReLU", "LeakyReLU"):  # the only supported activations with a kink
+                    bad |= (np.abs(pre) < tau * (np.abs(h) @ np.abs(W).T + np.abs(bias))).any(-1)
+                h = O_act(cond.activation)(pre)
         elif layer.kind == "elementwise":
             phi = np.broadcast_to(np.asarray(layer.phi, np.float64), (B, *np.asarray(layer.phi).shape))
         if phi is not None and layer.univariate in ("rqs", "crqs"):
@@ -278,6 +288,12 @@ def relu_kink_rows(spec, x, c, tau: float = 1e-5, tau_knot: float = 5e-5) -> np.
             bad |= (np.abs(zt[..., None] - X).min(-1) < tau_knot).any(-1)
         z, _ = layer.forward(z, c, np.float64)
     return bad
+
+
+def O_act(name):
+    from oracle import oracle as O
+
+    return O.ACTIVATIONS[name][0]
 
 
 def O_rqs_knots(phi, bins, bound, slope):

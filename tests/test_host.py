@@ -115,7 +115,7 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         MaskedMLP(torch.ones(4, 3, dtype=torch.bool), residual=True)
     with pytest.raises(NotImplementedError):
-        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), activation=torch.nn.ELU)
+        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), activation=torch.nn.PReLU)
     with pytest.raises(NotImplementedError):
         MaskedAutoregressiveTransform(3, univariate=torch.distributions.ExpTransform, shapes=[])
 

@@ -32,6 +32,8 @@ ZK_BASE_DIAG_NORMAL, ZK_BASE_BOX_UNIFORM = 0, 1
     ZK_LAYER_ROTATION,
 ) = range(1, 7)
 ZK_GEMM_AUTO, ZK_GEMM_FP32, ZK_GEMM_BF16X3, ZK_GEMM_BF16X1 = range(4)
+(ZK_ACT_RELU, ZK_ACT_ELU, ZK_ACT_TANH, ZK_ACT_SILU, ZK_ACT_GELU, ZK_ACT_LEAKY_RELU, ZK_ACT_SOFTPLUS,
+ ZK_ACT_SIGMOID) = (0, 2, 3, 4, 5, 6, 7, 8)  # fmt: skip
 GEMM_MODES = {"auto": ZK_GEMM_AUTO, "fp32": ZK_GEMM_FP32, "bf16x3": ZK_GEMM_BF16X3, "bf16x1": ZK_GEMM_BF16X1}
 
 
@@ -47,6 +49,7 @@ class MlpDesc(ctypes.Structure):
         ("bias", POINTER(c_void_p)),
         ("mask", POINTER(c_void_p)),
         ("gemm_mode", c_int),
+        ("activation", c_int),
     ]
 
 

@@ -73,21 +73,31 @@ def _conditioner_kwargs(hyper: nn.Module) -> tuple[dict, list]:
     """Recovers ``hidden_features`` from a reference ``MLP`` / ``MaskedMLP`` (an ``nn.Sequential``
     of linear layers and activations, zuko/nn.py:160-192, 295-318) and rejects the options the
     engine does not implement."""
+    from .nn import activation_code
+
     linears = []
+    activation = None
     for m in hyper:
         if hasattr(m, "weight") and isinstance(getattr(m, "weight", None), torch.Tensor):
             if m.weight.dim() != 2:
                 raise _unsupported("a stacked / non-matrix linear layer in the conditioner")
             linears.append(m)
-        elif isinstance(m, nn.ReLU):
-            continue
         elif type(m).__name__ in ("MaskedResidual", "Residual") or any(True for _ in m.children()):
             raise _unsupported("a residual conditioner block (zuko/nn.py:297-309)")
         else:
-            raise _unsupported(f"conditioner module {type(m).__name__} (ReLU MLPs only)")
+            try:
+                activation_code(m)
+            except NotImplementedError as e:
+                raise _unsupported(f"conditioner module {type(m).__name__} ({e})") from None
+            if activation is not None and activation is not type(m):
+                raise _unsupported("a conditioner mixing different activations")
+            activation = type(m)
     if not linears:
         raise _unsupported("a conditioner without linear layers")
-    return dict(hidden_features=[m.weight.shape[0] for m in linears[:-1]]), linears
+    kwargs = dict(hidden_features=[m.weight.shape[0] for m in linears[:-1]])
+    if activation is not None and activation is not nn.ReLU:
+        kwargs["activation"] = activation
+    return kwargs, linears
 
 
 def _convert(m: nn.Module, passthrough: bool = True) -> nn.Module:

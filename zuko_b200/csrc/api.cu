@@ -159,11 +159,13 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
     ZK_REQUIRE(d->dims && d->weight, "mlp_create: null dims/weight");
     ZK_REQUIRE(d->gemm_mode >= ZK_GEMM_AUTO && d->gemm_mode <= ZK_GEMM_BF16X1,
                "mlp_create: unknown gemm_mode %d", d->gemm_mode);
+    ZK_REQUIRE(d->activation >= 0 && d->activation <= ZK_ACT_SIGMOID, "mlp_create: unknown activation %d", d->activation);
     int cnt = 0;
     ZK_CUDA(cudaGetDeviceCount(&cnt));
     zk_mlp* m = new (std::nothrow) zk_mlp();
     if (!m) return fail(ZK_ENOMEM, "mlp_create: out of host memory");
     m->n_linear = d->n_linear;
+    m->act = (d->activation <= 1) ? 1 : d->activation;
     m->dims.assign(d->dims, d->dims + d->n_linear + 1);
     zk_status st = ZK_OK;
     for (int i = 0; i <= d->n_linear && st == ZK_OK; ++i)
@@ -244,11 +246,11 @@ zk_status zk_mlp_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, c
         const int64_t ldd = last ? ldo : m->dims[i + 1];
         if (i == 0) {
             ZK_TRY(launch_linear_fp32(x, ldx, dx, c, ldc, m->dims[0], m->w[0], m->b[0], B, m->dims[1],
-                                      !last, dst, ldd, st));
+                                      last ? 0 : m->act, dst, ldd, st));
         } else {
             const float* src = h[(i - 1) & 1];
             ZK_TRY(launch_linear_fp32(src, m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i],
-                                      m->b[i], B, m->dims[i + 1], !last, dst, ldd, st));
+                                      m->b[i], B, m->dims[i + 1], last ? 0 : m->act, dst, ldd, st));
         }
     }
     return ZK_OK;

@@ -42,13 +42,14 @@ zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
         m->wt.push_back(t);
         ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], t, st));
     }
-    if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr) ZK_TRY(tc_pack_backward(m, st));
+    if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1) ZK_TRY(tc_pack_backward(m, st));
     ZK_CUDA(cudaStreamSynchronize(st));
     return ZK_OK;
 }
 
 struct MlpBwdBufs {
     std::vector<float*> acts;  // acts[i]: input of linear layer i, (B, dims[i])
+    std::vector<float*> pre;   // pre[i]: pre-activation of hidden layer i + 1 (non-ReLU activations only)
     float* out = nullptr;      // (B, dims[n]): conditioner output, later its gradient
     float* gbuf[2] = {nullptr, nullptr};
     float* gin = nullptr;      // (B, dims[0])
@@ -65,6 +66,8 @@ size_t mlp_bwd_scratch(const zk_mlp* m) {
 size_t mlp_bwd_ws(const zk_mlp* m, int64_t B) {
     size_t s = 0;
     for (int i = 0; i <= m->n_linear; ++i) s += a256((size_t)B * m->dims[i] * 4);  // acts + out
+    if (m->act != 1)
+        for (int i = 1; i < m->n_linear; ++i) s += a256((size_t)B * m->dims[i] * 4);  // pre-activations
     if (m->n_linear > 1) s += 2 * a256((size_t)B * m->max_hidden * 4);
     s += a256((size_t)B * m->dims[0] * 4);  // gin
     return s + mlp_bwd_scratch(m);
@@ -73,6 +76,9 @@ size_t mlp_bwd_ws(const zk_mlp* m, int64_t B) {
 bool mlp_bwd_carve(const zk_mlp* m, int64_t B, Arena& ar, MlpBwdBufs& b) {
     b.acts.resize(m->n_linear);
     for (int i = 0; i < m->n_linear; ++i) b.acts[i] = ar.take<float>((size_t)B * m->dims[i]);
+    b.pre.assign(m->n_linear, nullptr);
+    if (m->act != 1)
+        for (int i = 1; i < m->n_linear; ++i) b.pre[i] = ar.take<float>((size_t)B * m->dims[i]);
     b.out = ar.take<float>((size_t)B * m->dims[m->n_linear]);
     if (m->n_linear > 1) {
         b.gbuf[0] = ar.take<float>((size_t)B * m->max_hidden);
@@ -87,9 +93,16 @@ bool mlp_bwd_carve(const zk_mlp* m, int64_t B, Arena& ar, MlpBwdBufs& b) {
 zk_status mlp_forward_save(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, cudaStream_t st) {
     const int n = m->n_linear;
     for (int i = 0; i < n; ++i) {
-        float* dst = (i < n - 1) ? b.acts[i + 1] : b.out;
+        const bool hidden = (i < n - 1);
+        if (hidden && m->act != 1) {  // general activation: keep the pre-activation for act'
+            ZK_TRY(launch_linear_fp32(b.acts[i], m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i], m->b[i],
+                                      B, m->dims[i + 1], 0, b.pre[i + 1], m->dims[i + 1], st));
+            ZK_TRY(launch_act_apply(b.pre[i + 1], b.acts[i + 1], B * (int64_t)m->dims[i + 1], m->act, st));
+            continue;
+        }
+        float* dst = hidden ? b.acts[i + 1] : b.out;
         ZK_TRY(launch_linear_fp32(b.acts[i], m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i], m->b[i],
-                                  B, m->dims[i + 1], i < n - 1, dst, m->dims[i + 1], st));
+                                  B, m->dims[i + 1], hidden ? 1 : 0, dst, m->dims[i + 1], st));
     }
     return ZK_OK;
 }
@@ -109,7 +122,10 @@ zk_status mlp_backward(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, bool wan
             float* dst = (i == 0) ? b.gin : b.gbuf[i & 1];
             // g (B, N) x W (N, K) = "linear" with the transposed weights (K, N)
             ZK_TRY(launch_linear_fp32(g, N, N, nullptr, 0, N, m->wt[i], nullptr, B, K, false, dst, K, st));
-            if (i > 0) ZK_TRY(launch_relu_gate(dst, b.acts[i], B * (int64_t)K, st));
+            if (i > 0) {
+                if (m->act == 1) ZK_TRY(launch_relu_gate(dst, b.acts[i], B * (int64_t)K, st));
+                else ZK_TRY(launch_act_gate(dst, b.pre[i], B * (int64_t)K, m->act, st));
+            }
             g = dst;
         }
     }
@@ -154,7 +170,9 @@ TcBwdPlan tc_plan(const zk_mlp* m, int64_t B) {
     return p;
 }
 
-bool mlp_uses_tc(const zk_mlp* m) { return m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr; }
+bool mlp_uses_tc(const zk_mlp* m) {  // the tensor-core backward gates with ReLU in the GEMM epilogue
+    return m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1;
+}
 
 size_t tc_bwd_ws(const zk_mlp* m, int64_t B) {
     const TcBwdPlan p = tc_plan(m, B);

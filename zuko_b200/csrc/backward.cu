@@ -6,6 +6,7 @@
 
 #include <algorithm>
 
+#include "activations.cuh"
 #include "backward.cuh"
 #include "bijector_grad.cuh"
 
@@ -151,6 +152,15 @@ __global__ void input_grad_kernel(const float* gin, int nx, int nc, const int* c
 __global__ void relu_gate_kernel(float* g, const float* a, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && !(a[i] > 0.f)) g[i] = 0.f;
+}
+
+__global__ void act_apply_kernel(const float* pre, float* y, int64_t n, int act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = act_apply(pre[i], act);
+}
+__global__ void act_gate_kernel(float* g, const float* pre, int64_t n, int act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] *= act_deriv(pre[i], act);
 }
 
 __global__ void add_kernel(float* y, const float* x, int64_t n) {
@@ -376,6 +386,17 @@ zk_status launch_relu_gate(float* g, const float* a, int64_t n, cudaStream_t st)
     if (n == 0) return ZK_OK;
     relu_gate_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, a, n);
     return check_launch("relu_gate_kernel");
+}
+
+zk_status launch_act_apply(const float* pre, float* y, int64_t n, int act, cudaStream_t st) {
+    if (n == 0) return ZK_OK;
+    act_apply_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(pre, y, n, act);
+    return check_launch("act_apply_kernel");
+}
+zk_status launch_act_gate(float* g, const float* pre, int64_t n, int act, cudaStream_t st) {
+    if (n == 0) return ZK_OK;
+    act_gate_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, pre, n, act);
+    return check_launch("act_gate_kernel");
 }
 
 zk_status launch_add(float* y, const float* x, int64_t n, cudaStream_t st) {

@@ -65,6 +65,10 @@ zk_status launch_input_grad(const float* gin, int nx, int nc, const int* cols, i
 // g[i] = a[i] > 0 ? g[i] : 0   (ReLU gate, n elements)
 zk_status launch_relu_gate(float* g, const float* a, int64_t n, cudaStream_t stream);
 
+// general activation (activations.cuh): y[i] = act(pre[i]);  g[i] *= act'(pre[i])
+zk_status launch_act_apply(const float* pre, float* y, int64_t n, int act, cudaStream_t stream);
+zk_status launch_act_gate(float* g, const float* pre, int64_t n, int act, cudaStream_t stream);
+
 // out[n] += sum_b v[b, n]  (fixed-order two-stage); scratch >= colsum_scratch_bytes(N)
 size_t colsum_scratch_bytes(int N);
 zk_status launch_colsum_add(const float* v, int64_t ldv, int64_t B, int N, float* out, void* scratch,

@@ -6,6 +6,7 @@
 // the production path for the large conditioners.  Restates zuko/nn.py:217-218 with the
 // mask multiplication hoisted to pack time.
 
+#include "activations.cuh"
 #include "mlp.cuh"
 
 namespace zk {
@@ -75,7 +76,7 @@ linear_fp32_kernel(const float* __restrict__ a0, int64_t lda0, int k0, const flo
             const int n = n0 + tx * TN + j;
             if (n >= N) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
-            if (relu) v = fmaxf(v, 0.f);
+            if (relu) v = act_apply(v, relu);  // 1 = ReLU, >= 2 = ZK_ACT_*
             C[m * ldc + n] = v;
         }
     }
@@ -89,7 +90,7 @@ __global__ void apply_mask_kernel(const float* W, const uint8_t* mask, int64_t n
 }  // namespace
 
 zk_status launch_linear_fp32(const float* a0, int64_t lda0, int k0, const float* a1, int64_t lda1,
-                             int K, const float* W, const float* bias, int64_t M, int N, bool relu,
+                             int K, const float* W, const float* bias, int64_t M, int N, int act,
                              float* C, int64_t ldc, cudaStream_t stream) {
     ZK_REQUIRE(M >= 0 && N > 0 && K > 0 && k0 >= 0 && k0 <= K, "linear: bad shape");
     ZK_REQUIRE(a0 != nullptr || k0 == 0, "linear: null A");
@@ -99,7 +100,7 @@ zk_status launch_linear_fp32(const float* a0, int64_t lda0, int k0, const float*
     ZK_REQUIRE(gx <= 0x7fffffff, "linear: batch too large");
     dim3 grid((unsigned)gx, (unsigned)ceil_div(N, BN));
     linear_fp32_kernel<<<grid, kThreads, 0, stream>>>(a0, lda0, k0, a1, lda1, K, W, bias, M, N,
-                                                       relu ? 1 : 0, C, ldc);
+                                                       act, C, ldc);
     return check_launch("linear_fp32_kernel");
 }
 

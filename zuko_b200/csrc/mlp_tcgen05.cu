@@ -24,6 +24,7 @@
 // (64 x rows) bf16 lands in shared memory as rows of 128 bytes with the 128B swizzle, which is
 // the canonical K-major SWIZZLE_128B UMMA operand layout (8-row groups 1024 B apart).
 
+#include "activations.cuh"
 #include "mlp_tcgen05.cuh"
 #include "tc_common.cuh"
 
@@ -194,7 +195,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c0 + j;
                     float f = __uint_as_float(r[j]) + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
-                    if (p.relu) f = fmaxf(f, 0.f);
+                    if (p.relu == 1) f = fmaxf(f, 0.f);
+                    else if (p.relu > 1) f = act_apply(f, p.relu);
                     v[j] = (n < p.N) ? f : 0.f;  // padded columns feed the next layer as exact zeros
                 }
                 if (!row_ok) continue;
@@ -440,7 +442,7 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
         p.M = (int)B; p.N = L.N; p.Kp = L.Kp;
         p.n_chunks = (L.N + BN - 1) / BN;
         p.n_terms = pk->n_terms;
-        p.relu = last ? 0 : 1;
+        p.relu = last ? 0 : m->act;
         p.bias = m->b[i];
         p.out_f32 = last ? out : nullptr;
         p.ldo = ldo;

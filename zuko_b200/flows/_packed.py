@@ -82,6 +82,7 @@ class PackedLayerMixin:
         hyper = getattr(self, "hyper", None)
         if hyper is not None:
             ts.append(hyper.gemm_mode)
+            ts.append(hyper._activation_code())
             for m in hyper._linears():
                 ts += [m.weight, m.bias, getattr(m, "mask", None)]
         for p in getattr(self, "phi", []) or []:

@@ -57,13 +57,41 @@ class MaskedLinear(nn.Linear):
         self.register_buffer("mask", adjacency)
 
 
-def _relu_only(activation: Callable[[], nn.Module] | None) -> type:
-    if activation is None or activation is nn.ReLU:
+# activation modules the engine implements (with torch's default arguments) -> ZK_ACT_* code
+_ACTIVATION_CODES = {
+    "ReLU": (E.ZK_ACT_RELU, {}),
+    "ELU": (E.ZK_ACT_ELU, {"alpha": 1.0}),
+    "Tanh": (E.ZK_ACT_TANH, {}),
+    "SiLU": (E.ZK_ACT_SILU, {}),
+    "GELU": (E.ZK_ACT_GELU, {"approximate": "none"}),
+    "LeakyReLU": (E.ZK_ACT_LEAKY_RELU, {"negative_slope": 0.01}),
+    "Softplus": (E.ZK_ACT_SOFTPLUS, {"beta": 1.0, "threshold": 20.0}),
+    "Sigmoid": (E.ZK_ACT_SIGMOID, {}),
+}
+
+
+def activation_code(module: nn.Module) -> int:
+    """ZK_ACT_* of an activation module instance; raises for modules / arguments the engine does not
+    implement (the reference accepts any constructor, zuko/nn.py:264-265)."""
+    name = type(module).__name__
+    if name not in _ACTIVATION_CODES or any(True for _ in module.children()):
+        raise NotImplementedError(
+            f"zuko_b200: activation {name} is not implemented by the engine "
+            f"(supported with their default arguments: {', '.join(_ACTIVATION_CODES)})"
+        )
+    code, defaults = _ACTIVATION_CODES[name]
+    for k, v in defaults.items():
+        if getattr(module, k, v) != v:
+            raise NotImplementedError(f"zuko_b200: {name}({k}={getattr(module, k)!r}) is not implemented (engine: {k}={v!r})")
+    return code
+
+
+def _relu_only(activation: Callable[[], nn.Module] | None) -> Callable[[], nn.Module]:
+    """Validates the ``activation=`` constructor hook (name kept for history: ReLU is the default)."""
+    if activation is None:
         return nn.ReLU
-    raise NotImplementedError(
-        f"zuko_b200: activation {activation!r} is not implemented by the engine (ReLU only); "
-        "the reference supports arbitrary activations (zuko/nn.py:264-265)"
-    )
+    activation_code(activation())  # raises NotImplementedError for unsupported modules
+    return activation
 
 
 class _EngineMLP(nn.Sequential):
@@ -76,8 +104,15 @@ class _EngineMLP(nn.Sequential):
     def _linears(self) -> list[nn.Module]:
         return [m for m in self if hasattr(m, "weight")]
 
+    def _activation_code(self) -> int:
+        acts = [m for m in self if not hasattr(m, "weight")]
+        codes = {activation_code(m) for m in acts}
+        if len(codes) > 1:
+            raise NotImplementedError("zuko_b200: a conditioner mixing different activations is not implemented")
+        return codes.pop() if codes else E.ZK_ACT_RELU
+
     def _signature(self) -> tuple:
-        sig = [self.gemm_mode]
+        sig = [self.gemm_mode, self._activation_code()]
         for m in self._linears():
             for t in (m.weight, m.bias, getattr(m, "mask", None)):
                 sig.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
@@ -106,7 +141,7 @@ class _EngineMLP(nn.Sequential):
                 mk = mask.detach().to(torch.uint8).contiguous()
                 keep.append(mk)
                 M[i] = mk.data_ptr()
-        desc = E.MlpDesc(n, dims, W, Bv, M, E.GEMM_MODES[self.gemm_mode])
+        desc = E.MlpDesc(n, dims, W, Bv, M, E.GEMM_MODES[self.gemm_mode], self._activation_code())
         keep += [dims, W, Bv, M]
         return desc, keep
 
@@ -160,8 +195,9 @@ class _EngineMLP(nn.Sequential):
 
 
 class MLP(_EngineMLP):
-    """Dense multi-layer perceptron ``in -> hidden... -> out`` with ReLU between layers
-    (zuko/nn.py:122-192; ``normalize`` / custom activations are not implemented)."""
+    """Dense multi-layer perceptron ``in -> hidden... -> out`` with an element-wise activation between
+    layers (zuko/nn.py:122-192; ReLU by default, see ``_ACTIVATION_CODES``; ``normalize`` is not
+    implemented)."""
 
     def __init__(
         self,
@@ -217,8 +253,8 @@ def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> l
 
 class MaskedMLP(_EngineMLP):
     """Masked multi-layer perceptron whose Jacobian ``dy_i/dx_j`` is null wherever
-    ``adjacency[i, j]`` is False (zuko/nn.py:221-318).  ``residual=True`` and non-ReLU
-    activations are not implemented by the engine."""
+    ``adjacency[i, j]`` is False (zuko/nn.py:221-318).  ``residual=True`` is not implemented by the
+    engine; activations: see ``_ACTIVATION_CODES``."""
 
     def __init__(
         self,
