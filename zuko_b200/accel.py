@@ -13,7 +13,7 @@ original are seen by the accelerated flow, whose packed weights are re-built whe
 The reference package is never imported: modules are recognised by class name and by the
 attributes their constructors set (file:line cited per converter), so the same code accepts
 ``zuko_b200``'s own modules.  Options the engine does not implement (residual conditioners,
-non-ReLU activations, other univariate bijectors, other bases) raise ``NotImplementedError``
+activation modules outside ZK_ACT_*, other univariate bijectors, other bases) raise ``NotImplementedError``
 here, at ``accelerate()`` time — never a silent eager fallback.
 """
 
