@@ -336,3 +336,128 @@ def flow_backward(spec: O.FlowSpec, x, c=None, g_log_prob=None, g_z=None, g_ladj
     if gc is not None and c is not None and np.asarray(c).ndim == 1:
         gc = gc.sum(0)
     return g, gc, grads
+
+
+# --------------------------------------------------------------------------- #
+# inverse direction (reparameterised sampling): implicit differentiation
+# --------------------------------------------------------------------------- #
+
+
+def _layer_passes(layer: O.Layer) -> int:
+    """Number of Richardson sweeps that solve J^T v = g exactly: J is triangular in the layer's order
+    classes, so (I - S J^T) is nilpotent with that index (S = 1 / diag J)."""
+    if layer.kind == "autoregressive":
+        return max(int(layer.passes), 1)
+    if layer.kind == "coupling":
+        return 2
+    return 1
+
+
+def layer_inverse_backward(layer: O.Layer, x, c, g):
+    """x = layer^{-1}(y; theta, c) at the solution x.  Given g = dL/dx returns
+    (v = dL/dy, gc, LayerGrads) by the implicit-function theorem applied to y = f(x; theta, c):
+        dL/dy = J^{-T} g,   dL/dtheta = -(df/dtheta)^T v,   dL/dc = -(df/dc)^T v,   J = df/dx.
+    (torch.autograd reaches the same numbers by back-propagating through the `passes` sweeps of
+    transforms.py:994-1000.)  J^T v is one call of `layer_backward` with gy = v, gl = 0."""
+    x = np.asarray(x, F)
+    g = np.asarray(g, F)
+    B, D = x.shape
+    zero = np.zeros(B, F)
+    if layer.kind == "permutation":
+        v = g[:, np.asarray(layer.order)]  # J = P (orthogonal): J^{-T} g = P g
+    elif layer.kind == "rotation":
+        v = g @ np.asarray(layer.R, F).T  # J = R (orthogonal): J^{-T} g = R g
+    else:
+        s, _, _ = layer_backward(layer, x, c, np.ones_like(x), zero)  # placeholder, corrected below
+        # diag J: direct derivative dy_d/dx_d = J^T 1 minus the conditioner paths; obtain it from the
+        # univariate backward alone
+        s = _layer_diag(layer, x, c)
+        v = g / s
+        for _ in range(_layer_passes(layer) - 1):
+            jtv, _, _ = layer_backward(layer, x, c, v, zero)
+            v = v + (g - jtv) / s
+    _, gc, lg = layer_backward(layer, x, c, -v, zero)
+    return v, gc, lg
+
+
+def _layer_diag(layer: O.Layer, x, c):
+    """diag(df/dx): the derivative of the univariate bijector at fixed parameters."""
+    B, D = x.shape
+    ones, zero = np.ones_like(x), np.zeros_like(x)
+    cc = _ctx_rows(c, B)
+    P = 3 * layer.bins - 1 if layer.univariate in ("rqs", "crqs") else 2
+    if layer.kind == "autoregressive":
+        inp = x if cc is None else np.concatenate([x, cc], -1)
+        phi = _cond_forward(layer.hyper, inp).reshape(B, D, P)
+        s, _ = _uni_backward(layer, x, phi, ones, np.zeros(B, F))
+        return s
+    if layer.kind == "coupling":
+        ia, ib = np.nonzero(layer.mask)[0], np.nonzero(~layer.mask)[0]
+        inp = x[:, ia] if cc is None else np.concatenate([x[:, ia], cc], -1)
+        phi = _cond_forward(layer.hyper, inp).reshape(B, len(ib), P)
+        sb, _ = _uni_backward(layer, x[:, ib], phi, ones[:, ib], np.zeros(B, F))
+        s = np.ones_like(x)
+        s[:, ib] = sb
+        return s
+    if layer.kind == "elementwise":
+        phi = np.asarray(layer.phi, F) if layer.hyper is None else _cond_forward(layer.hyper, cc).reshape(B, D, P)
+        s, _ = _uni_backward(layer, x, phi, ones, np.zeros(B, F))
+        return s
+    if layer.kind == "softclip":
+        return softclip_backward(x, ones, zero, layer.bound)
+    raise ValueError(layer.kind)
+
+
+def flow_inverse_backward(spec: O.FlowSpec, z, c=None, g_x=None, g_log_prob=None):
+    """Reverse mode of ``x = FlowSpec.inverse(z)`` (weights g_x (B, D)) and, with ``g_log_prob``, of the
+    second output of ``FlowSpec.inverse_and_log_prob`` (distributions.py:129-138).
+    Returns (gz, gc or None, [LayerGrads])."""
+    z = np.asarray(z, F)
+    B, D = z.shape
+    x = spec.inverse(z, c, F)
+    xs = [np.asarray(x, F)]  # xs[l] = input of layer l in the forward direction
+    for layer in spec.layers:
+        y, _ = layer.forward(xs[-1], c, F)
+        xs.append(np.asarray(y, F))
+    g = np.zeros((B, D), F) if g_x is None else np.asarray(g_x, F).copy()
+    n = len(spec.layers)
+    grads = [LayerGrads() for _ in range(n)]
+    gc_tot = None
+    gz = np.zeros((B, D), F)
+
+    def add_grads(dst: LayerGrads, src: LayerGrads):
+        if src.hyper is not None:
+            if dst.hyper is None:
+                dst.hyper = CondGrads([np.zeros_like(w) for w in src.hyper.weights],
+                                      [None if b is None else np.zeros_like(b) for b in src.hyper.biases])  # fmt: skip
+            for i in range(len(src.hyper.weights)):
+                dst.hyper.weights[i] += src.hyper.weights[i]
+                if src.hyper.biases[i] is not None:
+                    dst.hyper.biases[i] += src.hyper.biases[i]
+        if src.phi is not None:
+            dst.phi = src.phi if dst.phi is None else dst.phi + src.phi
+        if src.R is not None:
+            dst.R = src.R if dst.R is None else dst.R + src.R
+
+    if g_log_prob is not None:
+        # log p = base.log_prob(z) + sum_l ladj_l(x_l; theta): explicit part at fixed x, and d/dx joins g
+        glp = np.asarray(g_log_prob, F)
+        gx_l, gc_l, lgs = flow_backward(spec, x, c, g_ladj=glp)
+        g = g + gx_l
+        for i in range(n):
+            add_grads(grads[i], lgs[i])
+        if gc_l is not None:
+            gc_tot = gc_l if np.asarray(c).ndim > 1 else gc_l  # flow_backward already sums a broadcast row
+        if spec.base != "uniform":
+            gz = gz + glp[:, None] * (-(z - spec.loc) / spec.scale**2)
+    gc_rows = None
+    for i in range(n):
+        g, gci, lg = layer_inverse_backward(spec.layers[i], xs[i], c, g)
+        add_grads(grads[i], lg)
+        if gci is not None:
+            gc_rows = gci if gc_rows is None else gc_rows + gci
+    if gc_rows is not None:
+        if c is not None and np.asarray(c).ndim == 1:
+            gc_rows = gc_rows.sum(0)
+        gc_tot = gc_rows if gc_tot is None else gc_tot + gc_rows
+    return gz + g, gc_tot, grads

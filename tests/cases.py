@@ -300,3 +300,16 @@ def O_rqs_knots(phi, bins, bound, slope):
     from oracle import oracle as O
 
     return O.rqs_knots(phi, bins, bound, slope)
+
+
+INV_GRAD_CASES = ["cfg1_maf", "nsf35_row", "maf35_batch", "nice35", "nsf5_passes2", "maf5_randperm", "nsf1_elementwise",
+                  "ncsf34", "act_maf_elu", "act_nsf_tanh", "composed", "composed_uncond", "cfg2_nsf"]  # fmt: skip
+
+
+def inv_grad_inputs(name: str):
+    """(golden dict, z, c) of an inverse-direction gradient case (tests/golden/make_golden_inv_grad.py)."""
+    gg = load(f"invgrad_{name}")
+    c = load(f"flow_{name}").get("c")
+    if c is not None and c.ndim == 2:
+        c = c[: int(gg["rows"])]
+    return gg, gg["z"].astype(np.float32), c

@@ -5,7 +5,7 @@ hand-written reverse-mode restatement the GPU backward pass is checked against."
 import numpy as np
 import pytest
 
-from cases import GRAD_CASES_FULL, GRAD_CASES_SAMPLED, assert_param_grads, build_flow, grad_inputs, load, oracle_named_grads
+from cases import INV_GRAD_CASES, inv_grad_inputs, GRAD_CASES_FULL, GRAD_CASES_SAMPLED, assert_param_grads, build_flow, grad_inputs, load, oracle_named_grads
 from oracle import oracle as O
 from oracle import oracle_grad as OG
 
@@ -61,3 +61,19 @@ def test_flow_gradients(name):
     if c is not None:
         np.testing.assert_allclose(gc, gg["tr/gc"], rtol=1e-7, atol=1e-7)
     assert_param_grads(oracle_named_grads(flow, lgs), gg, "tr/", 1e-8, name)
+
+
+@pytest.mark.parametrize("name", INV_GRAD_CASES)
+def test_inverse_direction_gradients(name):
+    """Implicit differentiation of x = transform.inv(z) (and of rsample_and_log_prob's log-density)
+    against torch.autograd back-propagating through the reference's inverse sweeps."""
+    gg, z, c = inv_grad_inputs(name)
+    flow = build_flow(name)
+    spec = O.flowspec_from_module(flow)
+    np.testing.assert_allclose(spec.inverse(gg["z"], c), gg["x64"], rtol=1e-8, atol=1e-8)
+    for prefix, kw in (("inv/", dict(g_x=gg["w"])), ("invlp/", dict(g_x=gg["w"], g_log_prob=gg["wl"]))):
+        gz, gc, lgs = OG.flow_inverse_backward(spec, gg["z"], c, **kw)
+        np.testing.assert_allclose(gz, gg[prefix + "gx"], rtol=1e-7, atol=1e-7)
+        if c is not None:
+            np.testing.assert_allclose(gc, gg[prefix + "gc"], rtol=1e-7, atol=1e-7)
+        assert_param_grads(oracle_named_grads(flow, lgs), gg, prefix, 1e-8, name)
