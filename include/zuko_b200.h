@@ -312,6 +312,24 @@ zk_status zk_flow_backward(const zk_flow_desc* flow, const float* x, int64_t ldx
                            const zk_layer_grads* const* grads, void* workspace,
                            size_t workspace_bytes, zk_stream stream);
 
+/* Reverse mode of zk_flow_inverse (reparameterised sampling, reverse-KL training):
+ *   x = transform.inv(z)                      L = <grad_x, x> [+ <grad_log_prob, log_prob>]
+ * where log_prob is the second output of zk_flow_inverse / NormalizingFlow.rsample_and_log_prob
+ * (distributions.py:129-138).  `x` is the SAMPLE the forward call returned (the engine walks the
+ * forward chain from it); `z` is only read for the base term of grad_log_prob.  Writes grad_z (B, D),
+ * OVERWRITES grad_c and accumulates parameter gradients exactly like zk_flow_backward.  Implicit
+ * differentiation: per layer `passes` sweeps of J^T v = g, each one call of the forward direction's
+ * backward — torch.autograd reaches the same numbers by back-propagating through the inverse sweeps
+ * of transforms.py:994-1000. */
+size_t zk_flow_inverse_backward_workspace_bytes(const zk_flow_desc* flow, int64_t B);
+size_t zk_flow_inverse_backward_min_workspace_bytes(const zk_flow_desc* flow);
+zk_status zk_flow_inverse_backward(const zk_flow_desc* flow, const float* x, int64_t ldx, const float* c,
+                                   int64_t ldc, int64_t B, const float* grad_x, int64_t ldgx,
+                                   const float* grad_log_prob, const float* z, int64_t ldz, float* grad_z,
+                                   int64_t ldgz, float* grad_c, int64_t ldgc,
+                                   const zk_layer_grads* const* grads, void* workspace,
+                                   size_t workspace_bytes, zk_stream stream);
+
 /* 1 (default): the conditioner GEMMs of the backward pass (forward recompute, dgrad, wgrad) of a
  * handle packed for tcgen05 run on the tensor cores (split-bf16, fp32 accumulate); 0: fp32 FMA on
  * CUDA cores (exact-order arbitration path).  Returns the previous value. */

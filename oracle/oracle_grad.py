@@ -368,10 +368,7 @@ def layer_inverse_backward(layer: O.Layer, x, c, g):
     elif layer.kind == "rotation":
         v = g @ np.asarray(layer.R, F).T  # J = R (orthogonal): J^{-T} g = R g
     else:
-        s, _, _ = layer_backward(layer, x, c, np.ones_like(x), zero)  # placeholder, corrected below
-        # diag J: direct derivative dy_d/dx_d = J^T 1 minus the conditioner paths; obtain it from the
-        # univariate backward alone
-        s = _layer_diag(layer, x, c)
+        s = _layer_diag(layer, x, c)  # diag J: derivative of the univariate bijector at fixed parameters
         v = g / s
         for _ in range(_layer_passes(layer) - 1):
             jtv, _, _ = layer_backward(layer, x, c, v, zero)

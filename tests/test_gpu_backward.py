@@ -22,6 +22,8 @@ import pytest
 import torch
 
 from cases import (
+    INV_GRAD_CASES,
+    inv_grad_inputs,
     GRAD_CASES_FULL,
     GRAD_CASES_SAMPLED,
     assert_param_grads,
@@ -319,3 +321,93 @@ def test_accelerated_reference_style_module_gets_grads(device):
     xt, ct = dev_t(x, device), dev_t(c, device)
     (dev_t(w["g"], device) * acc(ct).log_prob(xt)).sum().backward()
     assert_param_grads(named_param_grads(src), gg, "lp/", 5e-5, "accelerate(maf35)", minus=ref["minus"])
+
+
+# --------------------------------------------------------------------------- #
+# inverse direction (rsample / rsample_and_log_prob): zk_flow_inverse_backward
+# --------------------------------------------------------------------------- #
+
+
+def _inverse_grads(flow, z, c, mode, w, wl, device):
+    for p in flow.parameters():
+        p.grad = None
+    zt = dev_t(z, device, grad=True)
+    ct = None if c is None else dev_t(c, device, grad=True)
+    d = flow(ct)
+    if mode == "inv":
+        x = d.transform.inv(zt)
+        loss = (dev_t(w, device) * x).sum()
+    else:  # what NormalizingFlow.rsample_and_log_prob does for its own draw of z (distributions.py:129-138)
+        call, ctx = d._flow_call()
+        x, lp = call.inverse(zt, ctx, with_log_prob=True)
+        loss = (dev_t(w, device) * x).sum() + (dev_t(wl, device) * lp).sum()
+    loss.backward()
+    return cpu(x), cpu(zt.grad), (None if ct is None else cpu(ct.grad)), named_param_grads(flow)
+
+
+INV_BAR = 2e-4  # gradients evaluated at a sample that itself carries ~1e-5 of inverse error
+
+
+@pytest.mark.parametrize("mode", ["inv", "invlp"])
+@pytest.mark.parametrize("name", INV_GRAD_CASES)
+def test_inverse_direction_gradients(device, name, mode):
+    """d/d(z, c, theta) of x = transform.inv(z) (and of the log-density returned next to it) against
+    torch.autograd back-propagating through the reference's inverse sweeps (fp64 goldens)."""
+    gg, z, c = inv_grad_inputs(name)
+    cpu_flow = build_flow(name)
+    spec = O.flowspec_from_module(cpu_flow)
+    flow = build_flow(name).to(device)
+    kink = relu_kink_rows(spec, gg["x64"], c)  # non-smooth rows, judged at the sample
+    w, wl = gg["w"].copy(), gg["wl"].copy()
+    w[kink], wl[kink] = 0.0, 0.0
+    pre = f"{mode}/"
+    ref_gz = gg[pre + "gx"].copy()
+    ref_gz[kink] = 0.0
+    ref_gc = None if c is None else gg[pre + "gc"].copy()
+    minus = None
+    if kink.any():
+        ck = c if (c is None or c.ndim == 1) else c[kink]
+        _, ogc, lgs = OG.flow_inverse_backward(spec, gg["z"][kink], ck, g_x=gg["w"][kink],
+                                               g_log_prob=gg["wl"][kink] if mode == "invlp" else None)  # fmt: skip
+        minus = oracle_named_grads(cpu_flow, lgs)
+        if c is not None:
+            if c.ndim == 1:
+                ref_gc = ref_gc - ogc
+            else:
+                ref_gc[kink] = 0.0
+    x, gz, gc, pg = _inverse_grads(flow, z, c, mode, w, wl, device)
+    close(x, gg["x64"], 1e-4, f"{name} sample")
+    close(gz, ref_gz, INV_BAR, f"{name} d/dz")
+    if c is not None:
+        close(gc, ref_gc, INV_BAR, f"{name} d/dc")
+    assert_param_grads(pg, gg, pre, INV_BAR, name, minus=minus)
+
+
+def test_reverse_kl_step_matches_reference(device):
+    """docs/tutorials/reverse_kl.ipynb:200 — loss = E[log q(x) - log p*(x)], x, log q = flow.rsample_and_log_prob:
+    one gradient through the sampler; compared with the oracle on the same draw."""
+    import zuko_b200 as zuko
+
+    torch.manual_seed(0)
+    flow = zuko.flows.NSF(3, 0, transforms=2, hidden_features=[32, 32]).to(device)
+    cpu_flow = zuko.flows.NSF(3, 0, transforms=2, hidden_features=[32, 32])
+    cpu_flow.load_state_dict({k: v.cpu() for k, v in flow.state_dict().items()})
+    spec = O.flowspec_from_module(cpu_flow)
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(512, 3, generator=gen)
+    kink = relu_kink_rows(spec, spec.inverse(z.numpy().astype(np.float64)), None)
+    wrow = torch.ones(512)
+    wrow[torch.from_numpy(kink)] = 0.0
+    call, ctx = flow()._flow_call()
+    x, lq = call.inverse(z.to(device), ctx, with_log_prob=True)
+    target = -0.5 * ((x - 1.0) ** 2).sum(-1)  # log p* up to a constant: N(1, I)
+    loss = (wrow.to(device) * (lq - target)).mean()
+    loss.backward()
+    # oracle: dL/dx = -w (-(x - 1)) / N = w (x - 1) / N ; dL/dlq = w / N
+    xs = spec.inverse(z.numpy().astype(np.float64))
+    gx = (wrow.numpy()[:, None] * (xs - 1.0)) / 512
+    _, _, lgs = OG.flow_inverse_backward(spec, z.numpy().astype(np.float64), None, g_x=gx, g_log_prob=wrow.numpy() / 512)
+    ref = oracle_named_grads(cpu_flow, lgs)
+    ours = named_param_grads(flow)
+    for k in ref:
+        close(ours[k], ref[k], 5e-4, f"reverse KL d/d{k}")

@@ -141,6 +141,10 @@ _SIGNATURES = {
     "zk_flow_backward_min_workspace_bytes": (c_size_t, [POINTER(FlowDesc)]),
     "zk_flow_backward": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64,
                                  POINTER(POINTER(LayerGrads)), _P, c_size_t, _P]),
+    "zk_flow_inverse_backward_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),
+    "zk_flow_inverse_backward_min_workspace_bytes": (c_size_t, [POINTER(FlowDesc)]),
+    "zk_flow_inverse_backward": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64,
+                                         _P, c_int64, POINTER(POINTER(LayerGrads)), _P, c_size_t, _P]),
     "zk_flow_log_prob_host": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, POINTER(c_double), _P, c_size_t, _P]),
 }  # fmt: skip
 

@@ -112,6 +112,32 @@ class _FlowFunction(torch.autograd.Function):
         return (None, None, None, gx, gc, *pg)
 
 
+class _FlowInverseFunction(torch.autograd.Function):
+    """Autograd seam of the inverse direction (reparameterised sampling): forward =
+    ``zk_flow_inverse`` (optionally with the log-density of the sample), backward = ONE
+    ``zk_flow_inverse_backward`` call (implicit differentiation at the sample)."""
+
+    @staticmethod
+    def forward(ctx, call, with_lp, ldc, z2, c2, *params):  # noqa: ANN001
+        ctx.call, ctx.with_lp, ctx.ldc = call, with_lp, ldc
+        ctx.has_c = c2 is not None
+        out = call._run_inverse(z2, c2, ldc, z2.shape[:-1], with_lp)
+        x = out[0] if with_lp else out
+        ctx.save_for_backward(*([x, z2, c2] if c2 is not None else [x, z2]))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):  # noqa: ANN001
+        saved = ctx.saved_tensors
+        x, z2 = saved[0], saved[1]
+        c2 = saved[2] if ctx.has_c else None
+        need = ctx.needs_input_grad
+        gz, gc, pg = ctx.call._run_inverse_backward(x, z2, c2, ctx.ldc, gouts[0], gouts[1] if ctx.with_lp else None,
+                                                    need[3], need[4], need[5:])  # fmt: skip
+        return (None, None, None, gz, gc, *pg)
+
+
 class FlowCall:
     """A ``zk_flow_desc`` over packed layers + DiagNormal base, ready to be invoked."""
 
@@ -213,17 +239,16 @@ class FlowCall:
 
     def inverse(self, z: Tensor, c: Tensor | None, with_log_prob: bool = False):
         """``transform.inv(z)`` (and the log-density of the result when ``with_log_prob``,
-        zuko/distributions.py:129-138)."""
+        zuko/distributions.py:129-138).  Differentiable w.r.t. z, c and the parameters."""
         z2, c2, ldc, lead = _flatten(z, c if self.C else None, self.D)
-        if torch.is_grad_enabled() and not FlowCall._warned_inverse and (
-            z2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
-        ):
-            FlowCall._warned_inverse = True
-            warnings.warn(
-                "zuko_b200: rsample() / transform.inv() return tensors that are NOT differentiable in this "
-                "version (a backward pass exists for log_prob and call_and_ladj only); the result is detached.",
-                stacklevel=3,
-            )
+        if self._wants_grad(z2, c2):
+            out = _FlowInverseFunction.apply(self, with_log_prob, ldc, z2, c2, *self._params)
+            if with_log_prob:
+                return out[0].reshape(*lead, self.D), out[1].reshape(lead)
+            return out.reshape(*lead, self.D)
+        return self._run_inverse(z2, c2, ldc, lead, with_log_prob)
+
+    def _run_inverse(self, z2: Tensor, c2: Tensor | None, ldc: int, lead, with_log_prob: bool = False):
         z2, c2 = z2.detach(), (None if c2 is None else c2.detach())
         B = z2.shape[0]
         x = torch.empty_like(z2)
@@ -260,6 +285,61 @@ class FlowCall:
         gc = None
         if need_c and c2 is not None:
             gc = torch.zeros(C, **f32) if ldc == 0 else torch.empty(B, C, **f32)
+        structs, pg, tables, keep = self._grad_structs(need_p, f32)
+        if B:
+            with torch.cuda.device(dev):
+                want = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), B)
+                minimum = L.zk_flow_backward_min_workspace_bytes(ctypes.byref(self.desc))
+                floor = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), min(B, 1024))
+                ws = E.Workspace.get(dev, want, max(minimum, floor))
+                E.check(
+                    L.zk_flow_backward(
+                        ctypes.byref(self.desc), x2.data_ptr(), D, _ptr(c2), ldc, B, _ptr(g_z), D, _ptr(g_l), _ptr(g_lp),
+                        _ptr(gx), D, _ptr(gc), C, structs, ws.data_ptr(), ws.numel(), E.stream_ptr(dev),
+                    )
+                )  # fmt: skip
+        elif gx is not None:
+            gx.zero_()
+        self._split_tables(pg, tables, need_p)
+        del keep
+        return gx, gc, pg
+
+    def _run_inverse_backward(self, x: Tensor, z2: Tensor, c2: Tensor | None, ldc: int, g_x, g_lp, need_z: bool,
+                              need_c: bool, need_p: Sequence[bool]):  # fmt: skip
+        """One ``zk_flow_inverse_backward`` call: returns (gz | None, gc | None, [param grads | None])."""
+        L = E.lib()
+        dev = x.device
+        x = x.detach().reshape(-1, self.D).contiguous()
+        B, D, C = x.shape[0], self.D, self.C
+        f32 = dict(device=dev, dtype=torch.float32)
+        g_x = None if g_x is None else g_x.detach().to(torch.float32).reshape(-1, D).contiguous()
+        g_lp = None if g_lp is None else g_lp.detach().to(torch.float32).reshape(-1).contiguous()
+        gz = torch.empty(B, D, **f32) if need_z else None
+        gc = None
+        if need_c and c2 is not None:
+            gc = torch.zeros(C, **f32) if ldc == 0 else torch.empty(B, C, **f32)
+        structs, pg, tables, keep = self._grad_structs(need_p, f32)
+        if B:
+            with torch.cuda.device(dev):
+                want = L.zk_flow_inverse_backward_workspace_bytes(ctypes.byref(self.desc), B)
+                minimum = L.zk_flow_inverse_backward_min_workspace_bytes(ctypes.byref(self.desc))
+                floor = L.zk_flow_inverse_backward_workspace_bytes(ctypes.byref(self.desc), min(B, 1024))
+                ws = E.Workspace.get(dev, want, max(minimum, floor))
+                E.check(
+                    L.zk_flow_inverse_backward(
+                        ctypes.byref(self.desc), x.data_ptr(), D, _ptr(c2), ldc, B, _ptr(g_x), D, _ptr(g_lp),
+                        z2.data_ptr(), D, _ptr(gz), D, _ptr(gc), C, structs, ws.data_ptr(), ws.numel(), E.stream_ptr(dev),
+                    )
+                )  # fmt: skip
+        elif gz is not None:
+            gz.zero_()
+        self._split_tables(pg, tables, need_p)
+        del keep
+        return gz, gc, pg
+
+    def _grad_structs(self, need_p: Sequence[bool], f32: dict):
+        """Zero-initialised parameter-gradient buffers + the ``zk_layer_grads`` array pointing at them."""
+        D = self.D
         # parameter gradient buffers (accumulated into by the engine => zero-initialised)
         nL = len(self._handles)
         pg: list[Tensor | None] = [None] * len(self._params)
@@ -297,29 +377,16 @@ class FlowCall:
                 lg.grad_rotation = d["R"].data_ptr()
             keep.append(lg)
             structs[li] = ctypes.pointer(lg)
-        if B:
-            with torch.cuda.device(dev):
-                want = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), B)
-                minimum = L.zk_flow_backward_min_workspace_bytes(ctypes.byref(self.desc))
-                floor = L.zk_flow_backward_workspace_bytes(ctypes.byref(self.desc), min(B, 1024))
-                ws = E.Workspace.get(dev, want, max(minimum, floor))
-                E.check(
-                    L.zk_flow_backward(
-                        ctypes.byref(self.desc), x2.data_ptr(), D, _ptr(c2), ldc, B, _ptr(g_z), D, _ptr(g_l), _ptr(g_lp),
-                        _ptr(gx), D, _ptr(gc), C, structs, ws.data_ptr(), ws.numel(), E.stream_ptr(dev),
-                    )
-                )  # fmt: skip
-        elif gx is not None:
-            gx.zero_()
-        # split shared-table gradients back into the pieces of the ParameterList
+        return structs, pg, tables, keep
+
+    def _split_tables(self, pg: list, tables: dict, need_p: Sequence[bool]) -> None:
+        """Splits shared-table gradients back into the pieces of the ParameterList."""
         for i, (li, kind, k) in enumerate(self._slots):
             if kind == "phi" and need_p[i]:
                 pieces = self._sources[li]["phi"]
                 col = sum(int(t[0].numel()) for t in pieces[:k])
                 w = int(pieces[k][0].numel())
                 pg[i] = tables[li][:, col : col + w].reshape(pieces[k].shape).contiguous()
-        del keep
-        return gx, gc, pg
 
     def log_prob_host(self, x_host: Tensor, c_host: Tensor | None, device: torch.device, out: Tensor | None = None):
         """End-to-end entry: HOST (pinned) inputs, HOST output; H2D / compute / D2H are

@@ -285,10 +285,13 @@ size_t layer_bwd_ws(const zk_layer* l, int64_t B) {
     }
 }
 
+// direct_only (autoregressive / coupling): stop after the bijector's own derivative — gx receives
+// gy * dy_d/dx_d on the transformed dims, nothing flows through the conditioner
 zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, const float* c,
                               int64_t ldc, int64_t B, const float* gy, int64_t ldgy, const float* gl,
                               float* gx, int64_t ldgx, float* gc, int64_t ldgc,
-                              const zk_layer_grads* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+                              const zk_layer_grads* grads, void* ws, size_t ws_bytes, cudaStream_t st,
+                              bool direct_only = false) {
     if (B == 0) return ZK_OK;
     ZK_REQUIRE(l->C == 0 || c != nullptr, "layer needs a context of %d features", l->C);
     Arena ar(ws, ws_bytes);
@@ -313,8 +316,9 @@ zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, co
                 ZK_REQUIRE(tc_bwd_carve(m, plan, B, ar, tb), "layer_backward: workspace too small");
                 ZK_TRY(launch_concat(x, ldx, coupling ? l->idx_a : nullptr, nx, c, ldc, l->C, B, tb.a0, st));
                 ZK_TRY(tc_forward_save(m, plan, tb, B, st));
-                u.phi = tb.out; u.gphi = tb.out;
+                u.phi = tb.out; u.gphi = direct_only ? nullptr : tb.out;
                 ZK_TRY(launch_univariate_backward(u, st));
+                if (direct_only) return ZK_OK;
                 ZK_TRY(tc_mlp_backward(m, plan, tb, B, true, grads, st));
                 ZK_TRY(launch_input_grad(tb.gin, nx, l->C, coupling ? l->idx_a : nullptr, B, gx, ldgx,
                                          coupling ? gy : nullptr, ldgy, per_row_gc ? gc : nullptr, ldgc, st));
@@ -326,8 +330,9 @@ zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, co
             ZK_REQUIRE(mlp_bwd_carve(m, B, ar, b), "layer_backward: workspace too small");
             ZK_TRY(launch_concat(x, ldx, coupling ? l->idx_a : nullptr, nx, c, ldc, l->C, B, b.acts[0], st));
             ZK_TRY(mlp_forward_save(m, b, B, st));
-            u.phi = b.out; u.gphi = b.out;
+            u.phi = b.out; u.gphi = direct_only ? nullptr : b.out;
             ZK_TRY(launch_univariate_backward(u, st));  // gx[:, transformed] = direct term
+            if (direct_only) return ZK_OK;
             ZK_TRY(mlp_backward(m, b, B, true, grads, st));
             // coupling: gx[:, idx_a] = gy[:, idx_a] + gin[:, :n_a] (y_a = x_a, transforms.py:1069)
             ZK_TRY(launch_input_grad(b.gin, nx, l->C, coupling ? l->idx_a : nullptr, B, gx, ldgx,
@@ -465,6 +470,127 @@ zk_status flow_backward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx
     return ZK_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// inverse direction (reparameterised sampling): x = layer^{-1}(y; theta, c).
+// By the implicit-function theorem on y = f(x; theta, c) at the solution x, with J = df/dx:
+//     dL/dy = J^{-T} g,     dL/dtheta = -(df/dtheta)^T v,     dL/dc = -(df/dc)^T v,     v = dL/dy.
+// J is triangular in the layer's order classes with diagonal s = dy_d/dx_d, so J^T v = g is solved
+// exactly by `passes` Richardson sweeps  v <- v + (g - J^T v) / s  (I - S J^T is nilpotent), and
+// J^T v is ONE call of the forward direction's backward (gy = v, no parameter gradients).
+// (torch.autograd gets the same numbers by back-propagating through the sweeps of transforms.py:994-1000.)
+// ---------------------------------------------------------------------------
+struct InvBwdBufs { float *s, *jtv, *negv, *ones; };
+
+zk_status layer_inverse_backward_impl(const zk_layer* l, const float* x, int64_t ldx, const float* c, int64_t ldc,
+                                      int64_t B, const float* g /*(B, D)*/, float* v /*(B, D)*/, float* gc,
+                                      int64_t ldgc, const zk_layer_grads* grads, const InvBwdBufs& ib, void* ws,
+                                      size_t ws_bytes, cudaStream_t st) {
+    const int D = l->D;
+    const int64_t n = B * (int64_t)D;
+    bool has_params = false;
+    switch (l->kind) {
+        case ZK_LAYER_PERMUTATION:  // J = P (orthogonal): J^{-T} g = P g
+            return launch_permute(g, D, l->perm, B, D, v, D, st);
+        case ZK_LAYER_ROTATION:     // J = R (orthogonal): J^{-T} g = R g
+            ZK_TRY(launch_rotate(g, D, l->rotation, 0, B, D, v, D, st));
+            has_params = true;
+            break;
+        default: {
+            const bool cond = (l->kind == ZK_LAYER_AUTOREGRESSIVE || l->kind == ZK_LAYER_COUPLING);
+            const int sweeps = (l->kind == ZK_LAYER_AUTOREGRESSIVE) ? std::max(1, l->passes) : (l->kind == ZK_LAYER_COUPLING ? 2 : 1);
+            // s = diag J: the bijector's own derivative (1 on the constant split of a coupling layer)
+            ZK_TRY(launch_fill(ib.s, n, 1.f, st));
+            ZK_TRY(layer_backward_impl(l, x, ldx, c, ldc, B, ib.ones, D, nullptr, ib.s, D, nullptr, 0, nullptr, ws, ws_bytes, st, cond));
+            ZK_TRY(launch_div(v, g, ib.s, n, st));
+            for (int it = 1; it < sweeps; ++it) {
+                ZK_TRY(layer_backward_impl(l, x, ldx, c, ldc, B, v, D, nullptr, ib.jtv, D, nullptr, 0, nullptr, ws, ws_bytes, st));
+                ZK_TRY(launch_richardson(v, g, ib.jtv, ib.s, n, st));
+            }
+            has_params = (l->hyper != nullptr) || (l->phi_shared != nullptr);
+        }
+    }
+    if (has_params && (grads != nullptr || (gc != nullptr && l->C > 0))) {
+        ZK_TRY(launch_scale(ib.negv, v, -1.f, n, st));
+        ZK_TRY(layer_backward_impl(l, x, ldx, c, ldc, B, ib.negv, D, nullptr, ib.jtv, D, l->C ? gc : nullptr, ldgc, grads, ws, ws_bytes, st));
+    }
+    return ZK_OK;
+}
+
+size_t flow_invbwd_ws_for(const zk_flow_desc* f, int64_t Bc) {
+    return flow_bwd_ws_for(f, Bc) + (size_t)(f->n_layers + 9) * a256((size_t)Bc * f->features * 4) + a256((size_t)Bc * 4);
+}
+
+int64_t flow_invbwd_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes) {
+    if (flow_invbwd_ws_for(f, B) <= ws_bytes) return B;
+    if (flow_invbwd_ws_for(f, 1) > ws_bytes) return 0;
+    int64_t lo = 1, hi = B;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        if (flow_invbwd_ws_for(f, mid) <= ws_bytes) lo = mid; else hi = mid - 1;
+    }
+    if (lo >= 2048) lo = lo / 1024 * 1024;
+    return lo;
+}
+
+zk_status flow_inverse_backward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx, const float* c, int64_t ldc,
+                                      int64_t B, const float* grad_x, int64_t ldgx, const float* g_lp, const float* z,
+                                      int64_t ldz, float* grad_z, int64_t ldgz, float* grad_c, int64_t ldgc,
+                                      const zk_layer_grads* const* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int D = f->features, T = f->n_layers;
+    const int64_t n = B * (int64_t)D;
+    Arena ar(ws, ws_bytes);
+    std::vector<const float*> xs(T + 1);
+    std::vector<int64_t> ldxs(T + 1, D);
+    std::vector<float*> xbuf(T + 1, nullptr);
+    xs[0] = x;
+    ldxs[0] = ldx;
+    for (int i = 1; i <= T; ++i) xs[i] = xbuf[i] = ar.take<float>((size_t)n);
+    float* ga = ar.take<float>((size_t)n);
+    float* gb = ar.take<float>((size_t)n);
+    float* gxl = ar.take<float>((size_t)n);
+    InvBwdBufs ib;
+    ib.s = ar.take<float>((size_t)n); ib.jtv = ar.take<float>((size_t)n); ib.negv = ar.take<float>((size_t)n);
+    ib.ones = ar.take<float>((size_t)n);
+    float* out = ar.take<float>((size_t)n);
+    float* lscr = ar.take<float>((size_t)B);
+    ZK_REQUIRE(ar.ok, "flow_inverse_backward: workspace too small");
+    void* lws = ar.base + ar.off;
+    const size_t lws_bytes = ar.size - ar.off;
+    ZK_TRY(launch_fill(ib.ones, n, 1.f, st));
+    // forward chain from the sample: xs[l] is the input of layer l in the forward direction
+    for (int i = 0; i < T; ++i) {
+        const zk_layer* l = f->layers[i];
+        ZK_TRY(layer_forward_impl(l, xs[i], ldxs[i], l->C ? c : nullptr, ldc, B, xbuf[i + 1], D, lscr, 0, nullptr,
+                                  nullptr, nullptr, lws, lws_bytes, st));
+    }
+    if (grad_x) ZK_TRY(copy_rows(grad_x, ldgx, B, D, ga, D, st));
+    else ZK_TRY(launch_fill(ga, n, 0.f, st));
+    if (g_lp) {
+        // log p = base.log_prob(z) + sum_l ladj_l(x_l; theta): explicit gradients at fixed x, d/dx joins g
+        ZK_TRY(flow_backward_chunk(f, x, ldx, c, ldc, B, nullptr, 0, g_lp, nullptr, gxl, D, grad_c, ldgc, grads, lws, lws_bytes, st));
+        ZK_TRY(launch_add(ga, gxl, n, st));
+    }
+    float* g = ga;
+    float* v = gb;
+    for (int i = 0; i < T; ++i) {
+        const zk_layer* l = f->layers[i];
+        ZK_TRY(layer_inverse_backward_impl(l, xs[i], ldxs[i], l->C ? c : nullptr, ldc, B, g, v, l->C ? grad_c : nullptr, ldgc,
+                                           grads ? grads[i] : nullptr, ib, lws, lws_bytes, st));
+        std::swap(g, v);
+    }
+    if (grad_z) {
+        if (g_lp && f->base_kind == ZK_BASE_DIAG_NORMAL) {  // + g_lp * d base.log_prob(z) / dz
+            ZK_REQUIRE(z != nullptr, "flow_inverse_backward: grad_log_prob needs z");
+            ZK_TRY(launch_base_grad(z, ldz, f->base_loc, f->base_scale, g_lp, g, D, nullptr, B, D, out, lscr, st));
+            ZK_TRY(copy_rows(out, D, B, D, grad_z, ldgz, st));
+        } else {
+            ZK_TRY(copy_rows(g, D, B, D, grad_z, ldgz, st));
+        }
+    }
+    return ZK_OK;
+}
+
 zk_status uni_backward_entry(int uni, const float* x, int64_t ldx, const float* phi, int64_t phi_ld,
                              int64_t B, int D, int K, float bound, float slope, const float* gy,
                              int64_t ldgy, const float* gl, float* gx, int64_t ldgx, float* gphi,
@@ -578,6 +704,45 @@ zk_status zk_flow_backward(const zk_flow_desc* f, const float* x, int64_t ldx, c
                                    grad_z ? grad_z + i0 * ldgz : nullptr, ldgz, grad_ladj ? grad_ladj + i0 : nullptr,
                                    grad_log_prob ? grad_log_prob + i0 : nullptr, grad_x ? grad_x + i0 * ldgx : nullptr,
                                    ldgx, gc, ldgc, grads, ws, ws_bytes, st));
+    }
+    return ZK_OK;
+}
+
+size_t zk_flow_inverse_backward_workspace_bytes(const zk_flow_desc* f, int64_t B) {
+    if (!f || B <= 0) return 1024;
+    return flow_invbwd_ws_for(f, B);
+}
+size_t zk_flow_inverse_backward_min_workspace_bytes(const zk_flow_desc* f) { return f ? flow_invbwd_ws_for(f, 1) : 1024; }
+
+zk_status zk_flow_inverse_backward(const zk_flow_desc* f, const float* x, int64_t ldx, const float* c, int64_t ldc,
+                                   int64_t B, const float* grad_x, int64_t ldgx, const float* grad_log_prob,
+                                   const float* z, int64_t ldz, float* grad_z, int64_t ldgz, float* grad_c,
+                                   int64_t ldgc, const zk_layer_grads* const* grads, void* ws, size_t ws_bytes,
+                                   zk_stream stream) {
+    ZK_TRY(flow_check(f));
+    ZK_REQUIRE(x, "flow_inverse_backward: null x");
+    ZK_REQUIRE(B >= 0 && ldx >= f->features, "flow_inverse_backward: bad shape");
+    ZK_REQUIRE(!grad_x || ldgx >= f->features, "flow_inverse_backward: bad ldgx");
+    ZK_REQUIRE(!grad_z || ldgz >= f->features, "flow_inverse_backward: bad ldgz");
+    ZK_REQUIRE(!grad_log_prob || !grad_z || f->base_kind != ZK_BASE_DIAG_NORMAL || (z && ldz >= f->features),
+               "flow_inverse_backward: grad_log_prob needs z");
+    ZK_REQUIRE(f->context == 0 || c, "flow_inverse_backward: flow needs a context");
+    ZK_REQUIRE(!grad_c || f->context == 0 || ldc == 0 || ldgc >= f->context, "flow_inverse_backward: bad ldgc");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = f->context;
+    if (C == 0) grad_c = nullptr;
+    if (grad_c && ldc == 0) ZK_CUDA(cudaMemsetAsync(grad_c, 0, (size_t)C * 4, st));
+    if (B == 0) return ZK_OK;
+    const int64_t Bc = flow_invbwd_chunk_rows(f, B, ws_bytes);
+    ZK_REQUIRE(Bc > 0, "flow_inverse_backward: workspace too small (%zu < %zu)", ws_bytes, zk_flow_inverse_backward_min_workspace_bytes(f));
+    for (int64_t i0 = 0; i0 < B; i0 += Bc) {
+        const int64_t n = std::min(Bc, B - i0);
+        float* gc = grad_c ? (ldc == 0 ? grad_c : grad_c + i0 * ldgc) : nullptr;
+        if (gc && ldc != 0) ZK_CUDA(cudaMemset2DAsync(gc, (size_t)ldgc * 4, 0, (size_t)C * 4, (size_t)n, st));
+        ZK_TRY(flow_inverse_backward_chunk(f, x + i0 * ldx, ldx, c ? c + i0 * ldc : nullptr, ldc, n,
+                                           grad_x ? grad_x + i0 * ldgx : nullptr, ldgx, grad_log_prob ? grad_log_prob + i0 : nullptr,
+                                           z ? z + i0 * ldz : nullptr, ldz, grad_z ? grad_z + i0 * ldgz : nullptr, ldgz, gc,
+                                           ldgc, grads, ws, ws_bytes, st));
     }
     return ZK_OK;
 }

@@ -163,6 +163,19 @@ __global__ void act_gate_kernel(float* g, const float* pre, int64_t n, int act) 
     if (i < n) g[i] *= act_deriv(pre[i], act);
 }
 
+__global__ void scale_kernel(float* out, const float* in, float alpha, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = alpha * in[i];
+}
+__global__ void div_kernel(float* out, const float* g, const float* s, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = g[i] / s[i];
+}
+__global__ void richardson_kernel(float* v, const float* g, const float* jtv, const float* s, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += (g[i] - jtv[i]) / s[i];
+}
+
 __global__ void add_kernel(float* y, const float* x, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -397,6 +410,22 @@ zk_status launch_act_gate(float* g, const float* pre, int64_t n, int act, cudaSt
     if (n == 0) return ZK_OK;
     act_gate_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, pre, n, act);
     return check_launch("act_gate_kernel");
+}
+
+zk_status launch_scale(float* out, const float* in, float alpha, int64_t n, cudaStream_t st) {
+    if (n == 0) return ZK_OK;
+    scale_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(out, in, alpha, n);
+    return check_launch("scale_kernel");
+}
+zk_status launch_div(float* out, const float* g, const float* s, int64_t n, cudaStream_t st) {
+    if (n == 0) return ZK_OK;
+    div_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(out, g, s, n);
+    return check_launch("div_kernel");
+}
+zk_status launch_richardson(float* v, const float* g, const float* jtv, const float* s, int64_t n, cudaStream_t st) {
+    if (n == 0) return ZK_OK;
+    richardson_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(v, g, jtv, s, n);
+    return check_launch("richardson_kernel");
 }
 
 zk_status launch_add(float* y, const float* x, int64_t n, cudaStream_t st) {

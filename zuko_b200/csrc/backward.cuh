@@ -86,5 +86,10 @@ zk_status launch_transpose(const float* in, int N, int K, float* out, cudaStream
 
 // y[i] += x[i]
 zk_status launch_add(float* y, const float* x, int64_t n, cudaStream_t stream);
+// out[i] = alpha * in[i]
+zk_status launch_scale(float* out, const float* in, float alpha, int64_t n, cudaStream_t stream);
+// out[i] = g[i] / s[i];   v[i] += (g[i] - jtv[i]) / s[i]   (Richardson sweep of the triangular solve J^T v = g)
+zk_status launch_div(float* out, const float* g, const float* s, int64_t n, cudaStream_t stream);
+zk_status launch_richardson(float* v, const float* g, const float* jtv, const float* s, int64_t n, cudaStream_t stream);
 
 }  // namespace zk
