@@ -345,7 +345,7 @@ def _inverse_grads(flow, z, c, mode, w, wl, device):
     return cpu(x), cpu(zt.grad), (None if ct is None else cpu(ct.grad)), named_param_grads(flow)
 
 
-INV_BAR = 2e-4  # gradients evaluated at a sample that itself carries ~1e-5 of inverse error
+INV_BAR = 1e-4  # gradients evaluated at a sample that itself carries ~1e-6..1e-5 of inverse error (measured worst: 2.6e-5)
 
 
 @pytest.mark.parametrize("mode", ["inv", "invlp"])

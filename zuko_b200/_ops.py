@@ -9,7 +9,6 @@ taken as contiguous fp32 copies when they are not already.
 from __future__ import annotations
 
 import ctypes
-import warnings
 from collections.abc import Sequence
 
 import torch
@@ -139,9 +138,7 @@ class _FlowInverseFunction(torch.autograd.Function):
 
 
 class FlowCall:
-    """A ``zk_flow_desc`` over packed layers + DiagNormal base, ready to be invoked."""
-
-    _warned_inverse = False
+    """A ``zk_flow_desc`` over packed layers + DiagNormal / BoxUniform base, ready to be invoked."""
 
     def __init__(self, handles: Sequence, D: int, C: int, loc: Tensor | None, scale: Tensor | None,
                  sources: Sequence[dict] | None = None, keep: Sequence | None = None, base_kind: int = 0) -> None:  # fmt: skip
