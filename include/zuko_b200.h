@@ -153,6 +153,13 @@ typedef struct {
     const uint8_t* const* mask;  /* host array of DEVICE ptrs (bool bytes), or NULL / NULL entries = dense */
     int gemm_mode;               /* ZK_GEMM_* */
     int activation;              /* ZK_ACT_* between the linear layers (0 = ReLU) */
+    /* residual conditioners (MaskedMLP(residual=True), zuko/nn.py:195-199, 297-309): per linear layer, host
+     * arrays of n_linear ints or NULL for the plain pattern (activation after every layer but the last):
+     * layer_act[i] = 0 none / 1 ReLU / ZK_ACT_* applied to the output of layer i; layer_res[i] != 0 adds the
+     * INPUT of layer i-1 to the output of layer i (second layer of a residual block; needs i >= 2 and equal
+     * widths).  Such handles run on the fp32 CUDA-core path. */
+    const int* layer_act;
+    const int* layer_res;
 } zk_mlp_desc;
 
 zk_status zk_mlp_create(const zk_mlp_desc* desc, zk_mlp** out);

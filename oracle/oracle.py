@@ -311,25 +311,56 @@ ACTIVATIONS = {
 @dataclass
 class Conditioner:
     """Weights of a MaskedMLP (nn.py:221-318) or MLP (nn.py:122-192), as numpy.
-    ``masks[i]`` is None for dense layers; ``activation`` names the module between the layers."""
+    ``masks[i]`` is None for dense layers; ``activation`` names the module between the layers.
+    ``layer_act`` / ``layer_res`` (residual conditioners, nn.py:195-199, 297-309) give, per linear
+    layer, the activation applied to its output (None = none) and whether the input of the
+    previous linear layer is added to its output (second layer of a ``Residual`` block)."""
 
     weights: list
     biases: list
     masks: list
     activation: str = "ReLU"
+    layer_act: list | None = None
+    layer_res: list | None = None
+
+    def flags(self):
+        n = len(self.weights)
+        if self.layer_act is None:
+            return [self.activation] * (n - 1) + [None], [False] * n
+        return list(self.layer_act), list(self.layer_res)
+
+    def trace(self, inp):
+        """fp64 numpy evaluation keeping everything: (inputs a[0..n], linear outputs o[0..n-1])."""
+        acts, res = self.flags()
+        a = [np.asarray(inp, np.float64)]
+        outs = []
+        for i, (W, b, m) in enumerate(zip(self.weights, self.biases, self.masks, strict=True)):
+            Wm = W * (1.0 if m is None else m)
+            o = a[i] @ Wm.T
+            if b is not None:
+                o = o + b
+            if res[i]:
+                o = o + a[i - 1]
+            outs.append(o)
+            a.append(ACTIVATIONS[acts[i]][0](o) if acts[i] else o)
+        return a, outs
 
     def __call__(self, x, c, dtype) -> np.ndarray:
+        acts, res = self.flags()
         h = None
-        n = len(self.weights)
-        relu = self.activation == "ReLU"
+        prev_in = None
         for i, (W, b, m) in enumerate(zip(self.weights, self.biases, self.masks, strict=True)):
-            hidden = i < n - 1
+            relu = acts[i] == "ReLU"
+            cur_in = h
             if i == 0:
-                h = linear(x, c, W, m, b, relu=(hidden and relu), dtype=dtype)
+                h = linear(x, c, W, m, b, relu=relu, dtype=dtype)
             else:
-                h = linear(h, None, W, m, b, relu=(hidden and relu), dtype=dtype)
-            if hidden and not relu:
-                h = np.ascontiguousarray(ACTIVATIONS[self.activation][0](h), dtype=dtype)
+                h = linear(h, None, W, m, b, relu=relu, dtype=dtype)
+            if acts[i] and not relu:
+                h = np.ascontiguousarray(ACTIVATIONS[acts[i]][0](h), dtype=dtype)
+            if res[i]:  # x + block(x): the block's input is the input of the previous linear layer
+                h = np.ascontiguousarray(h + prev_in, dtype=dtype)
+            prev_in = cur_in
         return h
 
 
@@ -505,17 +536,41 @@ def _np(t):
 
 def conditioner_from_module(hyper) -> Conditioner:
     Ws, bs, ms = [], [], []
+    layer_act, layer_res = [], []
     act = "ReLU"
-    for m in hyper:
-        if hasattr(m, "weight"):
-            Ws.append(_np(m.weight).astype(np.float64))
-            bs.append(None if m.bias is None else _np(m.bias).astype(np.float64))
-            ms.append(_np(m.mask).astype(bool) if hasattr(m, "mask") else None)
-        else:
-            name = type(m).__name__
-            if name not in ACTIVATIONS:
-                raise NotImplementedError(f"oracle: activation {name}")
-            act = name
+    residual = False
+
+    def add(lin, a, r):
+        Ws.append(_np(lin.weight).astype(np.float64))
+        bs.append(None if lin.bias is None else _np(lin.bias).astype(np.float64))
+        ms.append(_np(lin.mask).astype(bool) if hasattr(lin, "mask") else None)
+        layer_act.append(a)
+        layer_res.append(r)
+
+    mods = list(hyper)
+    for j, m in enumerate(mods):
+        name = type(m).__name__
+        if name == "Residual":  # nn.py:195-199: x + (Linear, activation, Linear)(x)
+            inner = list(m)
+            assert len(inner) == 3 and hasattr(inner[0], "weight") and hasattr(inner[2], "weight"), inner
+            a = type(inner[1]).__name__
+            if a not in ACTIVATIONS:
+                raise NotImplementedError(f"oracle: activation {a}")
+            act = a
+            residual = True
+            add(inner[0], a, False)
+            add(inner[2], None, True)
+        elif hasattr(m, "weight"):
+            nxt = mods[j + 1] if j + 1 < len(mods) else None
+            a = None
+            if nxt is not None and not hasattr(nxt, "weight") and type(nxt).__name__ != "Residual":
+                a = type(nxt).__name__
+                if a not in ACTIVATIONS:
+                    raise NotImplementedError(f"oracle: activation {a}")
+                act = a
+            add(m, a, False)
+    if residual:
+        return Conditioner(Ws, bs, ms, act, layer_act, layer_res)
     return Conditioner(Ws, bs, ms, act)
 
 

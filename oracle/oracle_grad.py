@@ -192,46 +192,31 @@ class CondGrads:
 
 
 def conditioner_backward(cond: O.Conditioner, inp, gout):
-    """Reverse mode of the (masked) MLP with ReLU (nn.py:217-218, 311-313).
-    inp (B, in), gout (B, out).  Returns (ginp, CondGrads) — weight gradients are w.r.t. the
-    RAW weights, i.e. already multiplied by the mask."""
+    """Reverse mode of the (masked) MLP (nn.py:217-218, 311-313), residual blocks included
+    (nn.py:195-199).  inp (B, in), gout (B, out).  Returns (ginp, CondGrads) — weight gradients are
+    w.r.t. the RAW weights, i.e. already multiplied by the mask."""
     n = len(cond.weights)
-    act, dact = O.ACTIVATIONS[cond.activation]
-    acts = [np.asarray(inp, F)]
-    pres = []
-    for i in range(n):
-        W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
-        hcur = acts[-1] @ W.T
-        if cond.biases[i] is not None:
-            hcur = hcur + cond.biases[i]
-        pres.append(hcur)
-        if i < n - 1:
-            hcur = act(hcur)
-        acts.append(hcur)
-    g = np.asarray(gout, F)
+    acts, res = cond.flags()
+    a, outs = cond.trace(inp)
+    g = np.asarray(gout, F)  # dL/d(output of linear layer i, before its activation)
     out = CondGrads([None] * n, [None] * n)
+    pending = {}  # index of a layer input -> gradient arriving through a residual connection
     for i in reversed(range(n)):
-        if i < n - 1:
-            g = g * dact(pres[i])
         mk = 1.0 if cond.masks[i] is None else cond.masks[i]
-        out.weights[i] = (g.T @ acts[i]) * mk
+        out.weights[i] = (g.T @ a[i]) * mk
         out.biases[i] = None if cond.biases[i] is None else g.sum(0)
-        g = g @ (cond.weights[i] * mk)
+        ga = g @ (cond.weights[i] * mk) + pending.pop(i, 0.0)
+        if res[i]:
+            pending[i - 1] = g
+        if i > 0:
+            g = ga * O.ACTIVATIONS[acts[i - 1]][1](outs[i - 1]) if acts[i - 1] else ga
+        else:
+            g = ga
     return g, out
 
 
 def _cond_forward(cond: O.Conditioner, inp):
-    h = np.asarray(inp, F)
-    n = len(cond.weights)
-    act = O.ACTIVATIONS[cond.activation][0]
-    for i in range(n):
-        W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
-        h = h @ W.T
-        if cond.biases[i] is not None:
-            h = h + cond.biases[i]
-        if i < n - 1:
-            h = act(h)
-    return h
+    return cond.trace(inp)[0][-1]
 
 
 # --------------------------------------------------------------------------- #

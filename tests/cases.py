@@ -40,8 +40,12 @@ FLOW_CASES = {
     "act_nice_lrelu": (0, lambda: NICE(4, 2, hidden_features=[32], activation=torch.nn.LeakyReLU)),
     "act_maf_softplus": (0, lambda: MAF(3, 0, transforms=2, hidden_features=[16], activation=torch.nn.Softplus)),
     "act_maf_sigmoid": (0, lambda: MAF(3, 1, transforms=2, hidden_features=[16, 16], activation=torch.nn.Sigmoid)),
+    # residual conditioners (tests/golden/make_golden_res.py)
+    "res_nsf_relu": (0, lambda: NSF(5, 2, transforms=2, residual=True, hidden_features=[32, 32])),
+    "res_maf_elu": (0, lambda: MAF(4, 0, transforms=2, residual=True, hidden_features=[24], activation=torch.nn.ELU)),
+    "res_nsf_mixed": (0, lambda: NSF(3, 1, transforms=2, residual=True, hidden_features=[16, 32, 32])),
 }
-ACT_CASES = [k for k in FLOW_CASES if k.startswith("act_")]
+ACT_CASES = [k for k in FLOW_CASES if k.startswith(("act_", "res_"))]
 SMALL_CASES = [k for k in FLOW_CASES if not k.startswith(("cfg2", "cfg3", "cfg4", "cfg5"))]
 BIG_CASES = ["cfg2_nsf", "cfg3_maf", "cfg4_nsf", "cfg5_nsf"]
 
@@ -177,7 +181,12 @@ def oracle_named_grads(flow, layer_grads) -> dict:
     for i, (t, lg) in enumerate(zip(flow.transform.transforms, layer_grads, strict=True)):
         pre = f"transform.transforms.{i}."
         if lg.hyper is not None:
-            lins = [(j, m) for j, m in enumerate(t.hyper) if hasattr(m, "weight")]
+            lins = []  # (state-dict index, linear module) in execution order, residual blocks flattened
+            for j, m in enumerate(t.hyper):
+                if type(m).__name__ == "Residual":
+                    lins += [(f"{j}.{k}", inner) for k, inner in enumerate(m) if hasattr(inner, "weight")]
+                elif hasattr(m, "weight"):
+                    lins.append((j, m))
             for (j, m), gw, gb in zip(lins, lg.hyper.weights, lg.hyper.biases, strict=True):
                 out[f"{pre}hyper.{j}.weight"] = np.asarray(gw).reshape(-1)
                 if m.bias is not None:
@@ -263,17 +272,15 @@ def relu_kink_rows(spec, x, c, tau: float = 1e-5, tau_knot: float = 5e-5) -> np.
                 h = za if cc is None else np.concatenate([za, cc], -1)
             else:
                 h = cc
-            n = len(cond.weights)
-            for i in range(n):
-                W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
-                bias = 0.0 if cond.biases[i] is None else cond.biases[i]
-                pre = h @ W.T + bias
-                if i == n - 1:
-                    phi = pre
-                    break
-                if cond.activation in ("ReLU", "LeakyReLU"):  # the only supported activations with a kink
-                    bad |= (np.abs(pre) < tau * (np.abs(h) @ np.abs(W).T + np.abs(bias))).any(-1)
-                h = O_act(cond.activation)(pre)
+            acts_, _res = cond.flags()
+            a_, outs_ = cond.trace(h)
+            phi = outs_[-1]
+            for i, name_ in enumerate(acts_):
+                if name_ in ("ReLU", "LeakyReLU"):  # the only supported activations with a kink
+                    W = cond.weights[i] * (1.0 if cond.masks[i] is None else cond.masks[i])
+                    bias = 0.0 if cond.biases[i] is None else cond.biases[i]
+                    scale = np.abs(a_[i]) @ np.abs(W).T + np.abs(bias) + (np.abs(a_[i - 1]) if _res[i] else 0.0)
+                    bad |= (np.abs(outs_[i]) < tau * scale).any(-1)
         elif layer.kind == "elementwise":
             phi = np.broadcast_to(np.asarray(layer.phi, np.float64), (B, *np.asarray(layer.phi).shape))
         if phi is not None and layer.univariate in ("rqs", "crqs"):
@@ -303,7 +310,8 @@ def O_rqs_knots(phi, bins, bound, slope):
 
 
 INV_GRAD_CASES = ["cfg1_maf", "nsf35_row", "maf35_batch", "nice35", "nsf5_passes2", "maf5_randperm", "nsf1_elementwise",
-                  "ncsf34", "act_maf_elu", "act_nsf_tanh", "composed", "composed_uncond", "cfg2_nsf"]  # fmt: skip
+                  "ncsf34", "act_maf_elu", "act_nsf_tanh", "composed", "composed_uncond", "cfg2_nsf",
+                  "res_nsf_relu", "res_maf_elu", "res_nsf_mixed"]  # fmt: skip
 
 
 def inv_grad_inputs(name: str):

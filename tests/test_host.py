@@ -113,11 +113,36 @@ def test_features_one_falls_back_to_elementwise():
 
 def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
-        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), residual=True)
-    with pytest.raises(NotImplementedError):
         MaskedMLP(torch.ones(4, 3, dtype=torch.bool), activation=torch.nn.PReLU)
     with pytest.raises(NotImplementedError):
+        MaskedMLP(torch.ones(4, 3, dtype=torch.bool), activation=lambda: torch.nn.ELU(alpha=0.5))
+    with pytest.raises(NotImplementedError):
         MaskedAutoregressiveTransform(3, univariate=torch.distributions.ExpTransform, shapes=[])
+
+
+def test_residual_masked_mlp_structure():
+    """MaskedMLP(residual=True) builds the reference's blocks (zuko/nn.py:297-309): module tree, per-layer
+    activation / residual flags handed to the engine, and the masks keep the Jacobian sparsity of the
+    adjacency (the reference's own property test, tests/test_nn.py:39-60, in exact arithmetic)."""
+    torch.manual_seed(1)
+    adjacency = torch.rand(6, 5) < 0.4
+    adjacency[:, 0] = True
+    net = MaskedMLP(adjacency, [16, 16, 24], activation=torch.nn.ELU, residual=True)
+    names = [type(m).__name__ for m in net]
+    assert names == ["MaskedLinear", "Residual", "Residual", "MaskedLinear", "Residual", "MaskedLinear"], names
+    acts, res = net._layer_flags()
+    assert acts == [0, 2, 0, 2, 0, 0, 2, 0, 0] and res == [0, 0, 1, 0, 1, 0, 0, 1, 0], (acts, res)
+    # boolean reachability through the masks = structural Jacobian; residual adds keep a unit's own class
+    lins = net._linears()
+    reach = torch.eye(5, dtype=torch.bool)  # (unit of the current layer input) x (network input)
+    prev_in = None
+    for lin, r in zip(lins, res, strict=True):
+        cur_in = reach
+        out = (lin.mask.to(torch.float64) @ reach.to(torch.float64)) > 0
+        if r:
+            out = out | prev_in
+        prev_in, reach = cur_in, out
+    assert not (reach & ~adjacency).any()
 
 
 # --------------------------------------------------------------------------- #

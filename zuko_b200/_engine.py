@@ -50,6 +50,8 @@ class MlpDesc(ctypes.Structure):
         ("mask", POINTER(c_void_p)),
         ("gemm_mode", c_int),
         ("activation", c_int),
+        ("layer_act", POINTER(c_int)),
+        ("layer_res", POINTER(c_int)),
     ]
 
 

@@ -77,13 +77,24 @@ def _conditioner_kwargs(hyper: nn.Module) -> tuple[dict, list]:
 
     linears = []
     activation = None
+    block_widths = []  # residual conditioners: one block per hidden depth (zuko/nn.py:297-309)
+    flat = []
     for m in hyper:
+        if type(m).__name__ == "Residual":
+            inner = list(m)
+            if len(inner) != 3 or not hasattr(inner[0], "weight") or hasattr(inner[1], "weight") or not hasattr(inner[2], "weight"):
+                raise _unsupported("a residual block that is not Linear-activation-Linear")
+            block_widths.append(inner[0].weight.shape[0])
+            flat += inner
+        else:
+            flat.append(m)
+    for m in flat:
         if hasattr(m, "weight") and isinstance(getattr(m, "weight", None), torch.Tensor):
             if m.weight.dim() != 2:
                 raise _unsupported("a stacked / non-matrix linear layer in the conditioner")
             linears.append(m)
-        elif type(m).__name__ in ("MaskedResidual", "Residual") or any(True for _ in m.children()):
-            raise _unsupported("a residual conditioner block (zuko/nn.py:297-309)")
+        elif any(True for _ in m.children()):
+            raise _unsupported(f"conditioner module {type(m).__name__}")
         else:
             try:
                 activation_code(m)
@@ -95,6 +106,8 @@ def _conditioner_kwargs(hyper: nn.Module) -> tuple[dict, list]:
     if not linears:
         raise _unsupported("a conditioner without linear layers")
     kwargs = dict(hidden_features=[m.weight.shape[0] for m in linears[:-1]])
+    if block_widths:
+        kwargs = dict(hidden_features=block_widths, residual=True)
     if activation is not None and activation is not nn.ReLU:
         kwargs["activation"] = activation
     return kwargs, linears

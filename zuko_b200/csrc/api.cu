@@ -166,10 +166,25 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
     if (!m) return fail(ZK_ENOMEM, "mlp_create: out of host memory");
     m->n_linear = d->n_linear;
     m->act = (d->activation <= 1) ? 1 : d->activation;
+    m->lact.assign(d->n_linear, m->act);
+    m->lact[d->n_linear - 1] = 0;
+    m->lres.assign(d->n_linear, 0);
+    if (d->layer_act || d->layer_res) {  // residual conditioner: explicit per-layer pattern
+        m->plain = false;
+        for (int i = 0; i < d->n_linear; ++i) {
+            if (d->layer_act) m->lact[i] = d->layer_act[i];
+            if (d->layer_res) m->lres[i] = d->layer_res[i] ? 1 : 0;
+        }
+    }
     m->dims.assign(d->dims, d->dims + d->n_linear + 1);
     zk_status st = ZK_OK;
     for (int i = 0; i <= d->n_linear && st == ZK_OK; ++i)
         if (m->dims[i] <= 0) st = fail(ZK_EINVAL, "mlp_create: dims[%d]=%d", i, m->dims[i]);
+    for (int i = 0; i < d->n_linear && st == ZK_OK; ++i) {
+        if (m->lact[i] < 0 || m->lact[i] > ZK_ACT_SIGMOID) st = fail(ZK_EINVAL, "mlp_create: layer_act[%d]=%d", i, m->lact[i]);
+        if (m->lres[i] && (i < 2 || i == d->n_linear - 1 || m->dims[i + 1] != m->dims[i - 1] || m->lact[i] != 0))
+            st = fail(ZK_EINVAL, "mlp_create: layer %d cannot close a residual block (needs i >= 2, a hidden layer, equal widths, no activation)", i);
+    }
     for (int i = 0; i < d->n_linear && st == ZK_OK; ++i) {
         const int64_t n = (int64_t)m->dims[i + 1] * m->dims[i];
         float *w = nullptr, *b = nullptr;
@@ -199,7 +214,12 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
         }
         if (i < d->n_linear - 1) m->max_hidden = std::max(m->max_hidden, m->dims[i + 1]);
     }
-    if (st == ZK_OK) st = tc_pack(m, d->gemm_mode);  // resolves m->gemm_mode
+    if (st == ZK_OK) {
+        if (!m->plain && (d->gemm_mode == ZK_GEMM_BF16X3 || d->gemm_mode == ZK_GEMM_BF16X1))
+            st = fail(ZK_EUNSUPPORTED, "mlp_create: residual conditioners run on the fp32 path only");
+        else
+            st = tc_pack(m, m->plain ? d->gemm_mode : ZK_GEMM_FP32);  // resolves m->gemm_mode
+    }
     if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "mlp_create: sync failed");
     if (st != ZK_OK) {
         std::string keep = g_last_error;
@@ -246,11 +266,14 @@ zk_status zk_mlp_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, c
         const int64_t ldd = last ? ldo : m->dims[i + 1];
         if (i == 0) {
             ZK_TRY(launch_linear_fp32(x, ldx, dx, c, ldc, m->dims[0], m->w[0], m->b[0], B, m->dims[1],
-                                      last ? 0 : m->act, dst, ldd, st));
+                                      m->lact[0], dst, ldd, st));
         } else {
             const float* src = h[(i - 1) & 1];
+            // residual block: the input of layer i-1 lives in the buffer this layer writes (ping-pong):
+            // the epilogue adds it in place
+            const float* res = m->lres[i] ? dst : nullptr;
             ZK_TRY(launch_linear_fp32(src, m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i],
-                                      m->b[i], B, m->dims[i + 1], last ? 0 : m->act, dst, ldd, st));
+                                      m->b[i], B, m->dims[i + 1], m->lact[i], dst, ldd, st, res, ldd));
         }
     }
     return ZK_OK;

@@ -66,8 +66,8 @@ size_t mlp_bwd_scratch(const zk_mlp* m) {
 size_t mlp_bwd_ws(const zk_mlp* m, int64_t B) {
     size_t s = 0;
     for (int i = 0; i <= m->n_linear; ++i) s += a256((size_t)B * m->dims[i] * 4);  // acts + out
-    if (m->act != 1)
-        for (int i = 1; i < m->n_linear; ++i) s += a256((size_t)B * m->dims[i] * 4);  // pre-activations
+    for (int i = 1; i < m->n_linear; ++i)
+        if (m->lact[i - 1] > 1) s += a256((size_t)B * m->dims[i] * 4);  // pre-activations (non-ReLU layers)
     if (m->n_linear > 1) s += 2 * a256((size_t)B * m->max_hidden * 4);
     s += a256((size_t)B * m->dims[0] * 4);  // gin
     return s + mlp_bwd_scratch(m);
@@ -77,8 +77,8 @@ bool mlp_bwd_carve(const zk_mlp* m, int64_t B, Arena& ar, MlpBwdBufs& b) {
     b.acts.resize(m->n_linear);
     for (int i = 0; i < m->n_linear; ++i) b.acts[i] = ar.take<float>((size_t)B * m->dims[i]);
     b.pre.assign(m->n_linear, nullptr);
-    if (m->act != 1)
-        for (int i = 1; i < m->n_linear; ++i) b.pre[i] = ar.take<float>((size_t)B * m->dims[i]);
+    for (int i = 1; i < m->n_linear; ++i)
+        if (m->lact[i - 1] > 1) b.pre[i] = ar.take<float>((size_t)B * m->dims[i]);
     b.out = ar.take<float>((size_t)B * m->dims[m->n_linear]);
     if (m->n_linear > 1) {
         b.gbuf[0] = ar.take<float>((size_t)B * m->max_hidden);
@@ -94,15 +94,18 @@ zk_status mlp_forward_save(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, cuda
     const int n = m->n_linear;
     for (int i = 0; i < n; ++i) {
         const bool hidden = (i < n - 1);
-        if (hidden && m->act != 1) {  // general activation: keep the pre-activation for act'
+        const int act = m->lact[i];
+        if (hidden && act > 1) {  // general activation: keep the pre-activation for act'
             ZK_TRY(launch_linear_fp32(b.acts[i], m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i], m->b[i],
                                       B, m->dims[i + 1], 0, b.pre[i + 1], m->dims[i + 1], st));
-            ZK_TRY(launch_act_apply(b.pre[i + 1], b.acts[i + 1], B * (int64_t)m->dims[i + 1], m->act, st));
+            ZK_TRY(launch_act_apply(b.pre[i + 1], b.acts[i + 1], B * (int64_t)m->dims[i + 1], act, st));
             continue;
         }
         float* dst = hidden ? b.acts[i + 1] : b.out;
+        // second layer of a residual block: + input of the previous layer (zuko/nn.py:195-199)
+        const float* res = m->lres[i] ? b.acts[i - 1] : nullptr;
         ZK_TRY(launch_linear_fp32(b.acts[i], m->dims[i], m->dims[i], nullptr, 0, m->dims[i], m->w[i], m->b[i],
-                                  B, m->dims[i + 1], hidden ? 1 : 0, dst, m->dims[i + 1], st));
+                                  B, m->dims[i + 1], act, dst, m->dims[i + 1], st, res, m->dims[i + 1]));
     }
     return ZK_OK;
 }
@@ -120,11 +123,15 @@ zk_status mlp_backward(const zk_mlp* m, const MlpBwdBufs& b, int64_t B, bool wan
             ZK_TRY(launch_colsum_add(g, N, B, N, grads->grad_bias[i], b.scratch, st));
         if (i > 0 || want_gin) {
             float* dst = (i == 0) ? b.gin : b.gbuf[i & 1];
-            // g (B, N) x W (N, K) = "linear" with the transposed weights (K, N)
-            ZK_TRY(launch_linear_fp32(g, N, N, nullptr, 0, N, m->wt[i], nullptr, B, K, false, dst, K, st));
-            if (i > 0) {
-                if (m->act == 1) ZK_TRY(launch_relu_gate(dst, b.acts[i], B * (int64_t)K, st));
-                else ZK_TRY(launch_act_gate(dst, b.pre[i], B * (int64_t)K, m->act, st));
+            // g (B, N) x W (N, K) = "linear" with the transposed weights (K, N).  When layer i + 1 closed a
+            // residual block, its output gradient also flows straight into this layer's input: it still sits
+            // in the ping-pong buffer this dgrad writes, and the epilogue adds it in place
+            const float* pend = (i + 1 < n && m->lres[i + 1]) ? dst : nullptr;
+            ZK_TRY(launch_linear_fp32(g, N, N, nullptr, 0, N, m->wt[i], nullptr, B, K, 0, dst, K, st, pend, K));
+            if (i > 0) {  // through the activation of layer i - 1 (none inside / after a residual block's sum)
+                const int act = m->lact[i - 1];
+                if (act == 1) ZK_TRY(launch_relu_gate(dst, b.acts[i], B * (int64_t)K, st));
+                else if (act > 1) ZK_TRY(launch_act_gate(dst, b.pre[i], B * (int64_t)K, act, st));
             }
             g = dst;
         }
@@ -171,7 +178,7 @@ TcBwdPlan tc_plan(const zk_mlp* m, int64_t B) {
 }
 
 bool mlp_uses_tc(const zk_mlp* m) {  // the tensor-core backward gates with ReLU in the GEMM epilogue
-    return m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1;
+    return m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1 && m->plain;
 }
 
 size_t tc_bwd_ws(const zk_mlp* m, int64_t B) {

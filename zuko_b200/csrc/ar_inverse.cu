@@ -200,7 +200,7 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
     *out = nullptr;
     const int L = m->n_linear;
     if (!order || L < 1 || L > 7) return ZK_OK;
-    if (m->act != 1) return ZK_OK;  // the kernel's hidden units are ReLU: other activations use the sweeps
+    if (m->act != 1 || !m->plain) return ZK_OK;  // ReLU MLPs only: other activations / residual blocks use the sweeps
     if (uni == ZK_UNI_RQS && bins != 8 && bins != 16) return ZK_OK;
     if (m->dims[0] != D + C) return ZK_OK;
     const int P = (uni == ZK_UNI_RQS) ? 3 * bins - 1 : 2;

@@ -665,7 +665,7 @@ long long* g_timeline = nullptr;
 bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
     if (!pk || m->gemm_mode == ZK_GEMM_FP32) return false;
-    if (m->act != 1) return false;  // the hidden epilogue implements ReLU only
+    if (m->act != 1 || !m->plain) return false;  // the hidden epilogue implements ReLU MLPs only
     if (m->n_linear < 2 || m->n_linear > ZK_FUSED_MAX_LINEAR) return false;
     const int H = m->dims[1];
     if (H % 64 != 0 || H < 64 || H > 256) return false;

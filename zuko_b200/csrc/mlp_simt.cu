@@ -20,7 +20,7 @@ constexpr int kThreads = (BM / TM) * (BN / TN);  // 256
 __global__ void __launch_bounds__(kThreads)
 linear_fp32_kernel(const float* __restrict__ a0, int64_t lda0, int k0, const float* __restrict__ a1,
                    int64_t lda1, int K, const float* __restrict__ W, const float* __restrict__ bias,
-                   int64_t M, int N, int relu, float* __restrict__ C, int64_t ldc) {
+                   int64_t M, int N, int relu, float* C, int64_t ldc, const float* res, int64_t ldres) {
     __shared__ __align__(16) float As[BK][BM];
     __shared__ __align__(16) float Ws[BK][BN];
 
@@ -77,6 +77,7 @@ linear_fp32_kernel(const float* __restrict__ a0, int64_t lda0, int k0, const flo
             if (n >= N) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
             if (relu) v = act_apply(v, relu);  // 1 = ReLU, >= 2 = ZK_ACT_*
+            if (res) v += res[m * ldres + n];  // residual add; res may be C itself (element read before written)
             C[m * ldc + n] = v;
         }
     }
@@ -91,7 +92,7 @@ __global__ void apply_mask_kernel(const float* W, const uint8_t* mask, int64_t n
 
 zk_status launch_linear_fp32(const float* a0, int64_t lda0, int k0, const float* a1, int64_t lda1,
                              int K, const float* W, const float* bias, int64_t M, int N, int act,
-                             float* C, int64_t ldc, cudaStream_t stream) {
+                             float* C, int64_t ldc, cudaStream_t stream, const float* res, int64_t ldres) {
     ZK_REQUIRE(M >= 0 && N > 0 && K > 0 && k0 >= 0 && k0 <= K, "linear: bad shape");
     ZK_REQUIRE(a0 != nullptr || k0 == 0, "linear: null A");
     ZK_REQUIRE(a1 != nullptr || k0 == K, "linear: null context");
@@ -100,7 +101,7 @@ zk_status launch_linear_fp32(const float* a0, int64_t lda0, int k0, const float*
     ZK_REQUIRE(gx <= 0x7fffffff, "linear: batch too large");
     dim3 grid((unsigned)gx, (unsigned)ceil_div(N, BN));
     linear_fp32_kernel<<<grid, kThreads, 0, stream>>>(a0, lda0, k0, a1, lda1, K, W, bias, M, N,
-                                                       act, C, ldc);
+                                                       act, C, ldc, res, ldres);
     return check_launch("linear_fp32_kernel");
 }
 

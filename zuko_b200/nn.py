@@ -12,7 +12,7 @@ unchanged and ``torch.manual_seed(s)`` yields bit-identical weights.
 
 from __future__ import annotations
 
-__all__ = ["MLP", "Linear", "MaskedLinear", "MaskedMLP"]
+__all__ = ["MLP", "Linear", "MaskedLinear", "MaskedMLP", "Residual"]
 
 import ctypes
 from collections.abc import Callable, Sequence
@@ -86,6 +86,12 @@ def activation_code(module: nn.Module) -> int:
     return code
 
 
+class Residual(nn.Sequential):
+    """Residual block ``x + block(x)`` (zuko/nn.py:195-199).  Inside an engine conditioner the block is
+    ``MaskedLinear -> activation -> MaskedLinear`` and runs as two GEMM layers, the second one adding
+    the block's input in its epilogue."""
+
+
 def _relu_only(activation: Callable[[], nn.Module] | None) -> Callable[[], nn.Module]:
     """Validates the ``activation=`` constructor hook (name kept for history: ReLU is the default)."""
     if activation is None:
@@ -102,17 +108,48 @@ class _EngineMLP(nn.Sequential):
     gemm_mode = "auto"  # "auto" | "fp32" | "bf16x3" | "bf16x1"
 
     def _linears(self) -> list[nn.Module]:
-        return [m for m in self if hasattr(m, "weight")]
+        """Linear layers in execution order (residual blocks flattened)."""
+        out: list[nn.Module] = []
+        for m in self:
+            if isinstance(m, Residual):
+                out += [k for k in m if hasattr(k, "weight")]
+            elif hasattr(m, "weight"):
+                out.append(m)
+        return out
+
+    def _layer_flags(self) -> tuple[list[int], list[int]] | None:
+        """Per linear layer: the activation applied to its output (0 = none, else ZK_ACT_* with ReLU = 1) and
+        whether the input of the PREVIOUS linear layer is added to its output (second layer of a residual
+        block).  ``None`` for the plain pattern (activation after every layer but the last)."""
+        mods = list(self)
+        if not any(isinstance(m, Residual) for m in mods):
+            return None
+        acts: list[int] = []
+        res: list[int] = []
+        for j, m in enumerate(mods):
+            if isinstance(m, Residual):
+                inner = list(m)
+                if len(inner) != 3 or not hasattr(inner[0], "weight") or hasattr(inner[1], "weight") or not hasattr(inner[2], "weight"):
+                    raise NotImplementedError("zuko_b200: residual blocks other than Linear-activation-Linear are not implemented")
+                acts += [activation_code(inner[1]) or 1, 0]
+                res += [0, 1]
+            elif hasattr(m, "weight"):
+                nxt = mods[j + 1] if j + 1 < len(mods) else None
+                follows = nxt is not None and not hasattr(nxt, "weight") and not isinstance(nxt, Residual)
+                acts.append((activation_code(nxt) or 1) if follows else 0)
+                res.append(0)
+        return acts, res
 
     def _activation_code(self) -> int:
-        acts = [m for m in self if not hasattr(m, "weight")]
+        acts = [k for m in self for k in (m if isinstance(m, Residual) else [m]) if not hasattr(k, "weight")]
         codes = {activation_code(m) for m in acts}
         if len(codes) > 1:
             raise NotImplementedError("zuko_b200: a conditioner mixing different activations is not implemented")
         return codes.pop() if codes else E.ZK_ACT_RELU
 
     def _signature(self) -> tuple:
-        sig = [self.gemm_mode, self._activation_code()]
+        flags = self._layer_flags()
+        sig = [self.gemm_mode, self._activation_code(), None if flags is None else (tuple(flags[0]), tuple(flags[1]))]
         for m in self._linears():
             for t in (m.weight, m.bias, getattr(m, "mask", None)):
                 sig.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
@@ -141,8 +178,12 @@ class _EngineMLP(nn.Sequential):
                 mk = mask.detach().to(torch.uint8).contiguous()
                 keep.append(mk)
                 M[i] = mk.data_ptr()
-        desc = E.MlpDesc(n, dims, W, Bv, M, E.GEMM_MODES[self.gemm_mode], self._activation_code())
-        keep += [dims, W, Bv, M]
+        flags = self._layer_flags()
+        la = lr = None
+        if flags is not None:
+            la, lr = (ctypes.c_int * n)(*flags[0]), (ctypes.c_int * n)(*flags[1])
+        desc = E.MlpDesc(n, dims, W, Bv, M, E.GEMM_MODES[self.gemm_mode], self._activation_code(), la, lr)
+        keep += [dims, W, Bv, M, la, lr]
         return desc, keep
 
     def _handle(self) -> ctypes.c_void_p:
@@ -219,7 +260,7 @@ class MLP(_EngineMLP):
         self.in_features, self.out_features = in_features, out_features
 
 
-def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> list[BoolTensor]:
+def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int], blocks: bool = False):
     """Masks of the masked MLP realising ``adjacency`` (out, in): every output may only
     depend on the inputs its adjacency row allows.  Restates zuko/nn.py:270-293.
 
@@ -228,6 +269,10 @@ def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> l
     layer is assigned the class ``reachable[u mod #reachable]`` — cyclically over the classes
     with a non-empty dependency set; it listens to the units of the previous layer whose
     class precedes its own.  The output layer restores the original row multiplicity.
+
+    With ``blocks=True`` also returns, per depth, the square mask of the residual block that follows
+    that layer (zuko/nn.py:297-309): unit ``u`` may listen to unit ``v`` of the same layer when
+    ``class(v)`` precedes ``class(u)``.
     """
     adjacency = torch.as_tensor(adjacency, dtype=torch.bool)
     classes, inverse = torch.unique(adjacency, dim=0, return_inverse=True)
@@ -236,6 +281,7 @@ def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> l
     precedes = overlap == classes.sum(dim=-1)  # [i, j]: deps(j) ⊆ deps(i)
 
     masks: list[BoolTensor] = []
+    block_masks: list[BoolTensor | None] = []
     unit_class = None
     widths = [*hidden_features, adjacency.shape[0]]
     for depth, width in enumerate(widths):
@@ -248,13 +294,16 @@ def masked_mlp_masks(adjacency: BoolTensor, hidden_features: Sequence[int]) -> l
             masks.append(table[unit_class])
         else:
             masks.append(table[inverse])
-    return masks
+        # the block after the output layer reuses the last hidden layer's classes: the reference builds it
+        # (drawing its initial weights) and drops it again
+        block_masks.append(None if unit_class is None else precedes[unit_class, :][:, unit_class])
+    return (masks, block_masks) if blocks else masks
 
 
 class MaskedMLP(_EngineMLP):
     """Masked multi-layer perceptron whose Jacobian ``dy_i/dx_j`` is null wherever
-    ``adjacency[i, j]`` is False (zuko/nn.py:221-318).  ``residual=True`` is not implemented by the
-    engine; activations: see ``_ACTIVATION_CODES``."""
+    ``adjacency[i, j]`` is False (zuko/nn.py:221-318).  ``residual=True`` builds the reference's residual
+    blocks (:class:`Residual`); activations: see ``_ACTIVATION_CODES``."""
 
     def __init__(
         self,
@@ -264,11 +313,24 @@ class MaskedMLP(_EngineMLP):
         residual: bool = False,
     ) -> None:
         act = _relu_only(activation)
-        if residual:
-            raise NotImplementedError("zuko_b200: residual MaskedMLP blocks are outside the accelerated path (zuko/nn.py:297-309)")
         out_features, in_features = adjacency.shape
         layers: list[nn.Module] = []
-        for mask in masked_mlp_masks(adjacency, hidden_features):
-            layers += [MaskedLinear(adjacency=mask), act()]
-        super().__init__(*layers[:-1])
+        if residual:
+            if len(hidden_features) == 0:
+                raise ValueError("zuko_b200: residual=True needs at least one hidden layer")
+            masks, block_masks = masked_mlp_masks(adjacency, hidden_features, blocks=True)
+            for depth, (mask, block) in enumerate(zip(masks, block_masks, strict=True)):
+                # same construction order as zuko/nn.py:295-313, so that torch.manual_seed(s) yields the same
+                # tensors: a hidden layer whose mask is square is built and replaced by its residual block,
+                # and the block after the output layer is built and dropped
+                layers.append(MaskedLinear(adjacency=mask))
+                if 0 < depth < len(hidden_features) and mask.shape[0] == mask.shape[1]:
+                    layers.pop()
+                layers.append(Residual(MaskedLinear(adjacency=block), act(), MaskedLinear(adjacency=block)))
+            layers.pop()
+            super().__init__(*layers)
+        else:
+            for mask in masked_mlp_masks(adjacency, hidden_features):
+                layers += [MaskedLinear(adjacency=mask), act()]
+            super().__init__(*layers[:-1])
         self.in_features, self.out_features = in_features, out_features
