@@ -66,6 +66,11 @@ struct TcParams {
 // ---------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------
+// GENERAL_ACT = false: epilogue activation none / ReLU only (the hot instantiation — every BASELINE config);
+// true: any ZK_ACT_* through act_apply().  Two instantiations because the general switch, inlined into
+// the 32-wide unrolled epilogue, grows the kernel from 2.8 k to 16 k SASS lines and slowed the ReLU
+// path ~2x (instruction cache) when it was a run-time branch of one kernel.
+template <bool GENERAL_ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                  const TcParams p) {
@@ -195,8 +200,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c0 + j;
                     float f = __uint_as_float(r[j]) + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
-                    if (p.relu == 1) f = fmaxf(f, 0.f);
-                    else if (p.relu > 1) f = act_apply(f, p.relu);
+                    if constexpr (GENERAL_ACT) {
+                        if (p.relu == 1) f = fmaxf(f, 0.f);
+                        else if (p.relu > 1) f = act_apply(f, p.relu);
+                    } else {
+                        if (p.relu) f = fmaxf(f, 0.f);
+                    }
                     v[j] = (n < p.N) ? f : 0.f;  // padded columns feed the next layer as exact zeros
                 }
                 if (!row_ok) continue;
@@ -396,7 +405,8 @@ zk_status tc_pack(zk_mlp* m, int requested_mode) {
         ZK_TRY(make_plane_map(&pk->layers.back().mapW64, L.w, L.N, L.Kp, 64));
         if (i < m->n_linear - 1) pk->max_np = std::max(pk->max_np, pad64(L.N));
     }
-    ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     m->gemm_mode = (pk->n_terms == 3) ? ZK_GEMM_BF16X3 : ZK_GEMM_BF16X1;
     return ZK_OK;
 }
@@ -455,7 +465,8 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
         }
         const int64_t tiles = ceil_div(B, BM) * p.n_chunks;
         const int grid = (int)std::min<int64_t>(tiles, sms);
-        linear_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
+        if (p.relu > 1) linear_tc_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
+        else linear_tc_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
         ZK_TRY(check_launch("linear_tc_kernel"));
         a = p.out_planes;
     }
@@ -654,7 +665,8 @@ zk_status tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
     if (a.slice_m) ZK_REQUIRE(a.slice_m % BM == 0, "tc_gemm: slice_m must be a multiple of %d", BM);
     const int64_t tiles = ceil_div(a.M, BM) * p.n_chunks;
     const int grid = (int)std::min<int64_t>(tiles, sm_count());
-    linear_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(mapA, *a.mapW, p);
+    if (p.relu > 1) linear_tc_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, *a.mapW, p);
+    else linear_tc_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, *a.mapW, p);
     return check_launch("linear_tc_kernel");
 }
 
