@@ -427,7 +427,9 @@ int64_t flow_bwd_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes) {
         const int64_t mid = lo + (hi - lo + 1) / 2;
         if (flow_bwd_ws_for(f, mid) <= ws_bytes) lo = mid; else hi = mid - 1;
     }
-    if (lo >= 2048) lo = lo / 1024 * 1024;
+    // keep tiles aligned when that still fits (the batch-slice plan of the tensor-core wgrad makes the
+    // requirement only approximately monotone in the row count, so the rounded value is re-checked)
+    if (lo >= 2048 && flow_bwd_ws_for(f, lo / 1024 * 1024) <= ws_bytes) lo = lo / 1024 * 1024;
     return lo;
 }
 
@@ -536,7 +538,7 @@ int64_t flow_invbwd_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes
         const int64_t mid = lo + (hi - lo + 1) / 2;
         if (flow_invbwd_ws_for(f, mid) <= ws_bytes) lo = mid; else hi = mid - 1;
     }
-    if (lo >= 2048) lo = lo / 1024 * 1024;
+    if (lo >= 2048 && flow_invbwd_ws_for(f, lo / 1024 * 1024) <= ws_bytes) lo = lo / 1024 * 1024;
     return lo;
 }
 
