@@ -346,15 +346,34 @@ int zk_set_tc_backward(int on);
  * approximations, 0 = IEEE division + expf / logf.  Process-wide; returns the previous
  * value.  Both settings meet the 1e-5 parity bar on the BASELINE configs (tests/). */
 int zk_set_fast_math(int on);
-/* 1 (default): an autoregressive layer whose conditioner fits the fused kernel (hidden widths
- * equal, multiple of 64, <= 256; D + C <= 256; RQS with 8 / 16 bins or affine; tensor-core GEMM
- * mode) runs as ONE kernel — conditioner + bijector + ladj, activations and phi stay on chip.
+/* 1 (default): an autoregressive layer whose conditioner fits a fused kernel (hidden widths
+ * equal; multiple of 64 and <= 256 with D + C <= 256, or 384 / 512 with D + C <= 512; RQS with
+ * 8 / 16 bins or affine; tensor-core GEMM mode; ReLU, no residual blocks) runs as ONE kernel —
+ * conditioner + bijector + ladj, activations and phi stay on chip (nn.py:217-218,
+ * flows/autoregressive.py:207-215, transforms.py:554-567 in one launch).
  * 0: always one GEMM kernel per linear layer + the stand-alone bijector kernel.  Returns the
  * previous value. */
 int zk_set_fused_layers(int on);
 /* Profiling hook: a DEVICE buffer of >= 256 int64 that the fused layer kernel fills with clock64()
  * stamps of its pipeline events (CTA 0, third tile); NULL (default) disables it. */
 void zk_debug_timeline(long long* device_buffer);
+
+/* Host-only (no CUDA call): the issue schedule the wide fused kernel (hidden width 384 / 512) would
+ * walk for a conditioner with layer widths dims[0..n_linear] and HOST masks (bool bytes
+ * (dims[l+1], dims[l]) row-major, NULL = dense) — nn.py:270-293 builds those masks.  Writes two
+ * words per entry (flags, first weight row; bit layout in csrc/fused_wide.cu), the K blocks each
+ * layer reads (out_rd_mask[8], may be NULL) and the degree-sort permutations of the hidden layers
+ * concatenated (out_perm, may be NULL).  Returns the number of entries; -1 shape not supported,
+ * -2 the protocol dry run rejected the schedule, -3 max_items too small. */
+int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
+                           int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
+                           int* out_perm);
+/* Debugging aid of the wide fused kernel: every wait inside it is bounded (~2 s); a wait that
+ * expires reports its role, barrier and position in the schedule into pinned host memory and
+ * traps.  Copies up to n_words 32-bit words of that report into `out` (word 0 = number of
+ * reports, 8 words per (CTA of cluster 0, warp) from word 8); returns the number of words
+ * copied, 0 when no wide kernel was launched yet.  Readable after the context died. */
+int zk_debug_watchdog_read(uint32_t* out, int n_words);
 
 /* number of kernel launches issued by this library since load (bench evidence) */
 int64_t zk_launch_count(void);

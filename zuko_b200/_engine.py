@@ -106,6 +106,8 @@ _SIGNATURES = {
     "zk_set_fused_layers": (c_int, [c_int]),
     "zk_set_tc_backward": (c_int, [c_int]),
     "zk_debug_timeline": (None, [c_void_p]),
+    "zk_debug_watchdog_read": (c_int, [c_void_p, c_int]),
+    "zk_debug_wide_schedule": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "zk_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "zk_rqs_forward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_float, c_float, _P, c_int64, _P, c_int, _P]),
     "zk_rqs_inverse": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_float, c_float, _P, c_int64, _P]),

@@ -54,6 +54,18 @@ int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
 void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
+int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
+                           int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
+                           int* out_perm) {
+    return zk::wide_schedule_host(n_linear, dims, masks_host, univariate, bins, features, context, out_items, max_items,
+                                  out_rd_mask, out_perm);
+}
+int zk_debug_watchdog_read(uint32_t* out, int n_words) {
+    if (!zk::g_watch_host || !out || n_words <= 0) return 0;
+    const int n = n_words < 1024 ? n_words : 1024;
+    for (int i = 0; i < n; ++i) out[i] = ((volatile uint32_t*)zk::g_watch_host)[i];
+    return n;
+}
 
 zk_status zk_device_info(int* sm, int* major, int* minor) {
     int dev = 0;

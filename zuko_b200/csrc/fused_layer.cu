@@ -42,9 +42,7 @@
 #include <utility>
 #include <vector>
 
-#include "bijector_math.cuh"
-#include "fused_layer.cuh"
-#include "tc_common.cuh"
+#include "fused_common.cuh"
 
 namespace zk {
 
@@ -105,59 +103,6 @@ struct FusedParams {
     } while (0)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-
-// D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
-// compile-time loop: f(integral_constant<int, Start>), ..., f(integral_constant<int, Start + N - 1>)
-template <int Start, class F, int... I>
-__device__ __forceinline__ void for_range_impl(F& f, std::integer_sequence<int, I...>) {
-    (f(std::integral_constant<int, Start + I>{}), ...);
-}
-template <int Start, int N, class F>
-__device__ __forceinline__ void for_range(F& f) {
-    for_range_impl<Start>(f, std::make_integer_sequence<int, N>{});
-}
-
-// per-(UNI, K) chunking of the last layer: DPC dims per accumulator chunk, split between the two
-// sets of the owning pair as [0, DA) and [DA, DPC)
-template <int UNI, int KT>
-struct LastCfg;
-template <>
-struct LastCfg<ZK_UNI_RQS, 8> { static constexpr int P = 23, DPC = 4; };
-template <>
-struct LastCfg<ZK_UNI_RQS, 16> { static constexpr int P = 47, DPC = 2; };
-template <>
-struct LastCfg<ZK_UNI_AFFINE, 0> { static constexpr int P = 2, DPC = 64; };
 
 template <int UNI, int KT, bool FAST, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
@@ -662,7 +607,7 @@ zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, size_t smem,
 
 long long* g_timeline = nullptr;
 
-bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
+static bool fused_narrow_shape(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
     if (!pk || m->gemm_mode == ZK_GEMM_FP32) return false;
     if (m->act != 1 || !m->plain) return false;  // the hidden epilogue implements ReLU MLPs only
@@ -674,6 +619,13 @@ bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int
     if (D + C > 256 || m->dims[0] != D + C) return false;
     if (univariate == ZK_UNI_RQS) return bins == 8 || bins == 16;
     return univariate == ZK_UNI_AFFINE;
+}
+
+bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
+    if (fused_narrow_shape(m, univariate, bins, D, C)) return true;
+    const TcPack* pk = (const TcPack*)m->tc;  // wide shapes: only once the issue schedule passed its dry run
+    return fused_wide_shape(m, univariate, bins, D, C) && pk->wide.ready && pk->wide.uni == univariate &&
+           pk->wide.bins == bins && pk->wide.D == D && pk->wide.C == C;
 }
 
 namespace {
@@ -694,54 +646,66 @@ __global__ void permute_bias_kernel(const float* b, int N, const int* perm, floa
 }
 }  // namespace
 
-zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {
-    if (!fused_layer_supported(m, univariate, bins, D, C)) return ZK_OK;
+// Dependency degree of every hidden unit = number of network inputs it can see
+// (flows/autoregressive.py:121-124 + nn.py:270-293: units of a lower order class see fewer inputs);
+// sorting by degree makes the hidden -> hidden masks block lower-triangular.  Pure host code.
+void fused_degree_perm(const int* dims, int L, const std::vector<std::vector<uint8_t>>& Mk,
+                       std::vector<std::vector<int>>& perm) {
+    const int K0 = dims[0];
+    perm.assign(L - 1, {});  // perm[l][new] = old index of hidden layer l+1's units
+    // dependency sets as bit rows: dep[unit] = OR of the dep rows of the inputs it is connected to
+    const int W64 = (K0 + 63) / 64;
+    std::vector<uint64_t> prev, cur;
+    for (int l = 0; l < L - 1; ++l) {
+        const int K = dims[l], N = dims[l + 1];
+        cur.assign((size_t)N * W64, 0);
+        for (int n = 0; n < N; ++n) {
+            uint64_t* dn = &cur[(size_t)n * W64];
+            const uint8_t* mrow = &Mk[l][(size_t)n * K];
+            for (int k = 0; k < K; ++k) {
+                if (!mrow[k]) continue;
+                if (l == 0) dn[k >> 6] |= (uint64_t)1 << (k & 63);
+                else {
+                    const uint64_t* dk = &prev[(size_t)k * W64];
+                    for (int w = 0; w < W64; ++w) dn[w] |= dk[w];
+                }
+            }
+        }
+        std::vector<int> deg(N, 0);
+        for (int n = 0; n < N; ++n)
+            for (int w = 0; w < W64; ++w) deg[n] += __builtin_popcountll(cur[(size_t)n * W64 + w]);
+        perm[l].resize(N);
+        for (int n = 0; n < N; ++n) perm[l][n] = n;
+        std::stable_sort(perm[l].begin(), perm[l].end(), [&](int a, int b) { return deg[a] < deg[b]; });
+        prev.swap(cur);
+    }
+}
+
+// Masks to the host, hidden units sorted by dependency degree, permuted bf16 hi / lo planes and
+// biases on the device (shared by the narrow and the wide fused kernel).
+zk_status fused_host_prepare(zk_mlp* m, const uint8_t* const* mask_dev, FusedPack& f, FusedHostPrep& hp) {
     TcPack* pk = (TcPack*)m->tc;
-    FusedPack& f = pk->fused;
     const int L = m->n_linear;
-    const int H = m->dims[1];
-    const int CW = (H % 128 == 0) ? 128 : 64;
-    const int P = (univariate == ZK_UNI_RQS) ? 3 * bins - 1 : 2;
-    const int DPC = (univariate == ZK_UNI_RQS) ? (bins == 8 ? 4 : 2) : 64;
     // ---- host copies of the masks (dense layers: all ones) ----
-    std::vector<std::vector<uint8_t>> Mk(L);
+    std::vector<std::vector<uint8_t>>& Mk = hp.Mk;
+    Mk.assign(L, {});
     for (int l = 0; l < L; ++l) {
         const size_t n = (size_t)m->dims[l + 1] * m->dims[l];
         Mk[l].assign(n, 1);
         if (mask_dev && mask_dev[l]) ZK_CUDA(cudaMemcpy(Mk[l].data(), mask_dev[l], n, cudaMemcpyDeviceToHost));
     }
-    // ---- dependency degree of every hidden unit = number of network inputs it can see ----
-    // (flows/autoregressive.py:121-124 + nn.py:270-293: units of a lower order class see fewer
-    // inputs; sorting by degree makes hidden -> hidden masks block lower-triangular)
-    const int K0 = m->dims[0];
-    std::vector<std::vector<int>> perm(L - 1);  // perm[l][new] = old index of hidden layer l+1's units
-    std::vector<std::vector<std::vector<uint8_t>>> dep(L);  // dep[l][unit][input]
-    for (int l = 0; l < L - 1; ++l) {
-        const int K = m->dims[l], N = m->dims[l + 1];
-        dep[l].assign(N, std::vector<uint8_t>(K0, 0));
-        for (int n = 0; n < N; ++n)
-            for (int k = 0; k < K; ++k) {
-                if (!Mk[l][(size_t)n * K + k]) continue;
-                if (l == 0) dep[l][n][k] = 1;
-                else for (int i = 0; i < K0; ++i) dep[l][n][i] |= dep[l - 1][k][i];
-            }
-        std::vector<int> deg(N, 0);
-        for (int n = 0; n < N; ++n) for (int i = 0; i < K0; ++i) deg[n] += dep[l][n][i];
-        perm[l].resize(N);
-        for (int n = 0; n < N; ++n) perm[l][n] = n;
-        std::stable_sort(perm[l].begin(), perm[l].end(), [&](int a, int b) { return deg[a] < deg[b]; });
-    }
-    // ---- permuted planes, biases, tensor maps ----
+    fused_degree_perm(m->dims.data(), L, hp.Mk, hp.perm);
+    std::vector<std::vector<int>>& perm = hp.perm;
+    // ---- permuted planes and biases ----
     for (auto* q : f.w) cudaFree(q);
     for (auto* q : f.bias) cudaFree(q);
-    f.w.clear(); f.bias.clear(); f.map64.clear();
-    f.map64.resize(L);
+    f.w.clear(); f.bias.clear();
     std::vector<int*> dperm(L - 1, nullptr);
     zk_status st = ZK_OK;
     for (int l = 0; l < L - 1 && st == ZK_OK; ++l) {
         if (cudaMalloc((void**)&dperm[l], perm[l].size() * 4) != cudaSuccess ||
             cudaMemcpy(dperm[l], perm[l].data(), perm[l].size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
-            st = fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");
+            st = fail(ZK_ENOMEM, "fused_host_prepare: cudaMalloc failed");
     }
     for (int l = 0; l < L && st == ZK_OK; ++l) {
         const int K = m->dims[l], N = m->dims[l + 1], Kp = pk->layers[l].Kp;
@@ -749,7 +713,7 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
         float* b = nullptr;
         if (cudaMalloc((void**)&w, (size_t)2 * N * Kp * 2) != cudaSuccess || cudaMalloc((void**)&b, ((size_t)N + 4) * 4) != cudaSuccess) {
             cudaFree(w);
-            st = fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");
+            st = fail(ZK_ENOMEM, "fused_host_prepare: cudaMalloc failed");
             break;
         }
         f.w.push_back(w);
@@ -762,12 +726,29 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
         cudaMemsetAsync(b, 0, ((size_t)N + 4) * 4, 0);
         permute_bias_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, 0>>>(m->b[l], N, rp, b);
         st = check_launch("permute_bias_kernel");
-        if (st != ZK_OK) break;
-        st = make_plane_map(&f.map64[l], w, N, Kp, 64);
     }
-    if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "fused_layer_prepare: sync failed");
+    if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "fused_host_prepare: sync failed");
     for (int* q : dperm) cudaFree(q);
-    if (st != ZK_OK) return st;
+    return st;
+}
+
+zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {
+    if (fused_wide_shape(m, univariate, bins, D, C)) return fused_wide_prepare(m, mask_dev, univariate, bins, D, C);
+    if (!fused_narrow_shape(m, univariate, bins, D, C)) return ZK_OK;
+    TcPack* pk = (TcPack*)m->tc;
+    FusedPack& f = pk->fused;
+    const int L = m->n_linear;
+    const int H = m->dims[1];
+    const int CW = (H % 128 == 0) ? 128 : 64;
+    const int P = fused_p(univariate, bins);
+    const int DPC = fused_dpc(univariate, bins);
+    FusedHostPrep hp;
+    ZK_TRY(fused_host_prepare(m, mask_dev, f, hp));
+    const std::vector<std::vector<uint8_t>>& Mk = hp.Mk;
+    const std::vector<std::vector<int>>& perm = hp.perm;
+    f.map64.clear();
+    f.map64.resize(L);
+    for (int l = 0; l < L; ++l) ZK_TRY(make_plane_map(&f.map64[l], f.w[l], m->dims[l + 1], pk->layers[l].Kp, 64));
     // ---- which (chunk, K block) tiles of the permuted masked matrices are non-zero ----
     memset(f.kbmask, 0, sizeof(f.kbmask));
     for (int l = 0; l < L; ++l) {
@@ -839,7 +820,8 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
 
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t st) {
     const TcPack* pk = (const TcPack*)m->tc;
-    ZK_REQUIRE(pk && fused_layer_supported(m, a.univariate, a.bins, a.D, a.C), "fused layer: unsupported shape");
+    if (pk && fused_wide_shape(m, a.univariate, a.bins, a.D, a.C)) return launch_fused_wide(m, a, st);
+    ZK_REQUIRE(pk && fused_narrow_shape(m, a.univariate, a.bins, a.D, a.C), "fused layer: unsupported shape");
     ZK_REQUIRE(a.B < ((int64_t)1 << 31) - FM, "fused layer: batch too large for one launch");
     if (a.B == 0) return ZK_OK;
     FusedParams p;

@@ -27,6 +27,14 @@ bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int
 // map); `mask_dev` are the DEVICE mask pointers of zk_mlp_desc (may be null = dense).  No-op when
 // the shape is not supported by the fused kernel.
 zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C);
+// ---- wide variant (fused_wide.cu): hidden width 384 / 512 on CTA pairs (cta_group::2) ----
+// shape test only; the layer runs fused once fused_wide_prepare built a schedule that passed its dry run
+bool fused_wide_shape(const zk_mlp* m, int univariate, int bins, int D, int C);
+zk_status fused_wide_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C);
+zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
+int wide_schedule_host(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins, int D,
+                       int C, uint32_t* out_items, int max_items, uint32_t* out_rd_mask, int* out_perm);
+extern uint32_t* g_watch_host;  // watchdog report buffer of the wide kernel (pinned host memory) or null
 extern long long* g_timeline;  // device buffer of >= 256 stamps, or null (zk_debug_timeline)
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
 

@@ -363,6 +363,7 @@ void tc_destroy(zk_mlp* m) {
     for (auto* q : pk->fused.w) cudaFree(q);
     for (auto* q : pk->fused.bias) cudaFree(q);
     cudaFree(pk->fused.sched);
+    cudaFree(pk->wide.sched);
     delete pk;
     m->tc = nullptr;
 }

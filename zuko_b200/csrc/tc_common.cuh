@@ -141,12 +141,23 @@ struct FusedPack {
     uint32_t* sched = nullptr;      // device: MMA issue schedule of one tile, one entry per non-zero tile (owned)
     int n_items = 0;
 };
+// the wide fused kernel's pack (fused_wide.cu): it shares FusedPack's permuted planes / biases
+// (fused.w, fused.bias) and adds its own tensor maps and issue schedule
+struct WidePack {
+    bool ready = false;
+    int uni = 0, bins = 0, D = 0, C = 0;
+    std::vector<CUtensorMap> maps;  // per layer: box (64 x 64 x 1) hidden, (64 x N_LAST/2 x 1) output layer
+    uint2* sched = nullptr;         // device: one entry per non-zero (layer, chunk, K block) tile (owned)
+    int n_items = 0;
+    uint8_t rd_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per layer: K blocks of the A operand the layer reads
+};
 struct TcPack {
     std::vector<TcLayer> layers;
     std::vector<TcLayer> bwd;  // transposed weights (dgrad): N = in features, K = out features; built on first backward
     int n_terms = 3;
     int max_np = 0;  // widest padded hidden activation
     FusedPack fused;
+    WidePack wide;
 };
 
 inline int pad64(int v) { return (v + 63) / 64 * 64; }
