@@ -450,6 +450,57 @@ def test_cfg2_full_batch_properties(device):
     assert abs(total.item() - lp.double().sum().item()) <= 1e-9 * abs(total.item())
 
 
+def _full_batch_properties(device, name, D, C, block_rows, copies, oracle_rows=2048):
+    g = load(f"flow_{name}")
+    cpu_flow = build_flow(name, g)
+    flow = build_flow(name, g).to(device)
+    gen = torch.Generator().manual_seed(1234)
+    xb = torch.randn(block_rows, D, generator=gen)
+    cb = torch.randn(block_rows, C, generator=gen) if C else None
+    x = xb.repeat(copies, 1).to(device)
+    c = None if cb is None else cb.repeat(copies, 1).to(device)
+    n0 = E.lib().zk_launch_count()
+    lp, total = flow(c).log_prob_and_sum(x)
+    assert lp.shape == (block_rows * copies,)
+    ref = O.flowspec_from_module(cpu_flow).log_prob(xb[:oracle_rows].numpy(), None if cb is None else cb[:oracle_rows].numpy())
+    assert rel_err(cpu(lp[:oracle_rows]), ref) < 1e-5
+    blocks = lp.reshape(copies, block_rows)
+    assert all(torch.equal(blocks[0], blocks[i]) for i in range(1, copies))
+    assert abs(total.item() - lp.double().sum().item()) <= 1e-9 * abs(total.item())
+    return flow, x, c
+
+
+def test_cfg3_full_batch_properties(device):
+    """BASELINE config 3 at its full size, B = 2^20 (MAF(32, T8, [512]^4): the wide fused kernel):
+    oracle parity on the first rows, block-for-block bit reproducibility across the batch (tiling /
+    chunking independence), and the fused sum against the host double sum."""
+    _full_batch_properties(device, "cfg3_maf", 32, 0, 1 << 16, 16)
+
+
+def test_cfg5_full_shard_properties(device):
+    """BASELINE config 5 at one GPU's share of the 2^24-row batch, B = 2^21
+    (NSF(64, 16, T8, K16, [512]^3): wide fused kernel, 47 parameters per dim)."""
+    _full_batch_properties(device, "cfg5_nsf", 64, 16, 1 << 17, 16, oracle_rows=1024)
+
+
+def test_cfg4_round_trip_2_20(device):
+    """BASELINE config 4 at its full size: t(t.inv(z)) ~ z for N = 2^20 draws (the reference's own
+    property, atol 1e-4, tests/test_flows.py:57-61), and the first rows against the oracle's inverse."""
+    g = load("flow_cfg4_nsf")
+    cpu_flow = build_flow("cfg4_nsf", g)
+    flow = build_flow("cfg4_nsf", g).to(device)
+    gen = torch.Generator().manual_seed(77)
+    z = torch.randn(1 << 20, 64, generator=gen)
+    t = flow(None).transform
+    zd = z.to(device)
+    x = t.inv(zd)
+    assert torch.isfinite(x).all()
+    back = t(x)
+    assert torch.allclose(back, zd, atol=1e-4)
+    ref = O.flowspec_from_module(cpu_flow).inverse(z[:512].numpy(), None)
+    assert rel_err(cpu(x[:512]), ref) < 1e-5
+
+
 def test_cfg2_round_trip_2_18(device):
     """inv(t(x)) ~ x at 2^18 rows (the reference's atol 1e-4, tests/test_flows.py:57-61)."""
     g = load("flow_cfg2_nsf")

@@ -100,7 +100,14 @@ FUSED_FLOWS = {
     "nsf7_k16_h128": lambda: zuko.flows.NSF(7, 0, transforms=2, bins=16, hidden_features=[128, 128]),  # odd D with DPC = 2
     "maf32_h256": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[256] * 2),              # affine, 64 dims / chunk
     "maf70c100_h128": lambda: zuko.flows.MAF(70, 100, transforms=2, hidden_features=[128] * 2),        # K0 = 170 -> 3 K blocks, 2 affine chunks
+    # ---- wide kernel (fused_wide.cu): hidden width 384 / 512 on CTA pairs, in-place descending schedule ----
+    "maf32_h512x4": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[512] * 4),            # cfg3 shape
+    "nsf64c16_k16_h512": lambda: zuko.flows.NSF(64, 16, transforms=2, bins=16, hidden_features=[512] * 3),  # cfg5 shape
+    "nsf24_k8_h512": lambda: zuko.flows.NSF(24, 0, transforms=2, bins=8, hidden_features=[512, 512]),  # degree classes not aligned to chunks
+    "nsf10c3_h384": lambda: zuko.flows.NSF(10, 3, transforms=3, bins=8, hidden_features=[384, 384]),   # 3 chunks / 6 K blocks
+    "maf100c28_h512": lambda: zuko.flows.MAF(100, 28, transforms=2, hidden_features=[512] * 2),        # K0 = 128, 2 affine chunks
 }
+WIDE_FLOWS = ["maf32_h512x4", "nsf64c16_k16_h512", "nsf24_k8_h512", "nsf10c3_h384", "maf100c28_h512"]
 
 
 @pytest.fixture
@@ -144,6 +151,26 @@ def test_fused_layer_matches_unfused_and_oracle(device, unfused, name, B):
     assert torch.allclose(lp_f, lp_u, rtol=2e-6, atol=2e-5)
     assert torch.allclose(z_f, z_u, rtol=1e-5, atol=1e-5)
     assert torch.allclose(ladj_f, ladj_u, rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", WIDE_FLOWS)
+def test_wide_layers_run_as_one_kernel_each(device, name):
+    """Hidden width 384 / 512: ONE launch per flow layer (no per-layer GEMM fallback), and a ragged
+    batch (partial pair tile, odd number of tiles) gives the rows of the full batch bit for bit."""
+    torch.manual_seed(5)
+    flow = FUSED_FLOWS[name]().to(device)
+    D = flow.base.loc.shape[0]
+    C = flow.transform.transforms[0].context
+    B = 256 * 3 + 129
+    x = torch.randn(B, D, device=device)
+    c = torch.randn(B, C, device=device) if C else None
+    with torch.no_grad():
+        lp = flow(c).log_prob(x)  # packs
+        n0 = E.lib().zk_launch_count()
+        lp = flow(c).log_prob(x)
+        assert E.lib().zk_launch_count() - n0 == len(flow.transform.transforms)
+        lp_part = flow(None if c is None else c[:300]).log_prob(x[:300])
+    assert torch.equal(lp[:300], lp_part)
 
 
 def test_fused_layer_broadcast_context_and_launch_count(device):

@@ -156,14 +156,18 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
     return r;
 }
+// Arrive on a barrier of the LEADER CTA.  Default semantics (.release.cta), as CUTLASS's
+// ClusterBarrier::arrive(cta_id): what the arrival publishes lives in THIS CTA's tensor / shared
+// memory and was completed before it (tcgen05.wait, fence.proxy.async); `.release.cluster` compiles to
+// MEMBAR.ALL.GPU in front of every arrive (~2000 cycles each: profiles/r02_wide_timeline_*_v1.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
