@@ -12,7 +12,11 @@ scaling) and ONE NCCL all-reduce of {sum log p, count} closes the step.
 
 Printed JSON (one line, rank 0): see the contract in the task description; additionally
 ``roofline`` (dominant kernel), ``kernels`` (every kernel class timed in isolation with CUDA
-events), ``cpu_baseline`` and ``parity``.
+events), ``cpu_baseline``, ``parity`` and ``configs``: the other BASELINE.json configurations
+(cfg3 MAF [512]^4 log_prob 2^20, cfg4 NSF(64, K16) rsample 2^20, cfg5 NSF(64, 16, K16, [512]^3)
+log_prob with 2^21 rows per GPU = 2^24 over 8 GPUs), each timed with CUDA events after warm-up,
+with its own roofline entry and oracle parity on a small slice.  Under torchrun every rank runs
+cfg5 on its own 2^21-row shard, so the scaling record carries the north-star config's 1 -> 8 curve.
 """
 
 from __future__ import annotations
@@ -31,6 +35,10 @@ sys.path.insert(0, str(ROOT))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
+
+# the CPU arm pins its OpenMP threads (must be in the environment before the runtime starts)
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
 
 METRIC = "nsf_log_prob_samples_per_sec"
 UNIT = "samples/s"
@@ -218,34 +226,181 @@ def cpu_reference_rate(rows: int, repeats: int = 1):
     return rows / best, best, threads
 
 
+CPU_ROWS = 1 << 19  # the bounded CPU sample of the workload: the same in the reference arm and in cpu_baseline
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # one step = a bounded sample of the workload, sized for ~4 s per step on this host
-    rate0, _, threads = cpu_reference_rate(1 << 15)  # also the warm-up
-    rows = args.cpu_rows
-    if not rows:  # refine once: the rate grows with the sample size on a many-core host
-        rows = min(1 << 22, 1 << max(15, int(rate0 * 4.0).bit_length() - 1))
-        rate1, sec1, _ = cpu_reference_rate(rows)
-        if sec1 < 2.0:
-            rows = min(1 << 22, 1 << max(15, int(rate1 * 4.0).bit_length() - 1))
+    # one step = one pass of the oracle port over a FIXED bounded sample of the workload (the same
+    # rows whatever N / steps are, so that the BENCH and SCALE reference arms agree); threads pinned
+    # (OMP_PROC_BIND=close, OMP_PLACES=cores, set at import)
+    rows = args.cpu_rows or CPU_ROWS
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_rate(min(rows, 1 << 16))
     times = []
+    threads = 1
     for _ in range(args.steps):
-        rate, sec, threads = cpu_reference_rate(rows)
+        _, sec, threads = cpu_reference_rate(rows)
         times.append(sec)
-    sec = float(np.mean(times))
+    sec = float(np.median(times))
     rate = rows / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": rows, "note": "oracle port (plain C, OpenMP) of the reference's CPU path; bounded sample per step"},
+        "config": {"workload": WORKLOAD, "rows_per_step": rows, "note": "oracle port (plain C, OpenMP, threads pinned) of the reference's CPU path; fixed bounded sample per step, median step time",
+                   "step_seconds_min_max": [float(min(times)), float(max(times))]},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{rows} rows of the workload per step"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# the other BASELINE.json configurations (configs[2..4])
+# --------------------------------------------------------------------------- #
+
+OTHER_CONFIGS = [
+    {"name": "cfg3", "workload": "MAF(features=32, transforms=8, hidden=[512]*4) log_prob, batch 2^20",
+     "kind": "maf", "D": 32, "C": 0, "T": 8, "K": 0, "H": [512] * 4, "op": "log_prob", "rows": 1 << 20},
+    {"name": "cfg4", "workload": "NSF(features=64, bins=16, transforms=8) rsample((2^20,)) inverse path",
+     "kind": "nsf", "D": 64, "C": 0, "T": 8, "K": 16, "H": [64, 64], "op": "rsample", "rows": 1 << 20},
+    {"name": "cfg5", "workload": "NSF(features=64, context=16, transforms=8, bins=16, hidden=[512]*3) log_prob, 2^21 rows per GPU (2^24 over 8)",
+     "kind": "nsf", "D": 64, "C": 16, "T": 8, "K": 16, "H": [512] * 3, "op": "log_prob", "rows": 1 << 21},
+]  # fmt: skip
+
+
+def build_config_model(cfg):
+    import zuko_b200 as zuko
+
+    torch.manual_seed(0)
+    if cfg["kind"] == "maf":
+        return zuko.flows.MAF(cfg["D"], cfg["C"], transforms=cfg["T"], hidden_features=cfg["H"]).eval()
+    return zuko.flows.NSF(cfg["D"], cfg["C"], transforms=cfg["T"], bins=cfg["K"], hidden_features=cfg["H"]).eval()
+
+
+def tensor_peak(peaks: dict, clocks: dict) -> tuple[float, str]:
+    """Burst peak when the run held the maximum SM clock without a power cap (a kernel-bound step of
+    milliseconds), else the sustained figure (MEASURED_PEAKS.json holds both)."""
+    sm, smax = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
+    capped = "sw_power_cap" in (clocks.get("reasons") or [])
+    if sm and smax and sm >= 0.98 * smax and not capped:
+        return peaks["bf16_tflops"], "burst"
+    return peaks["bf16_tflops_sustained"], "sustained"
+
+
+def fused_info(flow) -> dict:
+    """Which kernel runs the flow's layers and the tensor-core work its schedules ISSUE (non-zero
+    tiles only, all split terms) next to the dense work of nn.py:218 — from the packs."""
+    import ctypes
+
+    from zuko_b200 import _engine as E
+
+    kinds, issued, dense, entries = [], 0.0, 0.0, 0
+    for layer in flow.transform.transforms:
+        out = (ctypes.c_double * 4)()
+        k = E.lib().zk_layer_fused_info(layer._zk_layer(), out)
+        kinds.append({0: "per-layer GEMM kernels", 1: "fused_layer_kernel", 2: "fused_wide_kernel"}.get(k, "?"))
+        issued += out[2]
+        dense += out[3]
+        entries += int(out[1])
+    return {"kernel": sorted(set(kinds)), "dense_macs_per_row": dense, "issued_macs_per_row": issued, "schedule_entries": entries}
+
+
+def time_config(cfg, dev, rank, world, peaks, steps, nvml=None) -> dict:
+    """One BASELINE configuration: warm-up, `steps` timed steps (CUDA events, max over ranks), oracle
+    parity on a small slice (rank 0), roofline entry.  Inputs live in HBM; they rotate over buffers
+    that together exceed the 126 MB L2."""
+    import torch.distributed as dist
+
+    from zuko_b200 import _engine as E
+    from zuko_b200.dist import NllRing
+
+    D, C, rows = cfg["D"], cfg["C"], cfg["rows"]
+    flow_cpu = build_config_model(cfg)
+    flow = build_config_model(cfg).to(dev)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    nbuf = max(1, min(4, -(-(160 << 20) // (rows * (D + C) * 4))))  # > 126 MB in rotation
+    xs = [torch.randn(rows, D, generator=g, device=dev) for _ in range(nbuf)]
+    cs = [torch.randn(rows, C, generator=g, device=dev) for _ in range(nbuf)] if C else [None] * nbuf
+    ring = NllRing(dev, slots=32)
+    with torch.no_grad():
+        if cfg["op"] == "log_prob":
+            def step(i):
+                return flow(cs[i % nbuf]).log_prob_and_sum(xs[i % nbuf], sum_out=ring.slot(rows))[0]
+        else:  # rsample: z ~ N(0, I) supplied in HBM (RNG parity is not attempted, SURVEY §8c), x = transform.inv(z)
+            t = flow(None).transform
+            def step(i):
+                return t.inv(xs[i % nbuf])
+        parity = None
+        if rank == 0:
+            from oracle import oracle
+
+            spec = oracle.flowspec_from_module(flow_cpu)
+            n = 1024 if cfg["op"] == "log_prob" else 128
+            xh = xs[0][:n].cpu().numpy()
+            ch = None if cs[0] is None else cs[0][:n].cpu().numpy()
+            if cfg["op"] == "log_prob":
+                ours = flow(None if cs[0] is None else cs[0][:n]).log_prob(xs[0][:n]).cpu().numpy().astype(np.float64)
+                ref = spec.log_prob(xh, ch)
+            else:
+                ours = flow(None).transform.inv(xs[0][:n]).cpu().numpy().astype(np.float64)
+                ref = spec.inverse(xh, None)
+            parity = {"rows": n, "max_rel_err_vs_fp64_oracle": float(np.max(np.abs(ours - ref) / np.maximum(np.abs(ref), 1.0)))}
+        for i in range(3):
+            step(i)
+        ring.means()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = ClockSampler(dev.index or 0)
+        clk._nvml = nvml
+        n0 = E.lib().zk_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with clk:
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(steps):
+                step(i)
+            means = ring.means()  # the collective(s) of the mean NLL close the timed region
+            e1.record()
+            torch.cuda.synchronize()
+        launches = E.lib().zk_launch_count() - n0
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_per_step = ms.item() / steps
+    clocks = clk.summary()
+    out = {"name": cfg["name"], "workload": cfg["workload"], "rows_per_gpu": rows, "value": world * rows / (ms_per_step * 1e-3),
+           "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "gpu_launches": int(launches), "parity": parity, "clocks": clocks,
+           "l2": f"inputs rotate over {nbuf} buffer(s) of {rows * (D + C) * 4 >> 20} MB"}  # fmt: skip
+    if cfg["op"] == "log_prob":
+        info = fused_info(flow)
+        flops = 2.0 * info["dense_macs_per_row"] * rows
+        peak, kind = tensor_peak(peaks, clocks)
+        tf = flops / (ms_per_step * 1e-3) / 1e12
+        out["mean_nll"] = float(means[-1].item()) if means.numel() else None
+        out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_kind": kind,
+                           "kernel": info["kernel"], "algorithmic_flops_per_step": flops, "issued_flops_per_step": 2.0 * info["issued_macs_per_row"] * rows,
+                           "frac_issued": 2.0 * info["issued_macs_per_row"] * rows / (ms_per_step * 1e-3) / 1e12 / peak,
+                           "traffic": None, "algorithmic_hbm_bytes": 4.0 * (D + C + 1) * rows}  # fmt: skip
+    else:
+        # every weight of the masked conditioner is visited once per sample (ar_inverse.cu): 2 FLOP per
+        # non-zero weight; roofline = fp32 FMA pipe, 148 SMs x 128 lanes x 2 x SM clock (nominal)
+        nnz = sum(float(m.mask.sum()) for layer in flow_cpu.transform.transforms for m in layer.hyper if hasattr(m, "mask"))
+        flops = 2.0 * nnz * rows
+        smax = clocks.get("sm_max_mhz") or 1965.0
+        peak = 148 * 128 * 2 * smax * 1e6 / 1e12
+        tf = flops / (ms_per_step * 1e-3) / 1e12
+        out["roofline"] = {"bound": "fma", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_kind": "nominal fp32 FMA (148 SMs x 128 lanes x 2 x max SM clock)",
+                           "kernel": ["ar_inverse_kernel<RQS,16>"], "algorithmic_flops_per_step": flops, "traffic": None,
+                           "algorithmic_hbm_bytes": 4.0 * 2 * D * rows}  # fmt: skip
+    del xs, cs, flow
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- #
@@ -280,14 +435,15 @@ def run_ours(args) -> None:
     cs_host = [torch.randn(B, C, generator=g).pin_memory() for _ in range(NBUF)]
     xs = [t.to(dev) for t in xs_host]
     cs = [t.to(dev) for t in cs_host]
-    red = torch.zeros(2, dtype=torch.float64, device=dev)
+    from zuko_b200.dist import NllRing
 
-    from zuko_b200.dist import mean_nll
+    # the mean-NLL collective is off the critical path: the engine writes each step's sum log p into a
+    # ring slot; one asynchronous all-reduce per bank of 32 steps runs on a side stream
+    ring = NllRing(dev, slots=32)
 
     def step(i: int):
         d = flow(cs[i % NBUF])
-        lp, total = d.log_prob_and_sum(xs[i % NBUF])
-        red[0] = mean_nll(total, B)  # ONE collective over {sum log p, count} when world > 1
+        lp, _ = d.log_prob_and_sum(xs[i % NBUF], sum_out=ring.slot(B))
         return lp
 
     with torch.no_grad():
@@ -309,6 +465,7 @@ def run_ours(args) -> None:
         warm_steps = max(args.warmup, 3, 50)
         for i in range(warm_steps):
             step(i)
+        ring.means()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -319,6 +476,7 @@ def run_ours(args) -> None:
             e0.record()
             for i in range(args.steps):
                 step(i)
+            nll_means = ring.means()  # waits for the outstanding mean-NLL collectives: inside the timed region
             e1.record()
             torch.cuda.synchronize()
         if world > 1:
@@ -329,7 +487,7 @@ def run_ours(args) -> None:
         launches = E.lib().zk_launch_count() - launches0
         ms_per_step = elapsed_ms.item() / args.steps
         value = world * B / (ms_per_step * 1e-3)
-        nll_value = red[0].item()
+        nll_value = float(nll_means[-1].item())
 
         # ---- end to end through the public API with HOST buffers (H2D + compute + D2H per step)
         fc = flow(cs[0])._flow_call()[0]
@@ -359,27 +517,44 @@ def run_ours(args) -> None:
 
         # ---- per-kernel timing in isolation (CUDA events), rank 0
         kernels, roofline = [], None
+        peak_tf, peak_kind = tensor_peak(peaks, clk.summary())
         if rank == 0:
             try:
-                kernels = time_kernels(flow, xs[0], cs[0], dev, peaks, iters=max(3, min(args.steps, 10)))
+                kernels = time_kernels(flow, xs[0], cs[0], dev, peaks, iters=max(3, min(args.steps, 10)), peak_tf=peak_tf, peak_kind=peak_kind)
                 dom = max((k for k in kernels if k["in_step"]), key=lambda k: k["ms_per_step"])
                 roofline = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
                 roofline["kernel"] = dom["name"]
                 roofline["peak_source"] = peaks["source"]
+                roofline["peak_kind"] = dom.get("peak_kind")
+                roofline["traffic_captured_at"] = dom.get("traffic_captured_at")
             except Exception as e:  # noqa: BLE001
                 kernels, roofline = [], {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- the other BASELINE configurations: N = 1 all three, N > 1 the north-star config (cfg5) on every rank
+    configs = []
+    if not args.no_configs:
+        del xs, cs
+        torch.cuda.empty_cache()
+        for cfg in OTHER_CONFIGS:
+            if world > 1 and cfg["name"] != "cfg5":
+                continue
+            try:
+                r = time_config(cfg, dev, rank, world, peaks, steps=max(3, min(args.steps, 10)), nvml=getattr(clk, "_nvml", None))
+            except Exception as e:  # noqa: BLE001
+                r = {"name": cfg["name"], "workload": cfg["workload"], "error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+            configs.append(r)
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                if args.cpu_rows:
-                    rate, sec, threads = cpu_reference_rate(args.cpu_rows)
-                    rows = args.cpu_rows
-                else:
-                    rate, sec, threads, rows = cpu_reference_adaptive(12.0)
+                rows = args.cpu_rows or CPU_ROWS
+                cpu_reference_rate(min(rows, 1 << 16))  # warm-up
+                rate, sec, threads = cpu_reference_rate(rows, repeats=3)
                 cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                       "sample": f"{rows} rows of the workload, oracle fp32 C port with OpenMP, {sec:.1f} s"}  # fmt: skip
+                       "sample": f"{rows} rows of the workload, oracle fp32 C port with OpenMP (threads pinned), best of 3, {sec:.1f} s"}  # fmt: skip
             except Exception as e:  # noqa: BLE001
                 cpu = {"error": f"{type(e).__name__}: {e}"[:300]}
         line = {
@@ -391,7 +566,7 @@ def run_ours(args) -> None:
             "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4, "d2h_bytes_per_step": B * 4,
                                              "steps": e2e_steps, "api": "FlowCall.log_prob_host -> zk_flow_log_prob_host (pinned host buffers)"},
             "gpu_launches": int(launches), "mean_nll": nll_value, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "parity": parity, "training_step": training,
+            "cpu_baseline": cpu, "parity": parity, "training_step": training, "configs": configs,
         }  # fmt: skip
         print(json.dumps(line))
     if world > 1:
@@ -436,7 +611,7 @@ def ncu_traffic() -> dict:
     return json.loads(f.read_text()) if f.exists() else {}
 
 
-def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
+def time_kernels(flow, x, c, dev, peaks, iters: int, peak_tf: float | None = None, peak_kind: str = "sustained") -> list[dict]:
     """Times each kernel class of one flow layer in isolation through the C-ABI entry points
     (CUDA events on the current stream) and converts to roofline terms.  Algorithmic bytes /
     FLOPs per SURVEY §8d; a step launches each of them T = 4 times (once per flow layer)."""
@@ -470,6 +645,9 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     fused_bytes = 4.0 * (D + C + D + 1) * B    # fused layer: x, c in; y, ladj out
     out = []
     traffic = ncu_traffic()
+    peak_tf = peak_tf or peaks["bf16_tflops_sustained"]
+    info = fused_info(flow)
+    issued = 2.0 * info["issued_macs_per_row"] / T * B  # one flow layer, from the pack's tile table
     n0 = L.zk_launch_count()
     fused()
     is_fused = (L.zk_launch_count() - n0) == 1
@@ -478,9 +656,10 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
         t = cuda_time_ms(fused, iters)
         tf = flops / (t * 1e-3) / 1e12
         out.append({"name": "fused_layer_kernel<RQS,8> (conditioner 24-256-256-256-368 on tcgen05 + RQS + ladj), one flow layer",
-                    "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": tf / peaks["bf16_tflops_sustained"], "traffic": traffic.get("fused_layer_kernel"), "ms_per_launch": t, "ms_per_step": t * T,
-                    "algorithmic_flops": flops, "issued_flops": 3 * flops, "frac_issued": 3 * tf / peaks["bf16_tflops_sustained"],
+                    "bound": "tensor", "achieved": tf, "peak": peak_tf, "peak_kind": peak_kind, "unit": "TFLOP/s",
+                    "frac": tf / peak_tf, "traffic": traffic.get("fused_layer_kernel"), "traffic_captured_at": traffic.get("git_sha"),
+                    "ms_per_launch": t, "ms_per_step": t * T,
+                    "algorithmic_flops": flops, "issued_flops": issued, "frac_issued": issued / (t * 1e-3) / 1e12 / peak_tf,
                     "algorithmic_hbm_bytes": fused_bytes, "in_step": True})  # fmt: skip
     prev = L.zk_set_fused_layers(0)
     try:
@@ -495,10 +674,11 @@ def time_kernels(flow, x, c, dev, peaks, iters: int) -> list[dict]:
     gbs = rqs_bytes / (t_rqs * 1e-3) / 1e9
     out += [
         {"name": "unfused conditioner: split_input + 4 x linear_tc_kernel (24-256-256-256-368), one flow layer", "bound": "tensor",
-         "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
-         "traffic": traffic.get("linear_tc_kernel_stack"), "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops, "in_step": not is_fused},
+         "achieved": tf, "peak": peak_tf, "peak_kind": peak_kind, "unit": "TFLOP/s", "frac": tf / peak_tf,
+         "traffic": traffic.get("linear_tc_kernel_stack"), "traffic_captured_at": traffic.get("git_sha"), "ms_per_launch": t_mlp, "ms_per_step": t_mlp * T, "algorithmic_flops": flops, "in_step": not is_fused},
         {"name": "uni_kernel<RQS,8> stand-alone fused RQS + ladj (phi in HBM), one flow layer", "bound": "hbm", "achieved": gbs,
-         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("uni_kernel"), "ms_per_launch": t_rqs,
+         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("uni_kernel"),
+         "traffic_captured_at": traffic.get("git_sha"), "ms_per_launch": t_rqs,
          "ms_per_step": t_rqs * T, "algorithmic_bytes": rqs_bytes, "in_step": not is_fused},
     ]  # fmt: skip
     return out
@@ -511,9 +691,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
-    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = size it to ~12 s)")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = 2^19)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training-step", action="store_true", help="skip the forward+backward timing (extra object)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 entries of the line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -198,6 +198,12 @@ typedef struct {
 zk_status zk_layer_create(const zk_layer_desc* desc, zk_layer** out);
 zk_status zk_layer_destroy(zk_layer* layer);
 size_t zk_layer_workspace_bytes(const zk_layer* layer, int64_t B);
+/* Bench bookkeeping: which kernel runs an autoregressive layer's forward (flows/autoregressive.py:
+ * 207-215) and how much tensor-core work its issue schedule holds.  Returns 0 = per-layer GEMM
+ * kernels, 1 = fused layer kernel, 2 = wide fused layer kernel (CTA pairs); out[0] = the same,
+ * out[1] = schedule entries per tile, out[2] = MACs ISSUED per sample row (non-zero tiles only, all
+ * split-bf16 terms), out[3] = dense MACs per sample row (what nn.py:218 executes). */
+int zk_layer_fused_info(const zk_layer* layer, double* out);
 /* t(c).call_and_ladj(x): y (B, D), ladj (B) summed over the event dim; y must not alias x. */
 zk_status zk_layer_forward(const zk_layer* layer, const float* x, int64_t ldx, const float* c,
                            int64_t ldc, int64_t B, float* y, int64_t ldy, float* ladj,

@@ -20,6 +20,9 @@
  * torch/... for the installed torch 2.11.
  */
 
+#ifndef ZO_RB
+#define ZO_RB 8 /* rows per block of zo_linear */
+#endif
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 #define FN(name) CAT(name, SUFFIX)
@@ -45,20 +48,31 @@ void FN(zo_linear)(const REAL* x, int64_t ldx, int dx, const REAL* c, int64_t ld
             const int64_t k = (int64_t)o * in + i;
             Wt[(int64_t)i * out + o] = (mask && !mask[k]) ? (REAL)0 : W[k];
         }
+    /* ZO_RB rows share every weight row while it sits in L1 (the per-row loop streamed the whole
+     * matrix from L2 once per sample); each output element still accumulates over the inputs in
+     * index order, so the results are bit-identical to the row-at-a-time loop. */
 #pragma omp parallel for schedule(static)
-    for (int64_t r = 0; r < B; ++r) {
-        const REAL* xr = x + r * ldx;
-        const REAL* cr = c ? c + r * ldc : NULL;
-        REAL* __restrict__ yr = y + r * ldy;
-        for (int o = 0; o < out; ++o) yr[o] = 0;
-        for (int i = 0; i < in; ++i) {
-            const REAL xv = (i < dx) ? xr[i] : cr[i - dx];
-            const REAL* __restrict__ w = Wt + (int64_t)i * out;
-            for (int o = 0; o < out; ++o) yr[o] += xv * w[o];
+    for (int64_t r0 = 0; r0 < B; r0 += ZO_RB) {
+        const int nr = (int)((B - r0 < ZO_RB) ? (B - r0) : ZO_RB);
+        for (int j = 0; j < nr; ++j) {
+            REAL* __restrict__ yr = y + (r0 + j) * ldy;
+            for (int o = 0; o < out; ++o) yr[o] = 0;
         }
-        for (int o = 0; o < out; ++o) {
-            REAL v = yr[o] + (bias ? bias[o] : (REAL)0);
-            yr[o] = (relu && v < 0) ? (REAL)0 : v;
+        for (int i = 0; i < in; ++i) {
+            const REAL* __restrict__ w = Wt + (int64_t)i * out;
+            for (int j = 0; j < nr; ++j) {
+                const int64_t r = r0 + j;
+                const REAL xv = (i < dx) ? x[r * ldx + i] : c[r * ldc + (i - dx)];
+                REAL* __restrict__ yr = y + r * ldy;
+                for (int o = 0; o < out; ++o) yr[o] += xv * w[o];
+            }
+        }
+        for (int j = 0; j < nr; ++j) {
+            REAL* __restrict__ yr = y + (r0 + j) * ldy;
+            for (int o = 0; o < out; ++o) {
+                REAL v = yr[o] + (bias ? bias[o] : (REAL)0);
+                yr[o] = (relu && v < 0) ? (REAL)0 : v;
+            }
         }
     }
     free(Wt);

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from cases import build_flow, load
-from zuko_b200.dist import all_reduce_gradients, mean_nll, shard_rows
+from zuko_b200.dist import NllRing, all_reduce_gradients, mean_nll, shard_rows
 
 
 def test_shard_rows_partition():
@@ -60,6 +60,44 @@ def test_mean_nll_allreduce_gloo_world2():
     expect = -float(np.mean(g["log_prob64"]))
     assert got[0] == got[1]  # every rank holds the same reduced scalar
     assert abs(got[0] - expect) < 1e-9 * abs(expect)
+
+
+def _ring_worker(rank: int, world: int, port: int, out):
+    """Seven steps through a 3-slot ring (two banks, so banks are rewritten while the previous
+    reduction of the other bank is in flight): every step's global mean NLL, in order."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ring = NllRing("cpu", slots=3)
+        for step in range(7):
+            rows = 10 + rank + step  # ragged and changing counts
+            ring.slot(rows).fill_(-(step + 1.0) * rows * (rank + 1))  # the engine writes sum log p here
+        out[rank] = ring.means().tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nll_ring_gloo_world2():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_ring_worker, args=(2, port, out), nprocs=2, join=True)
+        got = dict(out)
+    expect = []
+    for step in range(7):
+        rows = [10 + r + step for r in range(2)]
+        sums = [-(step + 1.0) * rows[r] * (r + 1) for r in range(2)]
+        expect.append(-sum(sums) / sum(rows))
+    assert got[0] == got[1]
+    assert np.allclose(got[0], expect, rtol=1e-12)
+
+
+def test_nll_ring_without_process_group():
+    ring = NllRing("cpu", slots=2)
+    for step in range(5):
+        ring.slot(4).fill_(-8.0 * (step + 1))
+    assert ring.means().tolist() == [2.0, 4.0, 6.0, 8.0, 10.0]
+    assert ring.means().numel() == 0
 
 
 def test_mean_nll_without_process_group():

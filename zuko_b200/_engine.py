@@ -128,6 +128,7 @@ _SIGNATURES = {
     "zk_layer_create": (c_int, [POINTER(LayerDesc), POINTER(c_void_p)]),
     "zk_layer_destroy": (c_int, [_P]),
     "zk_layer_workspace_bytes": (c_size_t, [_P, c_int64]),
+    "zk_layer_fused_info": (c_int, [_P, c_void_p]),
     "zk_layer_forward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_int, _P, c_size_t, _P]),
     "zk_layer_inverse": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "zk_flow_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),

@@ -205,23 +205,40 @@ class FlowCall:
                 )  # fmt: skip
         return z.reshape(*lead, self.D), ladj.reshape(lead)
 
-    def log_prob(self, x: Tensor, c: Tensor | None, with_sum: bool = False):
+    def log_prob(self, x: Tensor, c: Tensor | None, with_sum: bool = False, sum_out: Tensor | None = None):
         """``NormalizingFlow.log_prob(x)`` — zuko/distributions.py:115-119.  With
         ``with_sum`` also returns a device double holding ``sum(log_prob)`` (fixed-order
-        reduction; the per-rank term of the mean NLL)."""
+        reduction; the per-rank term of the mean NLL) — written into ``sum_out`` (one float64
+        element on the device, e.g. a slot of ``dist.NllRing``) when given."""
         x2, c2, ldc, lead = _flatten(x, c if self.C else None, self.D)
         if self._wants_grad(x2, c2):
             lp = _FlowFunction.apply(self, "log_prob", ldc, x2, c2, *self._params).reshape(lead)
-            return (lp, lp.detach().double().sum().reshape(1)) if with_sum else lp
-        return self._run_log_prob(x2, c2, ldc, lead, with_sum)
+            if not with_sum:
+                return lp
+            total = lp.detach().double().sum().reshape(1)
+            if sum_out is not None:
+                sum_out.copy_(total)
+                total = sum_out
+            return lp, total
+        return self._run_log_prob(x2, c2, ldc, lead, with_sum, sum_out)
 
-    def _run_log_prob(self, x2: Tensor, c2: Tensor | None, ldc: int, lead, with_sum: bool = False):
+    def _run_log_prob(self, x2: Tensor, c2: Tensor | None, ldc: int, lead, with_sum: bool = False,
+                      sum_out: Tensor | None = None):  # fmt: skip
         x2, c2 = x2.detach(), (None if c2 is None else c2.detach())
         B = x2.shape[0]
         lp = torch.empty(B, device=x2.device, dtype=torch.float32)
-        total = torch.zeros(1, device=x2.device, dtype=torch.float64) if with_sum else None
+        total = None
+        if with_sum:
+            if sum_out is not None:
+                if sum_out.dtype != torch.float64 or sum_out.numel() != 1 or sum_out.device != x2.device:
+                    raise ValueError("sum_out must be one float64 element on the device of x")
+                total = sum_out
+            else:  # the reduction kernel overwrites its output: no fill needed
+                total = torch.empty(1, device=x2.device, dtype=torch.float64)
         if B == 0:
             lp = lp.reshape(lead)
+            if with_sum:
+                total.zero_()
             return (lp, total) if with_sum else lp
         with torch.cuda.device(x2.device):
             ws = self._ws(x2.device, max(B, 1))

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "api_internal.cuh"
+#include "tc_common.cuh"
 
 namespace zk {
 
@@ -415,6 +416,23 @@ zk_status zk_layer_create(const zk_layer_desc* d, zk_layer** out) {
     }
     *out = l;
     return ZK_OK;
+}
+
+int zk_layer_fused_info(const zk_layer* l, double* out) {
+    if (!l || !out) return -1;
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (l->kind != ZK_LAYER_AUTOREGRESSIVE || !l->hyper) return 0;
+    const zk_mlp* m = l->hyper;
+    double dense = 0;
+    for (int i = 0; i < m->n_linear; ++i) dense += (double)m->dims[i] * m->dims[i + 1];
+    out[3] = dense;
+    const TcPack* pk = tc_pack_of(m);
+    if (!pk || l->circ || !fused_layer_supported(m, l->uni, l->K, l->D, l->C)) return 0;
+    const bool wide = fused_wide_shape(m, l->uni, l->K, l->D, l->C);
+    out[0] = wide ? 2.0 : 1.0;
+    out[1] = wide ? pk->wide.n_items : pk->fused.n_items;
+    out[2] = wide ? pk->wide.issued_macs_per_row : pk->fused.issued_macs_per_row;
+    return wide ? 2 : 1;
 }
 
 size_t zk_layer_workspace_bytes(const zk_layer* l, int64_t B) {

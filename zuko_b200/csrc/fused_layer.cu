@@ -810,6 +810,12 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
     cudaFree(f.sched);
     f.sched = nullptr;
     f.n_items = (int)items.size();
+    {   // every entry is one (CW | N_LAST) x 64 tile of MACs per row, times the split terms
+        const int N_LAST = (DPC * P + 15) & ~15;
+        double macs = 0;
+        for (uint32_t it : items) macs += 64.0 * ((it & 0x10000u) ? N_LAST : CW);
+        f.issued_macs_per_row = macs * pk->n_terms;
+    }
     if (cudaMalloc((void**)&f.sched, items.size() * 4) != cudaSuccess ||
         cudaMemcpy(f.sched, items.data(), items.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(ZK_ENOMEM, "fused_layer_prepare: cudaMalloc failed");

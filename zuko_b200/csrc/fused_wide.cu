@@ -94,6 +94,7 @@ struct WideParams {
     int M;
     int in_vec;         // x / c rows can be read with 16-byte loads
     int n_wstages;
+    int base_off;       // offset (floats, after the bias copy) of the base table [3][D]: loc, 1/scale, log scale + log sqrt(2 pi)
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
     float* y; int64_t ldy;
@@ -270,6 +271,13 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
     for (int l = 0; l < L; ++l)
         if (p.bias_off[l] >= 0)
             for (int i = threadIdx.x; i < p.bias_len[l]; i += W_THREADS) s_bias[p.bias_off[l] + i] = p.bias[l][i];
+    if (p.log_prob != nullptr)  // DiagNormal terms (torch normal.py:87-102) hoisted out of the per-dim epilogue
+        for (int d = threadIdx.x; d < p.D; d += W_THREADS) {
+            const float sg = p.base_scale ? p.base_scale[d] : 1.f;
+            s_bias[p.base_off + d] = p.base_loc ? p.base_loc[d] : 0.f;
+            s_bias[p.base_off + p.D + d] = 1.f / sg;
+            s_bias[p.base_off + 2 * p.D + d] = logf(sg) + kHalfLog2Pi;
+        }
     if (warp == 2) tmem_alloc2(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -517,10 +525,9 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
                 auto finish_dim = [&](int d, float yv, float lj) {
                     if (p.y) p.y[row * p.ldy + d] = yv;
                     if (p.log_prob) {
-                        const float mu = p.base_loc ? p.base_loc[d] : 0.f;
-                        const float sg = p.base_scale ? p.base_scale[d] : 1.f;
-                        const float u = (yv - mu) / sg;
-                        lj += -0.5f * u * u - logf(sg) - kHalfLog2Pi;
+                        const float* bt = s_bias + p.base_off + d;
+                        const float u = (yv - bt[0]) * bt[p.D];
+                        lj += -0.5f * u * u - bt[2 * p.D];
                     }
                     lsum += lj;
                 };
@@ -559,25 +566,38 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
                         else do_dim(std::integral_constant<int, 3>{});
                     }
                 } else {
-                    // affine: 8 dims (16 columns: shift, scale pairs) per load; this set takes the
-                    // 2 groups [2 h, 2 h + 2) of the chunk's 8 groups
+                    // affine: 8 dims (16 columns: shift, scale pairs) per load; set h takes the groups
+                    // h and h + 4 of the chunk's 8 groups (D = 32: one group per set, all 16 warps busy)
                     static_assert(SPC == 4 && DPC == 64, "affine chunk layout");
+                    const int nd = min(DPC, p.D - ch * DPC);  // dims of this chunk
+                    const bool g1 = (h + 4) * 8 < nd;         // the second group holds real dims
                     uint32_t rr[2][16];
-                    tmem_ld_x16(td + (uint32_t)((h * 2) * 16), rr[0]);
-                    tmem_ld_x16(td + (uint32_t)((h * 2 + 1) * 16), rr[1]);
+                    tmem_ld_x16(td + (uint32_t)(h * 16), rr[0]);
+                    if (g1) tmem_ld_x16(td + (uint32_t)((h + 4) * 16), rr[1]);
                     tmem_ld_wait();
                     release();
+                    if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int c0 = (h * 2 + g) * 16;
+                        for (int g = 0; g < 2; ++g) {
+                            if (g == 1 && !g1) break;
+                            const int d0 = ch * DPC + (h + 4 * g) * 8;
+                            float xv[8];
+                            if (p.in_vec) {  // D % 4 == 0 and 16-byte aligned rows: the group's 8 x values in two loads
+                                const float4 a = (d0 < p.D) ? __ldg(reinterpret_cast<const float4*>(xrow + d0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b = (d0 + 4 < p.D) ? __ldg(reinterpret_cast<const float4*>(xrow + d0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+                            } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int d = ch * DPC + (c0 >> 1) + j;
-                            if (d < p.D && row_ok) {
-                                const float shift = __uint_as_float(rr[g][2 * j]) + bias[2 * d];
-                                const float ls = softclip<FAST>(__uint_as_float(rr[g][2 * j + 1]) + bias[2 * d + 1], p.ad);
-                                const float xv = __ldg(xrow + d);
-                                finish_dim(d, fmaf(xv, zexp<FAST>(ls), shift), ls);
+                                for (int j = 0; j < 8; ++j) xv[j] = (d0 + j < p.D) ? __ldg(xrow + d0 + j) : 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int d = d0 + j;
+                                if (d < p.D) {
+                                    const float shift = __uint_as_float(rr[g][2 * j]) + bias[2 * d];
+                                    const float ls = softclip<FAST>(__uint_as_float(rr[g][2 * j + 1]) + bias[2 * d + 1], p.ad);
+                                    finish_dim(d, fmaf(xv[j], zexp<FAST>(ls), shift), ls);
+                                }
                             }
                         }
                     }
@@ -889,6 +909,11 @@ zk_status fused_wide_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univ
     uint32_t rdm[8];
     if (!wide_build_schedule(m->dims.data(), L, hp.Mk, hp.perm, univariate, bins, D, items, rdm)) return ZK_OK;  // per-layer path
     for (int l = 0; l < 8; ++l) wp.rd_mask[l] = (uint8_t)rdm[l];
+    {
+        double macs = 0;
+        for (const uint2& it : items) macs += 64.0 * ((it.x & WS_OUT) ? N_LAST : 128);
+        wp.issued_macs_per_row = macs * pk->n_terms;
+    }
     cudaFree(wp.sched);
     wp.sched = nullptr;
     wp.n_items = (int)items.size();
@@ -942,6 +967,9 @@ zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     if (bias_room < 64u && p.n_wstages > 4) { --p.n_wstages; bias_room += W_WSTAGE / 4u; }
     ZK_REQUIRE(p.n_wstages >= 3, "fused wide layer: not enough shared memory for the weight ring");
     int off = 0;
+    const int base_floats = a.log_prob ? ((3 * a.D + 3) & ~3) : 0;
+    ZK_REQUIRE((uint32_t)base_floats <= bias_room, "fused wide layer: no shared memory left for the base table");
+    bias_room -= (uint32_t)base_floats;
     auto place = [&](int l) {
         const int len = (m->dims[l + 1] + 3) & ~3;  // keep every layer's bias 16-byte aligned
         p.bias[l] = pk->fused.bias[l];
@@ -953,7 +981,8 @@ zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     for (int l = 0; l < L - 1; ++l) place(l);
     for (int l = L; l < ZK_FUSED_MAX_LINEAR; ++l) { p.bias[l] = nullptr; p.bias_off[l] = -1; p.bias_len[l] = 0; }
     for (int l = 0; l < L; ++l) { p.mapW[l] = wp.maps[l]; p.rd_mask[l] = wp.rd_mask[l]; }
-    const size_t smem = 1024u + W_ALO_BYTES + (size_t)p.n_wstages * W_WSTAGE + W_AUX_BYTES + (size_t)off * 4u;
+    p.base_off = off;
+    const size_t smem = 1024u + W_ALO_BYTES + (size_t)p.n_wstages * W_WSTAGE + W_AUX_BYTES + (size_t)(off + base_floats) * 4u;
     if (g_watch_host == nullptr) {
         uint32_t* h = nullptr;
         if (cudaHostAlloc((void**)&h, W_WATCH_WORDS * 4, cudaHostAllocMapped) == cudaSuccess) {

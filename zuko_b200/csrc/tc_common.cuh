@@ -140,6 +140,7 @@ struct FusedPack {
     uint8_t kbmask[8][128];         // [layer][chunk]: bit kb = K block kb has non-zero weights
     uint32_t* sched = nullptr;      // device: MMA issue schedule of one tile, one entry per non-zero tile (owned)
     int n_items = 0;
+    double issued_macs_per_row = 0;  // MACs the schedule issues per sample row (all split terms), bench bookkeeping
 };
 // the wide fused kernel's pack (fused_wide.cu): it shares FusedPack's permuted planes / biases
 // (fused.w, fused.bias) and adds its own tensor maps and issue schedule
@@ -150,6 +151,7 @@ struct WidePack {
     uint2* sched = nullptr;         // device: one entry per non-zero (layer, chunk, K block) tile (owned)
     int n_items = 0;
     uint8_t rd_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per layer: K blocks of the A operand the layer reads
+    double issued_macs_per_row = 0;  // MACs the schedule issues per sample row (all split terms)
 };
 struct TcPack {
     std::vector<TcLayer> layers;

@@ -12,7 +12,7 @@ CPU tests).
 
 from __future__ import annotations
 
-__all__ = ["all_reduce_gradients", "mean_nll", "shard_rows"]
+__all__ = ["NllRing", "all_reduce_gradients", "mean_nll", "shard_rows"]
 
 import torch
 import torch.distributed as dist
@@ -39,6 +39,84 @@ def mean_nll(sum_log_prob: Tensor, count: int, group: dist.ProcessGroup | None =
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return -(buf[0] / buf[1])
+
+
+class NllRing:
+    """The mean-NLL collective taken off the critical path.
+
+    ``mean_nll`` issues a blocking 16-byte all-reduce (plus a few eager fills) on the compute
+    stream every step, so every step costs the max over ranks plus the collective's latency.
+    The ring keeps the per-step terms ``{sum log p, count}`` on the device instead — the engine's
+    fixed-order reduction writes ``sum log p`` straight into a slot (``log_prob_and_sum(x,
+    sum_out=ring.slot(count))``), nothing else is launched per step — and reduces a whole bank of
+    ``slots`` steps with ONE asynchronous ``all_reduce`` issued from a side stream when the bank
+    is full (or on ``flush()``).  The compute stream never waits for a collective; ``means()``
+    waits for the outstanding ones and returns the global mean NLL of every recorded step.
+    """
+
+    def __init__(self, device: torch.device | str, slots: int = 32, group: dist.ProcessGroup | None = None) -> None:
+        self.device = torch.device(device)
+        self.slots, self.group = int(slots), group
+        self.banks = torch.zeros(2, self.slots, 2, dtype=torch.float64, device=self.device)
+        self._counts = [[None] * self.slots, [None] * self.slots]
+        self.bank, self.i = 0, 0
+        self._inflight: list = [None, None]  # per bank: (work | None, event | None, n)
+        self._done: list[Tensor] = []
+        self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def _world(self) -> int:
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def slot(self, count: int) -> Tensor:
+        """The float64 element this step's ``sum log p`` goes into (pass it as ``sum_out``)."""
+        if self.i == self.slots:
+            self.flush()
+        b, i = self.bank, self.i
+        if self._inflight[b] is not None and i == 0:
+            self._collect(b)  # the bank's previous reduction must have landed before it is rewritten
+        if self._counts[b][i] != count:  # constant across steps in practice: written once
+            self.banks[b, i, 1] = float(count)
+            self._counts[b][i] = count
+        self.i += 1
+        return self.banks[b, i, 0:1]
+
+    def flush(self) -> None:
+        """Reduces the steps recorded since the last flush (asynchronously) and switches banks."""
+        n = self.i
+        if n == 0:
+            return
+        b = self.bank
+        view = self.banks[b, :n]
+        work = event = None
+        if self._world() > 1:
+            if self.side is not None:
+                self.side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self.side):
+                    work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            else:
+                work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        elif self.side is not None:
+            event = torch.cuda.Event()
+            event.record(torch.cuda.current_stream(self.device))
+        self._inflight[b] = (work, event, n)
+        self.bank, self.i = 1 - b, 0
+
+    def _collect(self, b: int) -> None:
+        work, event, n = self._inflight[b]
+        if work is not None:
+            work.wait()  # orders the current stream after the collective
+        self._done.append(-(self.banks[b, :n, 0] / self.banks[b, :n, 1]).clone())
+        self._inflight[b] = None
+
+    def means(self) -> Tensor:
+        """Global mean NLL of every step recorded so far (device float64 vector), in order."""
+        self.flush()
+        for b in (self.bank, 1 - self.bank):  # older bank first
+            if self._inflight[b] is not None:
+                self._collect(b)
+        out = torch.cat(self._done) if self._done else torch.zeros(0, dtype=torch.float64, device=self.device)
+        self._done = []
+        return out
 
 
 def all_reduce_gradients(module: torch.nn.Module, weights: tuple[int, int] | None = None,

@@ -199,15 +199,20 @@ class NormalizingFlow(Distribution):
             ladj = ladj.sum(dim=tuple(range(-self.reinterpreted, 0)))
         return self.base.log_prob(z) + ladj
 
-    def log_prob_and_sum(self, x: Tensor) -> tuple[Tensor, Tensor]:
+    def log_prob_and_sum(self, x: Tensor, sum_out: Tensor | None = None) -> tuple[Tensor, Tensor]:
         """``(log_prob(x), sum(log_prob(x)) as a device double[1])`` — the per-rank term of
-        the mean NLL, produced by a fixed-order reduction inside the same engine call."""
+        the mean NLL, produced by a fixed-order reduction inside the same engine call (written
+        into ``sum_out``, e.g. ``dist.NllRing.slot(count)``, when given)."""
         fc = self._flow_call()
         if fc is None:
             lp = self.log_prob(x)
-            return lp, lp.double().sum().reshape(1)
+            total = lp.detach().double().sum().reshape(1)
+            if sum_out is not None:
+                sum_out.copy_(total)
+                total = sum_out
+            return lp, total
         call, ctx = fc
-        return call.log_prob(x, ctx, with_sum=True)
+        return call.log_prob(x, ctx, with_sum=True, sum_out=sum_out)
 
     def rsample(self, shape: Size = ()) -> Tensor:
         z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
