@@ -206,12 +206,41 @@ def cpu_reference_adaptive(target_s: float, rows0: int = 1 << 15, max_rows: int 
     return rate, sec, threads, rows
 
 
+def usable_cores() -> dict:
+    """What the host really offers this process: os.cpu_count() counts the machine's logical CPUs, the
+    affinity mask and the cgroup quota (containers) may allow far fewer."""
+    info = {"cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        info["affinity"] = info["cpu_count"]
+    quota = None
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            q = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    info["cgroup_quota"] = quota
+    n = min(info["cpu_count"], info["affinity"])
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    info["threads"] = n
+    return info
+
+
 def cpu_reference_rate(rows: int, repeats: int = 1):
     """Times the oracle's fp32 CPU restatement of flow(c).log_prob(x) (all host threads, OpenMP)
     on `rows` rows of the bench workload.  Returns (samples/s, seconds, threads)."""
     from oracle import oracle
 
-    threads = oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    threads = oracle.set_threads(int(os.environ.get("ZK_BENCH_CPU_THREADS", "0")) or usable_cores()["threads"])  # torchrun exports OMP_NUM_THREADS=1
     flow = build_model()
     spec = oracle.flowspec_from_module(flow)
     g = torch.Generator().manual_seed(1234)
@@ -252,7 +281,7 @@ def run_reference(args) -> None:
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows_per_step": rows, "note": "oracle port (plain C, OpenMP, threads pinned) of the reference's CPU path; fixed bounded sample per step, median step time",
                    "step_seconds_min_max": [float(min(times)), float(max(times))]},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{rows} rows of the workload per step"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "host": usable_cores(), "sample": f"{rows} rows of the workload per step"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
@@ -553,7 +582,7 @@ def run_ours(args) -> None:
                 rows = args.cpu_rows or CPU_ROWS
                 cpu_reference_rate(min(rows, 1 << 16))  # warm-up
                 rate, sec, threads = cpu_reference_rate(rows, repeats=3)
-                cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "host": usable_cores(),
                        "sample": f"{rows} rows of the workload, oracle fp32 C port with OpenMP (threads pinned), best of 3, {sec:.1f} s"}  # fmt: skip
             except Exception as e:  # noqa: BLE001
                 cpu = {"error": f"{type(e).__name__}: {e}"[:300]}

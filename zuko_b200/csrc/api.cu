@@ -561,9 +561,15 @@ zk_status layer_forward_impl(const zk_layer* l, const float* x, int64_t ldx, con
     return fail(ZK_EUNSUPPORTED, "layer_forward: unknown kind %d", l->kind);
 }
 
+// Inverse of one layer.  With `ladj` the layer ALSO adds (accumulate) / writes the per-sample FORWARD
+// log-determinant at the solution — and with `base_lp` the base log-density of its input y — when its
+// inverse kernel can produce them in the same sweep; *ladj_done tells the caller whether it did
+// (otherwise the caller evaluates the layer's forward ladj separately).
 zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, const float* c,
                              int64_t ldc, int64_t B, float* x, int64_t ldx, void* ws,
-                             size_t ws_bytes, cudaStream_t st) {
+                             size_t ws_bytes, cudaStream_t st, float* ladj, int accumulate, bool base_lp,
+                             const float* base_loc, const float* base_scale, bool* ladj_done) {
+    if (ladj_done) *ladj_done = false;
     if (B == 0) return ZK_OK;
     ZK_REQUIRE(l->C == 0 || c != nullptr, "layer needs a context of %d features", l->C);
     Arena ar(ws, ws_bytes);
@@ -573,8 +579,16 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:994-1000: x = zeros_like(y); for _ in range(passes): x = meta(x).inv(y)
-            if (l->inv && g_fused.load())  // same fixed point, every weight visited once (ar_inverse.cu)
-                return launch_ar_inverse(l->inv, y, ldy, c, ldc, B, x, ldx, l->bound, l->slope, g_fast_math.load() != 0, l->circ, st);
+            if (l->inv && g_fused.load()) {  // same fixed point, every weight visited once (ar_inverse.cu)
+                ArInvArgs ia;
+                ia.y = y; ia.ldy = ldy; ia.c = c; ia.ldc = ldc; ia.B = B; ia.x = x; ia.ldx = ldx;
+                ia.bound = l->bound; ia.slope = l->slope; ia.fast = g_fast_math.load() != 0; ia.circular = l->circ;
+                if (ladj) {
+                    ia.ladj = ladj; ia.accumulate = accumulate; ia.base = base_lp; ia.base_loc = base_loc; ia.base_scale = base_scale;
+                    if (ladj_done) *ladj_done = true;
+                }
+                return launch_ar_inverse(l->inv, ia, st);
+            }
             float* phi = ar.take<float>((size_t)B * l->D * l->P);
             ZK_REQUIRE(ar.ok, "layer_inverse: workspace too small");
             if (ldx == l->D) {
@@ -732,20 +746,57 @@ zk_status flow_inverse_chunk(const zk_flow_desc* f, const float* z, int64_t ldz,
     const size_t lws_bytes = ar.size - ar.off;
     const float* cur = z;
     int64_t ldcur = ldz;
+    // distributions.py:129-138: log p(x) = base.log_prob(z) - ladj_inv, and ladj_inv = -ladj_fwd(x)
+    // (torch/distributions/transforms.py:277-280).  ONE sweep: every layer's inverse kernel also
+    // accumulates its forward ladj at the solution (and the first one the base log-density of z)
+    // into `log_prob`; only layers whose inverse kernel cannot (sweep-based inverses, coupling,
+    // element-wise tables) pay a forward evaluation of that layer alone.
+    const bool want = (log_prob != nullptr);
+    bool seeded = false;  // log_prob already holds the base term (+ earlier layers)
     for (int i = T - 1; i >= 0; --i) {
         const zk_layer* l = f->layers[i];
         const bool last = (i == 0);
         float* dst = last ? x : buf[i & 1];
         const int64_t ldd = last ? ldx : D;
-        ZK_TRY(layer_inverse_impl(l, cur, ldcur, l->C ? c : nullptr, ldc, B, dst, ldd, lws, lws_bytes, st));
+        bool done = false;
+        // the DiagNormal term of z can ride in the first inverted layer's kernel; a BoxUniform base is seeded apart
+        const bool can_seed = want && !seeded && i == T - 1 && f->base_kind != ZK_BASE_BOX_UNIFORM;
+        if (want && !seeded && !can_seed) {
+            ZK_TRY(launch_box_uniform(z, ldz, f->base_loc, f->base_scale, nullptr, B, D, log_prob, st));
+            seeded = true;
+        }
+        ZK_TRY(layer_inverse_impl(l, cur, ldcur, l->C ? c : nullptr, ldc, B, dst, ldd, lws, lws_bytes, st,
+                                  want ? log_prob : nullptr, seeded ? 1 : 0, can_seed, f->base_loc, f->base_scale, &done));
+        if (want) {
+            if (done) {
+                seeded = true;
+            } else {
+                if (!seeded) {  // base log-density of z = the first inverted layer's input
+                    if (f->base_kind == ZK_BASE_BOX_UNIFORM)
+                        ZK_TRY(launch_box_uniform(z, ldz, f->base_loc, f->base_scale, nullptr, B, D, log_prob, st));
+                    else
+                        ZK_TRY(launch_diag_normal(z, ldz, f->base_loc, f->base_scale, nullptr, B, D, log_prob, st));
+                    seeded = true;
+                }
+                // forward ladj of this layer alone at its input `dst`; its output is not needed and goes to
+                // the other ping-pong buffer (it holds this layer's y, which is dead now; never the caller's z)
+                float* scratch = buf[(i + 1) & 1];
+                if (l->kind != ZK_LAYER_PERMUTATION && l->kind != ZK_LAYER_ROTATION)  // those have ladj = 0
+                    ZK_TRY(layer_forward_impl(l, dst, ldd, l->C ? c : nullptr, ldc, B, scratch, D, log_prob, 1, nullptr,
+                                              nullptr, nullptr, lws, lws_bytes, st));
+            }
+        }
         cur = dst;
         ldcur = ldd;
     }
-    if (T == 0) ZK_TRY(copy_rows(z, ldz, B, D, x, ldx, st));
-    if (log_prob) {
-        // distributions.py:129-138: log p(x) = base.log_prob(z) - ladj_inv, and ladj_inv = -ladj_fwd(x)
-        // (torch/distributions/transforms.py:277-280), i.e. exactly log_prob(x).
-        ZK_TRY(flow_forward_chunk(f, x, ldx, c, ldc, B, nullptr, 0, nullptr, log_prob, ws, ws_bytes, st));
+    if (T == 0) {
+        ZK_TRY(copy_rows(z, ldz, B, D, x, ldx, st));
+        if (want) {
+            if (f->base_kind == ZK_BASE_BOX_UNIFORM)
+                ZK_TRY(launch_box_uniform(z, ldz, f->base_loc, f->base_scale, nullptr, B, D, log_prob, st));
+            else
+                ZK_TRY(launch_diag_normal(z, ldz, f->base_loc, f->base_scale, nullptr, B, D, log_prob, st));
+        }
     }
     return ZK_OK;
 }
@@ -772,7 +823,8 @@ zk_status zk_layer_inverse(const zk_layer* l, const float* y, int64_t ldy, const
     ZK_REQUIRE(x != y, "layer_inverse: x must not alias y");
     ZK_REQUIRE(B >= 0 && ldx >= l->D && ldy >= l->D, "layer_inverse: bad shape");
     ZK_REQUIRE(ws_bytes >= zk_layer_workspace_bytes(l, B), "layer_inverse: workspace too small");
-    return layer_inverse_impl(l, y, ldy, c, ldc, B, x, ldx, ws, ws_bytes, (cudaStream_t)stream);
+    return layer_inverse_impl(l, y, ldy, c, ldc, B, x, ldx, ws, ws_bytes, (cudaStream_t)stream, nullptr, 0, false,
+                              nullptr, nullptr, nullptr);
 }
 
 size_t zk_flow_workspace_bytes(const zk_flow_desc* f, int64_t B) {

@@ -14,7 +14,20 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
                           int univariate, int bins, int passes, ArInvPack** out);
 void ar_inverse_free(ArInvPack* pk);
 bool ar_inverse_threads(const ArInvPack* pk, int* threads, size_t* smem);
-zk_status launch_ar_inverse(const ArInvPack* pk, const float* y, int64_t ldy, const float* c, int64_t ldc, int64_t B,
-                            float* x, int64_t ldx, float bound, float slope, bool fast, bool circular, cudaStream_t stream);
+
+struct ArInvArgs {
+    const float* y = nullptr; int64_t ldy = 0;  // the layer's output (input of the inverse)
+    const float* c = nullptr; int64_t ldc = 0;
+    int64_t B = 0;
+    float* x = nullptr; int64_t ldx = 0;
+    float bound = 5.f, slope = 1e-3f;
+    bool fast = true, circular = false;
+    // optional: per-sample sum over D of the FORWARD log-derivative at the solution x (what
+    // rsample_and_log_prob needs, distributions.py:129-138), accumulated into `ladj` when
+    // `accumulate`; with `base` the DiagNormal(loc, scale) log-density of y is added as well
+    float* ladj = nullptr; int accumulate = 0;
+    bool base = false; const float* base_loc = nullptr; const float* base_scale = nullptr;
+};
+zk_status launch_ar_inverse(const ArInvPack* pk, const ArInvArgs& a, cudaStream_t stream);
 
 }  // namespace zk
