@@ -197,6 +197,18 @@ typedef struct {
 
 zk_status zk_layer_create(const zk_layer_desc* desc, zk_layer** out);
 zk_status zk_layer_destroy(zk_layer* layer);
+/* The conditioner's weights / biases changed (optimizer step, nn.py:217-218 reads them on every
+ * call) but shapes, masks and options did not: refreshes every packed copy IN PLACE — `mask * W`, the
+ * bf16 hi / lo planes of the GEMM and fused kernels — with kernels on `stream`: no allocation, no
+ * host synchronisation, no mask download.  The transposed weights of the backward pass and the
+ * step-ordered stream of the sequential inverse are rebuilt by the next call that needs them.
+ * weight / bias: host arrays of n_linear DEVICE pointers as in zk_mlp_desc (bias entries may be NULL).
+ * Calls already queued on `stream` see the old weights, later ones the new. */
+zk_status zk_layer_update_weights(zk_layer* layer, const float* const* weight, const float* const* bias,
+                                  zk_stream stream);
+/* Names the stream the caller's tensors are produced on (thread-local; NULL = none): zk_mlp_create /
+ * zk_layer_create synchronise it before their pack kernels (legacy default stream) read the weights. */
+void zk_set_pack_stream(zk_stream stream);
 size_t zk_layer_workspace_bytes(const zk_layer* layer, int64_t B);
 /* Bench bookkeeping: which kernel runs an autoregressive layer's forward (flows/autoregressive.py:
  * 207-215) and how much tensor-core work its issue schedule holds.  Returns 0 = per-layer GEMM

@@ -129,6 +129,8 @@ _SIGNATURES = {
     "zk_layer_destroy": (c_int, [_P]),
     "zk_layer_workspace_bytes": (c_size_t, [_P, c_int64]),
     "zk_layer_fused_info": (c_int, [_P, c_void_p]),
+    "zk_layer_update_weights": (c_int, [_P, c_void_p, c_void_p, _P]),
+    "zk_set_pack_stream": (None, [_P]),
     "zk_layer_forward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_int, _P, c_size_t, _P]),
     "zk_layer_inverse": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "zk_flow_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),
@@ -203,7 +205,10 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 class Workspace:
-    """Per-device grow-only scratch tensor handed to the C ABI (the caller owns all memory)."""
+    """Grow-only scratch tensor handed to the C ABI (the caller owns all memory), one per (device, CUDA
+    stream): engine calls issued on different torch streams never share scratch, and a buffer that is
+    outgrown is handed back to the caching allocator with ``record_stream`` so that it cannot be reused
+    while kernels queued on its stream still run."""
 
     _cache: dict = {}
     # workspace ceiling: the flow calls chunk the batch to fit whatever they are given
@@ -212,11 +217,15 @@ class Workspace:
     @classmethod
     def get(cls, device: torch.device, want: int, minimum: int) -> torch.Tensor:
         want = max(minimum, min(want, cls.max_bytes))
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(device)
+        key = (device.type, index, stream.cuda_stream)
         buf = cls._cache.get(key)
         if buf is None or buf.numel() < want:
-            cls._cache.pop(key, None)
-            buf = None
+            old = cls._cache.pop(key, None)
+            if old is not None:
+                old.record_stream(stream)
+            del old
             buf = torch.empty(want, dtype=torch.uint8, device=device)
             cls._cache[key] = buf
         return buf

@@ -92,8 +92,10 @@ class _FlowFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, call, mode, ldc, x2, c2, *params):  # noqa: ANN001
+        # params = the call's conditioner / table parameters, then (log_prob mode) the base's loc, scale
         ctx.call, ctx.mode, ctx.ldc = call, mode, ldc
         ctx.has_c = c2 is not None
+        ctx.generations = call._generations()
         ctx.save_for_backward(*([x2, c2] if c2 is not None else [x2]))
         lead = x2.shape[:-1]
         if mode == "log_prob":
@@ -107,8 +109,17 @@ class _FlowFunction(torch.autograd.Function):
         x2 = saved[0]
         c2 = saved[1] if ctx.has_c else None
         need = ctx.needs_input_grad
-        gx, gc, pg = ctx.call._run_backward(ctx.mode, x2, c2, ctx.ldc, gouts, need[3], need[4], need[5:])
-        return (None, None, None, gx, gc, *pg)
+        call = ctx.call
+        call._check_generations(ctx.generations)
+        n = len(call._params)
+        gx, gc, pg = call._run_backward(ctx.mode, x2, c2, ctx.ldc, gouts, need[3], need[4], need[5 : 5 + n])
+        base_g = []
+        if len(need) > 5 + n:  # base loc / scale were passed: d log N(z; loc, scale) / d(loc, scale), z = f(x)
+            base_g = [None, None]
+            if need[5 + n] or need[6 + n]:
+                z = call._run_forward(x2, c2, ctx.ldc, x2.shape[:-1])[0]
+                base_g = list(call._base_param_grads(z, gouts[0], need[5 + n], need[6 + n]))
+        return (None, None, None, gx, gc, *pg, *base_g)
 
 
 class _FlowInverseFunction(torch.autograd.Function):
@@ -120,6 +131,7 @@ class _FlowInverseFunction(torch.autograd.Function):
     def forward(ctx, call, with_lp, ldc, z2, c2, *params):  # noqa: ANN001
         ctx.call, ctx.with_lp, ctx.ldc = call, with_lp, ldc
         ctx.has_c = c2 is not None
+        ctx.generations = call._generations()
         out = call._run_inverse(z2, c2, ldc, z2.shape[:-1], with_lp)
         x = out[0] if with_lp else out
         ctx.save_for_backward(*([x, z2, c2] if c2 is not None else [x, z2]))
@@ -132,9 +144,17 @@ class _FlowInverseFunction(torch.autograd.Function):
         x, z2 = saved[0], saved[1]
         c2 = saved[2] if ctx.has_c else None
         need = ctx.needs_input_grad
-        gz, gc, pg = ctx.call._run_inverse_backward(x, z2, c2, ctx.ldc, gouts[0], gouts[1] if ctx.with_lp else None,
-                                                    need[3], need[4], need[5:])  # fmt: skip
-        return (None, None, None, gz, gc, *pg)
+        call = ctx.call
+        call._check_generations(ctx.generations)
+        n = len(call._params)
+        g_lp = gouts[1] if ctx.with_lp else None
+        gz, gc, pg = call._run_inverse_backward(x, z2, c2, ctx.ldc, gouts[0], g_lp, need[3], need[4], need[5 : 5 + n])  # fmt: skip
+        base_g = []
+        if len(need) > 5 + n:  # explicit dependence of log p(x) = log N(z; loc, scale) + ... on loc, scale at fixed z
+            base_g = [None, None]
+            if g_lp is not None and (need[5 + n] or need[6 + n]):
+                base_g = list(call._base_param_grads(z2, g_lp, need[5 + n], need[6 + n]))
+        return (None, None, None, gz, gc, *pg, *base_g)
 
 
 class FlowCall:
@@ -163,6 +183,11 @@ class FlowCall:
         self._arr = (ctypes.c_void_p * max(1, len(handles)))(*[h.value if isinstance(h, ctypes.c_void_p) else h for h in handles])
         self._loc = None if loc is None else loc.detach().contiguous()
         self._scale = None if scale is None else scale.detach().contiguous()
+        # a trainable DiagNormal base (UnconditionalDistribution(DiagNormal, loc, scale) with parameters,
+        # zuko/lazy.py:242-287): loc / scale join the autograd seam as extra inputs
+        self._base_src: list[Tensor] = []
+        if base_kind == E.ZK_BASE_DIAG_NORMAL and loc is not None and (loc.requires_grad or scale.requires_grad):
+            self._base_src = [loc, scale]
         if self._loc is not None:
             E.require_cuda(self._loc, "base loc")
             E.require_cuda(self._scale, "base scale")
@@ -187,7 +212,29 @@ class FlowCall:
     def _wants_grad(self, x2: Tensor, c2: Tensor | None) -> bool:
         if not torch.is_grad_enabled():
             return False
-        return x2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
+        return (x2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
+                or bool(self._base_src))  # fmt: skip
+
+    def _generations(self) -> tuple:
+        return tuple(getattr(r, "generation", 0) for r in self._keep)
+
+    def _check_generations(self, then: tuple) -> None:
+        if then != self._generations():
+            raise RuntimeError(
+                "zuko_b200: the conditioner weights of this flow were refreshed in place (optimizer step) after the "
+                "forward call of this graph; run backward() before the step, as torch requires for tensors modified in place"
+            )
+
+    def _base_param_grads(self, z: Tensor, g: Tensor, need_loc: bool, need_scale: bool):
+        """d/d(loc, scale) of sum_b g_b log N(z_b; loc, scale) (torch/distributions/normal.py:87-102) at
+        fixed z — reductions over the batch of element-wise terms (autograd plumbing of two D-vectors)."""
+        loc, scale = self._base_src
+        zf = z.detach().reshape(-1, self.D).to(torch.float32)
+        gf = g.detach().reshape(-1, 1).to(torch.float32)
+        u = (zf - loc.detach()) / scale.detach()
+        g_loc = (gf * u / scale.detach()).sum(0).to(loc.dtype) if need_loc else None
+        g_scale = (gf * (u * u - 1.0) / scale.detach()).sum(0).to(scale.dtype) if need_scale else None
+        return g_loc, g_scale
 
     def _run_forward(self, x2: Tensor, c2: Tensor | None, ldc: int, lead) -> tuple[Tensor, Tensor]:
         x2, c2 = x2.detach(), (None if c2 is None else c2.detach())
@@ -212,7 +259,7 @@ class FlowCall:
         element on the device, e.g. a slot of ``dist.NllRing``) when given."""
         x2, c2, ldc, lead = _flatten(x, c if self.C else None, self.D)
         if self._wants_grad(x2, c2):
-            lp = _FlowFunction.apply(self, "log_prob", ldc, x2, c2, *self._params).reshape(lead)
+            lp = _FlowFunction.apply(self, "log_prob", ldc, x2, c2, *self._params, *self._base_src).reshape(lead)
             if not with_sum:
                 return lp
             total = lp.detach().double().sum().reshape(1)
@@ -256,7 +303,8 @@ class FlowCall:
         zuko/distributions.py:129-138).  Differentiable w.r.t. z, c and the parameters."""
         z2, c2, ldc, lead = _flatten(z, c if self.C else None, self.D)
         if self._wants_grad(z2, c2):
-            out = _FlowInverseFunction.apply(self, with_log_prob, ldc, z2, c2, *self._params)
+            out = _FlowInverseFunction.apply(self, with_log_prob, ldc, z2, c2, *self._params,
+                                             *(self._base_src if with_log_prob else []))
             if with_log_prob:
                 return out[0].reshape(*lead, self.D), out[1].reshape(lead)
             return out.reshape(*lead, self.D)

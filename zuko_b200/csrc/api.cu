@@ -54,6 +54,7 @@ const char* zk_last_error(void) { return g_last_error.c_str(); }
 int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
+static thread_local cudaStream_t g_pack_stream = nullptr;
 void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
 int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
                            int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
@@ -168,6 +169,9 @@ zk_status zk_mlp_destroy(zk_mlp* m) {
 zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
     ZK_REQUIRE(d && out, "mlp_create: null argument");
     *out = nullptr;
+    // the pack kernels run on the legacy default stream; the tensors they read may still be written by
+    // work queued on the caller's (non-blocking) stream — zk_set_pack_stream names it
+    if (g_pack_stream != nullptr) ZK_CUDA(cudaStreamSynchronize(g_pack_stream));
     ZK_REQUIRE(d->n_linear >= 1 && d->n_linear <= 64, "mlp_create: n_linear=%d out of range", d->n_linear);
     ZK_REQUIRE(d->dims && d->weight, "mlp_create: null dims/weight");
     ZK_REQUIRE(d->gemm_mode >= ZK_GEMM_AUTO && d->gemm_mode <= ZK_GEMM_BF16X1,
@@ -337,6 +341,7 @@ static zk_status layer_create_impl(const zk_layer_desc* d, zk_layer* l) {
                        "layer_create: conditioner out_features %d != D*P %d",
                        l->hyper->dims[l->hyper->n_linear], l->D * l->P);
             ZK_TRY(fused_layer_prepare(l->hyper, d->hyper->mask, l->uni, l->K, l->D, l->C));
+            if (d->order) l->order.assign(d->order, d->order + l->D);
             {
                 int T = 0;
                 size_t smem = 0;
@@ -415,6 +420,26 @@ zk_status zk_layer_create(const zk_layer_desc* d, zk_layer** out) {
         return st;
     }
     *out = l;
+    return ZK_OK;
+}
+
+void zk_set_pack_stream(zk_stream stream) { g_pack_stream = (cudaStream_t)stream; }
+
+zk_status zk_layer_update_weights(zk_layer* l, const float* const* weight, const float* const* bias, zk_stream stream) {
+    ZK_REQUIRE(l && weight, "layer_update_weights: null argument");
+    ZK_REQUIRE(l->hyper, "layer_update_weights: the layer has no conditioner");
+    zk_mlp* m = l->hyper;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < m->n_linear; ++i) {
+        ZK_REQUIRE(weight[i], "layer_update_weights: weight[%d] is null", i);
+        const int64_t n = (int64_t)m->dims[i + 1] * m->dims[i];
+        ZK_TRY(launch_apply_mask(weight[i], m->mask[i], n, m->w[i], st));  // nn.py:218 `mask * W`, once per update
+        if (bias && bias[i]) ZK_CUDA(cudaMemcpyAsync(m->b[i], bias[i], (size_t)m->dims[i + 1] * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    ZK_TRY(tc_refresh(m, st));
+    ZK_TRY(fused_refresh(m, st));
+    m->bwd_dirty = true;          // transposed weights / backward planes: refilled by the next backward call
+    if (l->inv) l->inv_dirty = true;  // step-ordered inverse stream: rebuilt by the next inverse call
     return ZK_OK;
 }
 
@@ -579,6 +604,25 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE: {
             // transforms.py:994-1000: x = zeros_like(y); for _ in range(passes): x = meta(x).inv(y)
+            if (l->inv_dirty) {  // the weights were refreshed in place: rebuild the step-ordered stream once
+                static std::mutex mu;
+                std::lock_guard<std::mutex> lk(mu);
+                zk_layer* ml = const_cast<zk_layer*>(l);
+                if (ml->inv_dirty) {
+                    ZK_CUDA(cudaStreamSynchronize(st));  // the refresh kernels ran on the caller's stream
+                    ar_inverse_free(ml->inv);
+                    ml->inv = nullptr;
+                    int T = 0;
+                    size_t smem = 0;
+                    ZK_TRY(ar_inverse_pack(ml->hyper, ml->hyper->mask.data(), ml->order.empty() ? nullptr : ml->order.data(), ml->D,
+                                           ml->C, ml->uni, ml->K, ml->passes, &ml->inv));
+                    if (ml->inv && !ar_inverse_threads(ml->inv, &T, &smem)) {
+                        ar_inverse_free(ml->inv);
+                        ml->inv = nullptr;
+                    }
+                    ml->inv_dirty = false;
+                }
+            }
             if (l->inv && g_fused.load()) {  // same fixed point, every weight visited once (ar_inverse.cu)
                 ArInvArgs ia;
                 ia.y = y; ia.ldy = ldy; ia.c = c; ia.ldc = ldc; ia.B = B; ia.x = x; ia.ldx = ldx;

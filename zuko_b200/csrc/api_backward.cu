@@ -33,7 +33,14 @@ std::atomic<int> g_tc_backward{1};
 zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
     zk_mlp* m = const_cast<zk_mlp*>(cm);
     std::lock_guard<std::mutex> lk(g_bwd_mu);
-    if ((int)m->wt.size() == m->n_linear) return ZK_OK;
+    if ((int)m->wt.size() == m->n_linear) {
+        if (!m->bwd_dirty) return ZK_OK;
+        // the weights were refreshed in place (zk_layer_update_weights): same buffers, new transposes
+        for (int i = 0; i < m->n_linear; ++i) ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], m->wt[i], st));
+        if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1) ZK_TRY(tc_pack_backward(m, st));
+        m->bwd_dirty = false;
+        return ZK_OK;
+    }
     for (float* p : m->wt) cudaFree(p);
     m->wt.clear();
     for (int i = 0; i < m->n_linear; ++i) {

@@ -60,6 +60,8 @@ struct zk_layer {
     int* idx_b = nullptr;          // device: transformed columns (coupling), owned
     int n_a = 0, n_b = 0;
     zk::ArInvPack* inv = nullptr;  // step-ordered weights for the dimension-sequential inverse (owned)
+    bool inv_dirty = false;        // weights refreshed in place since `inv` was built: rebuilt on the next inverse call
+    std::vector<int64_t> order;    // host copy of the order classes (autoregressive), for that rebuild
 };
 
 

@@ -699,8 +699,10 @@ zk_status fused_host_prepare(zk_mlp* m, const uint8_t* const* mask_dev, FusedPac
     // ---- permuted planes and biases ----
     for (auto* q : f.w) cudaFree(q);
     for (auto* q : f.bias) cudaFree(q);
+    for (auto* q : f.dperm) cudaFree(q);
     f.w.clear(); f.bias.clear();
-    std::vector<int*> dperm(L - 1, nullptr);
+    f.dperm.assign(L - 1, nullptr);
+    std::vector<int*>& dperm = f.dperm;  // kept: a weight refresh re-runs the split kernels with them
     zk_status st = ZK_OK;
     for (int l = 0; l < L - 1 && st == ZK_OK; ++l) {
         if (cudaMalloc((void**)&dperm[l], perm[l].size() * 4) != cudaSuccess ||
@@ -728,8 +730,28 @@ zk_status fused_host_prepare(zk_mlp* m, const uint8_t* const* mask_dev, FusedPac
         st = check_launch("permute_bias_kernel");
     }
     if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "fused_host_prepare: sync failed");
-    for (int* q : dperm) cudaFree(q);
     return st;
+}
+
+// The weights of `m` changed in place (same shapes, same masks): rebuild the fused kernels' permuted
+// planes and biases with the permutations of the last fused_host_prepare.  Stream-ordered, no
+// allocation, no host synchronisation; schedules / tensor maps depend on the masks only and stay.
+zk_status fused_refresh(zk_mlp* m, cudaStream_t st) {
+    TcPack* pk = (TcPack*)m->tc;
+    if (!pk) return ZK_OK;
+    FusedPack& f = pk->fused;
+    const int L = m->n_linear;
+    if ((int)f.w.size() != L || (int)f.dperm.size() != L - 1) return ZK_OK;  // no fused pack was built
+    for (int l = 0; l < L; ++l) {
+        const int K = m->dims[l], N = m->dims[l + 1], Kp = pk->layers[l].Kp;
+        const int* rp = (l < L - 1) ? f.dperm[l] : nullptr;
+        const int* cp = (l > 0) ? f.dperm[l - 1] : nullptr;
+        split_permuted_kernel<<<(unsigned)ceil_div((int64_t)N * Kp, 256), 256, 0, st>>>(m->w[l], N, K, Kp, rp, cp, f.w[l]);
+        ZK_TRY(check_launch("split_permuted_kernel"));
+        permute_bias_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(m->b[l], N, rp, f.bias[l]);
+        ZK_TRY(check_launch("permute_bias_kernel"));
+    }
+    return ZK_OK;
 }
 
 zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {

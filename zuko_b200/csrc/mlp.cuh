@@ -16,6 +16,7 @@ struct zk_mlp {
     bool plain = true;           // activation after every layer but the last, no residual adds
     std::vector<int> lact;       // per layer: activation applied to its output (0 none, 1 ReLU, ZK_ACT_*)
     std::vector<int> lres;       // per layer: add the input of layer i-1 to the output (residual block)
+    bool bwd_dirty = false;        // weights refreshed since wt / the backward planes were built
     int gemm_mode = ZK_GEMM_FP32;  // resolved path
     int max_hidden = 0;
     // tcgen05 path: packed bf16 hi/lo weights (owned), see mlp_tcgen05.cu

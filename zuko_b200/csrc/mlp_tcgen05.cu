@@ -362,6 +362,7 @@ void tc_destroy(zk_mlp* m) {
     for (auto& l : pk->bwd) cudaFree(l.w);
     for (auto* q : pk->fused.w) cudaFree(q);
     for (auto* q : pk->fused.bias) cudaFree(q);
+    for (auto* q : pk->fused.dperm) cudaFree(q);
     cudaFree(pk->fused.sched);
     cudaFree(pk->wide.sched);
     delete pk;
@@ -409,6 +410,17 @@ zk_status tc_pack(zk_mlp* m, int requested_mode) {
     ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     ZK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     m->gemm_mode = (pk->n_terms == 3) ? ZK_GEMM_BF16X3 : ZK_GEMM_BF16X1;
+    return ZK_OK;
+}
+
+zk_status tc_refresh(zk_mlp* m, cudaStream_t st) {
+    TcPack* pk = (TcPack*)m->tc;
+    if (!pk) return ZK_OK;
+    for (int i = 0; i < m->n_linear; ++i) {
+        const TcLayer& L = pk->layers[i];
+        split_weight_kernel<<<(unsigned)ceil_div((int64_t)L.N * L.Kp, 256), 256, 0, st>>>(m->w[i], L.N, L.K, L.Kp, L.w);
+        ZK_TRY(check_launch("split_weight_kernel"));
+    }
     return ZK_OK;
 }
 
@@ -675,8 +687,16 @@ zk_status tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
 zk_status tc_pack_backward(zk_mlp* m, cudaStream_t st) {
     TcPack* pk = (TcPack*)m->tc;
     ZK_REQUIRE(pk, "tc_pack_backward: handle has no tensor-core pack");
-    if ((int)pk->bwd.size() == m->n_linear) return ZK_OK;
     ZK_REQUIRE((int)m->wt.size() == m->n_linear, "tc_pack_backward: transposed weights missing");
+    if ((int)pk->bwd.size() == m->n_linear) {
+        if (!m->bwd_dirty) return ZK_OK;
+        for (int i = 0; i < m->n_linear; ++i) {  // same planes, new values
+            const TcLayer& L = pk->bwd[i];
+            split_weight_kernel<<<(unsigned)ceil_div((int64_t)L.N * L.Kp, 256), 256, 0, st>>>(m->wt[i], L.N, L.K, L.Kp, L.w);
+            ZK_TRY(check_launch("split_weight_kernel"));
+        }
+        return ZK_OK;
+    }
     for (auto& l : pk->bwd) cudaFree(l.w);
     pk->bwd.clear();
     for (int i = 0; i < m->n_linear; ++i) {

@@ -12,6 +12,8 @@ namespace zk {
 // tensor-core path is selected.  Runs on stream 0.
 zk_status tc_pack(zk_mlp* m, int requested_mode);
 void tc_destroy(zk_mlp* m);
+// re-splits m->w into the existing bf16 planes (weights changed, shapes / masks did not); stream-ordered
+zk_status tc_refresh(zk_mlp* m, cudaStream_t stream);
 size_t tc_workspace_bytes(const zk_mlp* m, int64_t B);
 zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const float* c,
                      int64_t ldc, int dc, int64_t B, float* out, int64_t ldo, void* ws,

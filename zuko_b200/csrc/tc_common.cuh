@@ -136,6 +136,7 @@ struct FusedPack {
     int uni = 0, bins = 0, D = 0, C = 0;
     std::vector<__nv_bfloat16*> w;  // per layer [2][N][Kp], permuted (owned)
     std::vector<float*> bias;       // per layer, permuted, padded (owned)
+    std::vector<int*> dperm;        // per hidden layer: device copy of the degree permutation (owned; weight refresh)
     std::vector<CUtensorMap> map64; // box (64 x 64 x 1)
     uint8_t kbmask[8][128];         // [layer][chunk]: bit kb = K block kb has non-zero weights
     uint32_t* sched = nullptr;      // device: MMA issue schedule of one tile, one entry per non-zero tile (owned)

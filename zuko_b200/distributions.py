@@ -74,13 +74,46 @@ class DiagNormal(Distribution):
         D = self.loc.shape[0]
         lead = torch.broadcast_shapes(z.shape[:-1], self.batch_shape)
         z2 = z.expand(*lead, D).reshape(-1, D).contiguous()
-        out = torch.empty(z2.shape[0], device=z.device, dtype=torch.float32)
-        loc, scale = self.loc.detach().contiguous(), self.scale.detach().contiguous()
-        E.require_cuda(loc, "base loc")
-        with torch.cuda.device(z.device):
-            E.check(E.lib().zk_diag_normal_log_prob(z2.data_ptr(), D, loc.data_ptr(), scale.data_ptr(), None,
-                                                    z2.shape[0], D, out.data_ptr(), E.stream_ptr(z.device)))  # fmt: skip
-        return out.reshape(lead)
+        E.require_cuda(self.loc, "base loc")
+        if torch.is_grad_enabled() and (z2.requires_grad or self.loc.requires_grad or self.scale.requires_grad):
+            # the unfused path of NormalizingFlow.log_prob (`base.log_prob(z) + ladj`) and direct users
+            # differentiate through the base term: autograd seam around the same kernel
+            return _DiagNormalLogProb.apply(z2, self.loc, self.scale).reshape(lead)
+        return _diag_normal_log_prob(z2.detach(), self.loc.detach(), self.scale.detach()).reshape(lead)
+
+
+def _diag_normal_log_prob(z2: Tensor, loc: Tensor, scale: Tensor) -> Tensor:
+    D = loc.shape[0]
+    out = torch.empty(z2.shape[0], device=z2.device, dtype=torch.float32)
+    loc, scale = loc.contiguous(), scale.contiguous()
+    with torch.cuda.device(z2.device):
+        E.check(E.lib().zk_diag_normal_log_prob(z2.data_ptr(), D, loc.data_ptr(), scale.data_ptr(), None,
+                                                z2.shape[0], D, out.data_ptr(), E.stream_ptr(z2.device)))  # fmt: skip
+    return out
+
+
+class _DiagNormalLogProb(torch.autograd.Function):
+    """``DiagNormal(loc, scale).log_prob(z)`` with its gradient (torch/distributions/normal.py:87-102,
+    independent.py:120-122): forward = ``zk_diag_normal_log_prob``; backward = the analytic
+    ``d/dz = -(z - loc) / scale^2``, ``d/dloc = -d/dz`` summed over the batch, ``d/dscale = ((z - loc)^2 /
+    scale^2 - 1) / scale`` summed over the batch."""
+
+    @staticmethod
+    def forward(ctx, z2, loc, scale):  # noqa: ANN001
+        ctx.save_for_backward(z2, loc, scale)
+        return _diag_normal_log_prob(z2.detach(), loc.detach(), scale.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):  # noqa: ANN001
+        z2, loc, scale = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        u = (z2 - loc) / scale
+        gu = g.reshape(-1, 1) * u
+        gz = -gu / scale if need[0] else None
+        g_loc = (gu / scale).sum(0) if need[1] else None
+        g_scale = (g.reshape(-1, 1) * (u * u - 1.0) / scale).sum(0) if need[2] else None
+        return gz, g_loc, g_scale
 
 
 class BoxUniform(Distribution):

@@ -60,10 +60,14 @@ def resolve_univariate(univariate: Callable, shapes: Sequence[Size]) -> dict:
 
 
 class OwnedLayer:
-    """Owns one ``zk_layer`` handle; destroys it when the last reference goes away."""
+    """Owns one ``zk_layer`` handle; destroys it when the last reference goes away.  ``generation``
+    counts the in-place weight refreshes (``zk_layer_update_weights``): an autograd graph built
+    before a refresh and back-propagated after it would differentiate the new weights — the
+    engine's seam raises instead, as torch does for tensors modified in place."""
 
     def __init__(self, handle: ctypes.c_void_p) -> None:
         self.handle = handle
+        self.generation = 0
 
     def __del__(self) -> None:
         try:
@@ -97,17 +101,60 @@ class PackedLayerMixin:
             (t.data_ptr(), t._version, t.device, t.dtype) if torch.is_tensor(t) else t for t in self._layer_tensors()
         )
 
+    def _weights_only_change(self, old: tuple, new: tuple) -> bool:
+        """True when the two signatures differ only in the ``_version`` of conditioner weights / biases
+        (an optimizer step): same storage, device, dtype, masks, options."""
+        hyper = getattr(self, "hyper", None)
+        if hyper is None or len(old) != len(new):
+            return False
+        n_lin = len(hyper._linears())
+        wb = {2 + 3 * i + j for i in range(n_lin) for j in (0, 1)}  # positions of (weight, bias) in _layer_tensors
+        for k, (a, b) in enumerate(zip(old, new)):
+            if a == b:
+                continue
+            if k not in wb or a is None or b is None or (a[0], a[2], a[3]) != (b[0], b[2], b[3]):
+                return False
+        return True
+
     def _zk_layer_ref(self) -> OwnedLayer:
-        """The packed handle as a reference-counted owner: calls that outlive a re-pack (an
-        autograd graph held across an optimizer step) keep the handle they were built with."""
+        """The packed handle as a reference-counted owner.  A change of anything structural (storage,
+        masks, options, device) builds a new handle — calls that outlive it keep the one they were built
+        with; an optimizer step (only the weights' versions moved) refreshes the packed copies IN PLACE
+        with stream-ordered kernels (``zk_layer_update_weights``: no mask download, no allocation, no
+        host synchronisation).
+
+        Writes through ``.data`` (EMA copies, weight clipping) do not bump ``_version`` and are invisible
+        here: call :func:`zuko_b200.invalidate` on the module afterwards."""
         sig = self._layer_signature()
         cached = self.__dict__.get("_zk_cache")
         if cached is not None and cached[0] == sig:
             return cached[1]
+        dev = next((t.device for t in self._layer_tensors() if torch.is_tensor(t) and t.is_cuda), None)
+        if cached is not None and dev is not None and self._weights_only_change(cached[0], sig):
+            ref = cached[1]
+            lins = self.hyper._linears()
+            n = len(lins)
+            keep = [m.weight.detach().contiguous() for m in lins]
+            keep += [None if m.bias is None else m.bias.detach().contiguous() for m in lins]
+            W = (ctypes.c_void_p * n)(*[t.data_ptr() for t in keep[:n]])
+            Bv = (ctypes.c_void_p * n)(*[None if t is None else t.data_ptr() for t in keep[n:]])
+            with torch.cuda.device(dev):
+                E.check(E.lib().zk_layer_update_weights(ref.handle, W, Bv, E.stream_ptr(dev)))
+            ref.generation += 1
+            self.__dict__["_zk_cache"] = (sig, ref)
+            return ref
         self._zk_release()
         desc, keep = self._layer_desc()
         h = ctypes.c_void_p()
-        E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
+        if dev is not None:
+            with torch.cuda.device(dev):
+                E.lib().zk_set_pack_stream(E.stream_ptr(dev))  # the pack kernels wait for work queued on this stream
+                try:
+                    E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
+                finally:
+                    E.lib().zk_set_pack_stream(None)
+        else:
+            E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
         del keep
         ref = OwnedLayer(h)
         self.__dict__["_zk_cache"] = (sig, ref)

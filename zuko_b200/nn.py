@@ -194,7 +194,13 @@ class _EngineMLP(nn.Sequential):
         self._release()
         desc, keep = self.mlp_desc()
         h = ctypes.c_void_p()
-        E.check(E.lib().zk_mlp_create(ctypes.byref(desc), ctypes.byref(h)))
+        dev = self._linears()[0].weight.device
+        with torch.cuda.device(dev):
+            E.lib().zk_set_pack_stream(E.stream_ptr(dev))  # the pack kernels wait for work queued on this stream
+            try:
+                E.check(E.lib().zk_mlp_create(ctypes.byref(desc), ctypes.byref(h)))
+            finally:
+                E.lib().zk_set_pack_stream(None)
         del keep
         self.__dict__["_zk_cache"] = (sig, h)
         return h
@@ -217,6 +223,13 @@ class _EngineMLP(nn.Sequential):
 
     def forward(self, x: Tensor) -> Tensor:
         E.require_cuda(x, "conditioner input")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # the stand-alone conditioner call has no autograd seam (gradients flow through the flow-level
+            # calls, _ops._FlowFunction): refuse rather than return a tensor that silently drops them
+            raise NotImplementedError(
+                "zuko_b200: MLP / MaskedMLP called on its own is forward-only; wrap the call in torch.no_grad(), "
+                "or differentiate through flow(c).log_prob / transform.call_and_ladj / rsample"
+            )
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         B = x2.shape[0]
