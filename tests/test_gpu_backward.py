@@ -135,9 +135,50 @@ def _flow_grads(flow, x, c, mode, gg, device):
     return cpu(xt.grad), (None if ct is None else cpu(ct.grad)), named_param_grads(flow)
 
 
+# kink tiers (cases.relu_kink_rows): the split-bf16 conditioner carries ~1e-6..1e-5 of relative error in a
+# pre-activation, the exact-order fp32 conditioner ~1e-7; layer inputs ~1e-5 / ~1e-6 against the knots
+TAU_BF16, TAU_KNOT_BF16 = 1e-5, 5e-5
+TAU_FP32, TAU_KNOT_FP32 = 1e-6, 5e-6
+MAX_EXCLUDED = 0.10
+
+
+def _kink_tiers(name, gg, x, c, mode):
+    """Splits the golden rows into (A) rows away from every non-smooth point at the production
+    (split-bf16) precision, (B) rows within that precision of a ReLU kink / spline knot but NOT within the
+    exact-order fp32 precision — arbitrated with gemm_mode="fp32" instead of being dropped — and (C) rows
+    where even fp32 arithmetic may sit on either side (zero weight; the golden sums are corrected for
+    them with the pinned gradient oracle: gradients are linear in the per-row weights).
+    Returns (weights of tier A, weights of tier B, corrected golden reference, fractions)."""
+    cpu_flow = build_flow(name)
+    spec = O.flowspec_from_module(cpu_flow)
+    near_bf16 = relu_kink_rows(spec, x, c, tau=TAU_BF16, tau_knot=TAU_KNOT_BF16)
+    excluded = relu_kink_rows(spec, x, c, tau=TAU_FP32, tau_knot=TAU_KNOT_FP32)
+    tier_b = near_bf16 & ~excluded
+    tier_a = ~near_bf16
+    wa = {k: gg[k].copy() for k in ("g", "gz", "gl")}
+    wb = {k: gg[k].copy() for k in ("g", "gz", "gl")}
+    for k in wa:
+        wa[k][~tier_a] = 0.0
+        wb[k][~tier_b] = 0.0
+    ref = {"gx": gg[f"{mode}/gx"].copy(), "gc": None if c is None else gg[f"{mode}/gc"].copy(), "minus": None}
+    if excluded.any():
+        ck = c if (c is None or c.ndim == 1) else c[excluded]
+        kw = dict(g_log_prob=gg["g"][excluded]) if mode == "lp" else dict(g_z=gg["gz"][excluded], g_ladj=gg["gl"][excluded])
+        _, ogc, lgs = OG.flow_backward(spec, x[excluded], ck, **kw)
+        ref["gx"][excluded] = 0.0
+        if c is not None:
+            if c.ndim == 1:
+                ref["gc"] = ref["gc"] - ogc
+            else:
+                ref["gc"][excluded] = 0.0
+        ref["minus"] = oracle_named_grads(cpu_flow, lgs)
+    frac = {"production": float(tier_a.mean()), "fp32_arbitrated": float(tier_b.mean()), "excluded": float(excluded.mean())}
+    return wa, wb, ref, frac
+
+
 def _without_kink_rows(name, gg, x, c, mode):
-    """Gives the rows at a ReLU kink (cases.relu_kink_rows) zero weight: returns the modified weights,
-    the golden gradients corrected by the gradient oracle for those rows, and the row mask."""
+    """Single-tier variant (rows near a non-smooth point at the production precision get zero weight):
+    used by the tests that compare two engine arithmetics with each other."""
     cpu_flow = build_flow(name)
     spec = O.flowspec_from_module(cpu_flow)
     kink = relu_kink_rows(spec, x, c)
@@ -159,15 +200,31 @@ def _without_kink_rows(name, gg, x, c, mode):
     return w, ref, kink
 
 
+def _fp32_mode_flow(name, device):
+    flow = build_flow(name)
+    for t in flow.transform.transforms:
+        if getattr(t, "hyper", None) is not None and hasattr(t.hyper, "gemm_mode"):
+            t.hyper.gemm_mode = "fp32"
+    return flow.to(device)
+
+
 @pytest.mark.parametrize("mode", ["lp", "tr"])
 @pytest.mark.parametrize("name", GRAD_CASES_FULL + GRAD_CASES_SAMPLED)
-def test_flow_gradients_vs_reference_autograd(device, name, mode):
+def test_flow_gradients_vs_reference_autograd(device, name, mode, record_property):
     gg, x, c = grad_inputs(name)
     flow = build_flow(name).to(device)
     rtol = 1e-2 if name == "nsf6_stress" else 5e-5
-    w, ref, kink = _without_kink_rows(name, gg, x, c, mode)
-    assert kink.mean() <= 0.6, f"{name}: {kink.sum()} of {kink.size} rows at a ReLU kink"
-    gx, gc, pg = _flow_grads(flow, x, c, mode, w, device)
+    wa, wb, ref, frac = _kink_tiers(name, gg, x, c, mode)
+    record_property("kink_rows", frac)
+    print(f"{name}/{mode}: rows checked in production mode {frac['production']:.1%}, arbitrated in fp32 mode "
+          f"{frac['fp32_arbitrated']:.1%}, excluded {frac['excluded']:.1%}")
+    assert frac["excluded"] <= MAX_EXCLUDED, f"{name}: {frac['excluded']:.1%} of the golden rows are non-smooth even at fp32 precision"
+    gx, gc, pg = _flow_grads(flow, x, c, mode, wa, device)
+    if frac["fp32_arbitrated"] > 0:  # the rows the split-bf16 arithmetic cannot decide: exact-order conditioner
+        gx2, gc2, pg2 = _flow_grads(_fp32_mode_flow(name, device), x, c, mode, wb, device)
+        gx = gx + gx2
+        gc = None if gc is None else gc + gc2
+        pg = {k: v + pg2[k] for k, v in pg.items()}
     close(gx, ref["gx"], grad_bar(gg, f"{mode}/", "gx", rtol, 3.0), f"{name} d/dx")
     if c is not None:
         close(gc, ref["gc"], grad_bar(gg, f"{mode}/", "gc", rtol, 3.0), f"{name} d/dc")
