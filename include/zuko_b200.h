@@ -372,6 +372,10 @@ int zk_set_fast_math(int on);
  * 0: always one GEMM kernel per linear layer + the stand-alone bijector kernel.  Returns the
  * previous value. */
 int zk_set_fused_layers(int on);
+/* Smallest (equal) hidden width that is routed to the CTA-pair fused kernel (cta_group::2 MMAs, the only
+ * one for widths 384 / 512): 256 (default) or 384 — with 384, width-256 conditioners run on the
+ * one-CTA-per-tile kernel as in round 1.  Applies to handles created afterwards.  Returns the previous value. */
+int zk_set_wide_min_hidden(int h);
 /* Profiling hook: a DEVICE buffer of >= 256 int64 that the fused layer kernel fills with clock64()
  * stamps of its pipeline events (CTA 0, third tile); NULL (default) disables it. */
 void zk_debug_timeline(long long* device_buffer);

@@ -8,12 +8,14 @@ torch.manual_seed(0)
 torch.set_grad_enabled(False)
 dev = torch.device('cuda:0')
 which = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
-if which == 'cfg3':
+if which == 'cfg2':
+    flow, D, C = zuko.flows.NSF(16, 8, transforms=1, bins=8, hidden_features=[256] * 3), 16, 8
+elif which == 'cfg3':
     flow, D, C = zuko.flows.MAF(32, 0, transforms=1, hidden_features=[512] * 4), 32, 0
 else:
     flow, D, C = zuko.flows.NSF(64, 16, transforms=1, bins=16, hidden_features=[512] * 3), 64, 16
 flow = flow.to(dev)
-B = 1 << 19
+B = 1 << 20 if which == 'cfg2' else 1 << 19
 x = torch.randn(B, D, device=dev); c = torch.randn(B, C, device=dev) if C else None
 flow(c).log_prob(x); torch.cuda.synchronize()
 buf = torch.zeros(512, dtype=torch.int64, device=dev)

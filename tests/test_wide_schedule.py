@@ -16,6 +16,7 @@ from zuko_b200 import _engine as E
 FIRST, LAST, AWAIT, AFREE, OUT = 8, 16, 32, 64, 128
 
 CASES = {
+    "cfg2_nsf": lambda: zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 3),  # hidden width 256: 2 chunks, 4 K blocks
     "cfg3_maf": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[512] * 4),
     "cfg5_nsf": lambda: zuko.flows.NSF(64, 16, transforms=2, bins=16, hidden_features=[512] * 3),
     "nsf24_k8_h512": lambda: zuko.flows.NSF(24, 0, transforms=2, bins=8, hidden_features=[512, 512]),  # classes not aligned to chunks
@@ -241,5 +242,5 @@ def test_wide_input_with_context_is_rejected_not_deadlocked():
 
 def test_unsupported_shapes_are_reported():
     ones = lambda d: [np.ones((d[i + 1], d[i]), np.uint8) for i in range(len(d) - 1)]  # noqa: E731
-    assert _schedule([16, 256, 256, 32], ones([16, 256, 256, 32]), E.ZK_UNI_AFFINE, 0, 16, 0)[0] == -1  # narrow kernel's shape
+    assert _schedule([16, 128, 128, 32], ones([16, 128, 128, 32]), E.ZK_UNI_AFFINE, 0, 16, 0)[0] == -1  # narrow kernel's shape
     assert _schedule([16, 512, 384, 32], ones([16, 512, 384, 32]), E.ZK_UNI_AFFINE, 0, 16, 0)[0] == -1  # unequal hidden widths

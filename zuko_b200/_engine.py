@@ -104,6 +104,7 @@ _SIGNATURES = {
     "zk_launch_count": (c_int64, []),
     "zk_set_fast_math": (c_int, [c_int]),
     "zk_set_fused_layers": (c_int, [c_int]),
+    "zk_set_wide_min_hidden": (c_int, [c_int]),
     "zk_set_tc_backward": (c_int, [c_int]),
     "zk_debug_timeline": (None, [c_void_p]),
     "zk_debug_watchdog_read": (c_int, [c_void_p, c_int]),

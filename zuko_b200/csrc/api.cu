@@ -54,6 +54,7 @@ const char* zk_last_error(void) { return g_last_error.c_str(); }
 int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
+int zk_set_wide_min_hidden(int h) { return g_wide_min_h.exchange(h); }
 static thread_local cudaStream_t g_pack_stream = nullptr;
 void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
 int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
@@ -453,7 +454,7 @@ int zk_layer_fused_info(const zk_layer* l, double* out) {
     out[3] = dense;
     const TcPack* pk = tc_pack_of(m);
     if (!pk || l->circ || !fused_layer_supported(m, l->uni, l->K, l->D, l->C)) return 0;
-    const bool wide = fused_wide_shape(m, l->uni, l->K, l->D, l->C);
+    const bool wide = fused_wide_shape(m, l->uni, l->K, l->D, l->C) && pk->wide.ready;
     out[0] = wide ? 2.0 : 1.0;
     out[1] = wide ? pk->wide.n_items : pk->fused.n_items;
     out[2] = wide ? pk->wide.issued_macs_per_row : pk->fused.issued_macs_per_row;
@@ -695,24 +696,41 @@ struct FlowPlan {
     size_t fixed = 0;    // fixed bytes
 };
 
-size_t flow_ws_for(const zk_flow_desc* f, int64_t Bc) {
+// scratch one layer needs beyond its input / output for ONE direction, with the kernels that will
+// actually run (a fused forward layer or a dimension-sequential inverse layer keeps phi and the hidden
+// activations on chip: nothing), dir: 1 forward, 2 inverse, 0 either (the public, conservative figure)
+size_t layer_ws_dir(const zk_layer* l, int64_t Bc, int dir) {
+    if (dir != 0 && l->kind == ZK_LAYER_AUTOREGRESSIVE && g_fused.load()) {
+        const bool fwd_fused = !l->circ && fused_layer_supported(l->hyper, l->uni, l->K, l->D, l->C);
+        const bool inv_seq = (l->inv != nullptr || l->inv_dirty);
+        if (dir == 1 && fwd_fused) return 0;
+        if (dir == 2 && inv_seq) return 0;
+    }
+    return zk_layer_workspace_bytes(l, Bc);
+}
+
+size_t flow_ws_for(const zk_flow_desc* f, int64_t Bc, int dir = 0) {
     const int D = f->features;
     size_t layer_max = 0;
-    for (int i = 0; i < f->n_layers; ++i)
-        layer_max = std::max(layer_max, zk_layer_workspace_bytes(f->layers[i], Bc));
+    for (int i = 0; i < f->n_layers; ++i) {
+        size_t need = layer_ws_dir(f->layers[i], Bc, dir);
+        // inverse + log_prob: a layer whose inverse kernel cannot emit its ladj runs its forward as well
+        if (dir == 2 && need != 0) need = std::max(need, layer_ws_dir(f->layers[i], Bc, 1));
+        layer_max = std::max(layer_max, need);
+    }
     return 2 * a256((size_t)Bc * D * 4)      // ping-pong activations
            + a256((size_t)Bc * 4)            // ladj
            + a256((size_t)Bc * D * 4)        // x scratch for inverse + log_prob
            + a256(reduce_scratch_bytes()) + layer_max + 1024;
 }
 
-int64_t flow_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes) {
-    if (flow_ws_for(f, B) <= ws_bytes) return B;
+int64_t flow_chunk_rows(const zk_flow_desc* f, int64_t B, size_t ws_bytes, int dir = 0) {
+    if (flow_ws_for(f, B, dir) <= ws_bytes) return B;
     int64_t lo = 1, hi = B;  // largest chunk that fits (monotone in Bc)
-    if (flow_ws_for(f, 1) > ws_bytes) return 0;
+    if (flow_ws_for(f, 1, dir) > ws_bytes) return 0;
     while (lo < hi) {
         int64_t mid = lo + (hi - lo + 1) / 2;
-        if (flow_ws_for(f, mid) <= ws_bytes) lo = mid; else hi = mid - 1;
+        if (flow_ws_for(f, mid, dir) <= ws_bytes) lo = mid; else hi = mid - 1;
     }
     // keep tiles aligned: round down to a multiple of 1024 rows when possible
     if (lo >= 2048) lo = lo / 1024 * 1024;
@@ -886,7 +904,7 @@ zk_status zk_flow_forward(const zk_flow_desc* f, const float* x, int64_t ldx, co
     ZK_REQUIRE(B >= 0 && ldx >= f->features && ldz >= f->features, "flow_forward: bad shape");
     ZK_REQUIRE(f->context == 0 || c, "flow_forward: flow needs a context");
     if (B == 0) return ZK_OK;
-    const int64_t Bc = flow_chunk_rows(f, B, ws_bytes);
+    const int64_t Bc = flow_chunk_rows(f, B, ws_bytes, 1);
     ZK_REQUIRE(Bc > 0, "flow_forward: workspace too small (%zu < %zu)", ws_bytes, zk_flow_min_workspace_bytes(f));
     for (int64_t i0 = 0; i0 < B; i0 += Bc) {
         const int64_t n = std::min(Bc, B - i0);
@@ -905,7 +923,7 @@ zk_status zk_flow_log_prob(const zk_flow_desc* f, const float* x, int64_t ldx, c
     ZK_REQUIRE(f->context == 0 || c, "flow_log_prob: flow needs a context");
     cudaStream_t st = (cudaStream_t)stream;
     if (B > 0) {
-        const int64_t Bc = flow_chunk_rows(f, B, ws_bytes);
+        const int64_t Bc = flow_chunk_rows(f, B, ws_bytes, 1);
         ZK_REQUIRE(Bc > 0, "flow_log_prob: workspace too small (%zu < %zu)", ws_bytes, zk_flow_min_workspace_bytes(f));
         for (int64_t i0 = 0; i0 < B; i0 += Bc) {
             const int64_t n = std::min(Bc, B - i0);
@@ -929,7 +947,7 @@ zk_status zk_flow_inverse(const zk_flow_desc* f, const float* z, int64_t ldz, co
     ZK_REQUIRE(B >= 0 && ldx >= f->features && ldz >= f->features, "flow_inverse: bad shape");
     ZK_REQUIRE(f->context == 0 || c, "flow_inverse: flow needs a context");
     if (B == 0) return ZK_OK;
-    const int64_t Bc = flow_chunk_rows(f, B, ws_bytes);
+    const int64_t Bc = flow_chunk_rows(f, B, ws_bytes, 2);
     ZK_REQUIRE(Bc > 0, "flow_inverse: workspace too small (%zu < %zu)", ws_bytes, zk_flow_min_workspace_bytes(f));
     for (int64_t i0 = 0; i0 < B; i0 += Bc) {
         const int64_t n = std::min(Bc, B - i0);

@@ -621,11 +621,14 @@ static bool fused_narrow_shape(const zk_mlp* m, int univariate, int bins, int D,
     return univariate == ZK_UNI_AFFINE;
 }
 
-bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
-    if (fused_narrow_shape(m, univariate, bins, D, C)) return true;
+static bool wide_ready(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;  // wide shapes: only once the issue schedule passed its dry run
-    return fused_wide_shape(m, univariate, bins, D, C) && pk->wide.ready && pk->wide.uni == univariate &&
+    return pk && fused_wide_shape(m, univariate, bins, D, C) && pk->wide.ready && pk->wide.uni == univariate &&
            pk->wide.bins == bins && pk->wide.D == D && pk->wide.C == C;
+}
+
+bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
+    return fused_narrow_shape(m, univariate, bins, D, C) || wide_ready(m, univariate, bins, D, C);
 }
 
 namespace {
@@ -755,7 +758,10 @@ zk_status fused_refresh(zk_mlp* m, cudaStream_t st) {
 }
 
 zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {
-    if (fused_wide_shape(m, univariate, bins, D, C)) return fused_wide_prepare(m, mask_dev, univariate, bins, D, C);
+    if (fused_wide_shape(m, univariate, bins, D, C)) {  // CTA-pair kernel first; hidden width 256 may fall back to this one
+        ZK_TRY(fused_wide_prepare(m, mask_dev, univariate, bins, D, C));
+        if (wide_ready(m, univariate, bins, D, C)) return ZK_OK;
+    }
     if (!fused_narrow_shape(m, univariate, bins, D, C)) return ZK_OK;
     TcPack* pk = (TcPack*)m->tc;
     FusedPack& f = pk->fused;
@@ -848,7 +854,7 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
 
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t st) {
     const TcPack* pk = (const TcPack*)m->tc;
-    if (pk && fused_wide_shape(m, a.univariate, a.bins, a.D, a.C)) return launch_fused_wide(m, a, st);
+    if (wide_ready(m, a.univariate, a.bins, a.D, a.C)) return launch_fused_wide(m, a, st);
     ZK_REQUIRE(pk && fused_narrow_shape(m, a.univariate, a.bins, a.D, a.C), "fused layer: unsupported shape");
     ZK_REQUIRE(a.B < ((int64_t)1 << 31) - FM, "fused layer: batch too large for one launch");
     if (a.B == 0) return ZK_OK;

@@ -1,6 +1,8 @@
 // zuko_b200 — fully fused flow-layer kernel (conditioner + bijector + ladj): interface.
 #pragma once
 
+#include <atomic>
+
 #include "mlp.cuh"
 
 #define ZK_FUSED_MAX_LINEAR 6
@@ -34,6 +36,7 @@ zk_status fused_wide_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univ
 zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t stream);
 int wide_schedule_host(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins, int D,
                        int C, uint32_t* out_items, int max_items, uint32_t* out_rd_mask, int* out_perm);
+extern std::atomic<int> g_wide_min_h;
 extern uint32_t* g_watch_host;  // watchdog report buffer of the wide kernel (pinned host memory) or null
 zk_status fused_refresh(zk_mlp* m, cudaStream_t stream);  // weights changed in place: re-split into the fused packs
 extern long long* g_timeline;  // device buffer of >= 256 stamps, or null (zk_debug_timeline)

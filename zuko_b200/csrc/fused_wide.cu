@@ -27,8 +27,14 @@
 //   [  0,256)  A hi : bf16 pairs, K element k in column k/2                     (K <= 512)
 //   [256,384)  D buffer 0 (fp32 accumulators of one <= 128-column chunk)
 //   [384,512)  D buffer 1
-// Shared memory (per CTA): A lo 8 x 16 KB | W ring n x 16 KB (64 rows x 64 K x hi, lo) | barriers,
+// Shared memory (per CTA): A lo (H / 64) x 16 KB | W ring n x 16 KB (64 rows x 64 K x hi, lo) | barriers,
 //   ladj partials | bias copy.
+//
+// Hidden width 256 (BASELINE cfg2) runs here as well: the narrow kernel (fused_layer.cu) multicasts
+// FULL weight tiles to both CTAs of a pair and reads all three split products' B operand from its own
+// shared memory — 64 B/clk of operand reads plus 42 B/clk of TMA writes, against the 128 B/clk the
+// shared memory delivers: its K blocks take ~1250 cycles instead of 768 (profiles/
+// r01_fused_timeline_v14.txt).  The pair-MMA form halves both.
 //
 // Warp roles (640 threads, 1 CTA / SM, persistent over 256-row pair tiles):
 //   warp 0      W producer (both CTAs: each loads its half tile; completion counted on the LEADER's barrier)
@@ -41,6 +47,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "fused_common.cuh"
 
@@ -94,6 +101,7 @@ struct WideParams {
     int M;
     int in_vec;         // x / c rows can be read with 16-byte loads
     int n_wstages;
+    int alo_blocks;     // K blocks of the A lo plane kept in shared memory: max(KB0, H / 64)
     int base_off;       // offset (floats, after the bias copy) of the base table [3][D]: loc, 1/scale, log scale + log sqrt(2 pi)
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
@@ -238,7 +246,7 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int NW = p.n_wstages;
     uint8_t* sAlo = smem;
-    uint8_t* sW = smem + W_ALO_BYTES;
+    uint8_t* sW = smem + (size_t)p.alo_blocks * W_APLANE;
     uint64_t* bars = (uint64_t*)(sW + (size_t)NW * W_WSTAGE);
     uint64_t* w_full = bars;        // [8]  (leader's copy is the one in use)
     uint64_t* w_empty = bars + 8;   // [8]  each CTA its own (multicast commit)
@@ -775,10 +783,12 @@ bool wide_dry_run(const std::vector<uint2>& items, const uint32_t* rd_mask, cons
 
 }  // namespace
 
+std::atomic<int> g_wide_min_h{256};  // smallest hidden width routed to this kernel (zk_set_wide_min_hidden)
+
 static bool wide_dims_ok(const int* dims, int L, int univariate, int bins, int D, int C) {
     if (L < 2 || L > ZK_FUSED_MAX_LINEAR) return false;
     const int H = dims[1];
-    if (H % 128 != 0 || H <= 256 || H > 512) return false;
+    if (H % 128 != 0 || H < std::max(256, g_wide_min_h.load()) || H > 512) return false;
     for (int i = 1; i < L; ++i)
         if (dims[i] != H) return false;
     if (D + C > 512 || dims[0] != D + C) return false;
@@ -961,7 +971,9 @@ zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     p.in_vec = (x_ok && c_ok) ? 1 : 0;
     // shared memory: A lo + aux are fixed; the weight ring gets what is left after the bias copy of
     // the OUTPUT layer (47 reads per dim and thread) and as many hidden-layer biases as still fit
-    const uint32_t avail = W_SMEM_MAX - 1024u - W_ALO_BYTES - W_AUX_BYTES;
+    p.alo_blocks = std::max(p.KB0, p.H / WK);
+    const uint32_t alo_bytes = (uint32_t)p.alo_blocks * W_APLANE;
+    const uint32_t avail = W_SMEM_MAX - 1024u - alo_bytes - W_AUX_BYTES;
     p.n_wstages = (int)std::min<uint32_t>(W_MAX_WSTAGES, avail / W_WSTAGE);
     uint32_t bias_room = (avail - (uint32_t)p.n_wstages * W_WSTAGE) / 4u;  // floats
     if (bias_room < 64u && p.n_wstages > 4) { --p.n_wstages; bias_room += W_WSTAGE / 4u; }
@@ -982,7 +994,7 @@ zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     for (int l = L; l < ZK_FUSED_MAX_LINEAR; ++l) { p.bias[l] = nullptr; p.bias_off[l] = -1; p.bias_len[l] = 0; }
     for (int l = 0; l < L; ++l) { p.mapW[l] = wp.maps[l]; p.rd_mask[l] = wp.rd_mask[l]; }
     p.base_off = off;
-    const size_t smem = 1024u + W_ALO_BYTES + (size_t)p.n_wstages * W_WSTAGE + W_AUX_BYTES + (size_t)(off + base_floats) * 4u;
+    const size_t smem = 1024u + alo_bytes + (size_t)p.n_wstages * W_WSTAGE + W_AUX_BYTES + (size_t)(off + base_floats) * 4u;
     if (g_watch_host == nullptr) {
         uint32_t* h = nullptr;
         if (cudaHostAlloc((void**)&h, W_WATCH_WORDS * 4, cudaHostAllocMapped) == cudaSuccess) {
