@@ -332,7 +332,7 @@ def fused_info(flow) -> dict:
     for layer in flow.transform.transforms:
         out = (ctypes.c_double * 4)()
         k = E.lib().zk_layer_fused_info(layer._zk_layer(), out)
-        kinds.append({0: "per-layer GEMM kernels", 1: "fused_layer_kernel", 2: "fused_wide_kernel"}.get(k, "?"))
+        kinds.append({0: "per-layer GEMM kernels", 1: "fused_layer_kernel", 2: "fused_wide_kernel", 3: "fused_dual_kernel"}.get(k, "?"))
         issued += out[2]
         dense += out[3]
         entries += int(out[1])
@@ -416,6 +416,11 @@ def time_config(cfg, dev, rank, world, peaks, steps, nvml=None) -> dict:
                            "kernel": info["kernel"], "algorithmic_flops_per_step": flops, "issued_flops_per_step": 2.0 * info["issued_macs_per_row"] * rows,
                            "frac_issued": 2.0 * info["issued_macs_per_row"] * rows / (ms_per_step * 1e-3) / 1e12 / peak,
                            "traffic": None, "algorithmic_hbm_bytes": 4.0 * (D + C + 1) * rows}  # fmt: skip
+        tj = ncu_traffic().get(f"{cfg['name']}_layer")
+        if tj:  # one `ncu --set full` capture of one flow layer of this config: bytes per launch and the rows it covered
+            out["roofline"]["traffic"] = tj.get("bytes")
+            out["roofline"]["traffic_rows"] = tj.get("rows")
+            out["roofline"]["traffic_captured_at"] = ncu_traffic().get("git_sha")
     else:
         # every weight of the masked conditioner is visited once per sample (ar_inverse.cu): 2 FLOP per
         # non-zero weight; roofline = fp32 FMA pipe, 148 SMs x 128 lanes x 2 x SM clock (nominal)
@@ -675,6 +680,7 @@ def time_kernels(flow, x, c, dev, peaks, iters: int, peak_tf: float | None = Non
     def fused():
         E.check(L.zk_layer_forward(hl, x.data_ptr(), D, c.data_ptr(), C, B, y.data_ptr(), D, ladj.data_ptr(), 1, ws.data_ptr(), ws.numel(), st))
 
+
     dims = [D + C, *H, D * P]
     flops = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * B  # dense FLOPs nn.py:218 executes
     rqs_bytes = 4.0 * (D + D * P + D + 1) * B  # x + phi + y + ladj
@@ -684,6 +690,8 @@ def time_kernels(flow, x, c, dev, peaks, iters: int, peak_tf: float | None = Non
     peak_tf = peak_tf or peaks["bf16_tflops_sustained"]
     info = fused_info(flow)
     issued = 2.0 * info["issued_macs_per_row"] / T * B  # one flow layer, from the pack's tile table
+    fused_name = {"fused_wide_kernel": "fused_wide_kernel<RQS,8> (CTA pairs, cta_group::2)",
+                  "fused_dual_kernel": "fused_dual_kernel<RQS,8> (CTA pairs, two sub-tiles in flight)"}.get(info["kernel"][0], "fused_layer_kernel<RQS,8>")
     n0 = L.zk_launch_count()
     fused()
     is_fused = (L.zk_launch_count() - n0) == 1
@@ -691,9 +699,9 @@ def time_kernels(flow, x, c, dev, peaks, iters: int, peak_tf: float | None = Non
         fused()
         t = cuda_time_ms(fused, iters)
         tf = flops / (t * 1e-3) / 1e12
-        out.append({"name": "fused_layer_kernel<RQS,8> (conditioner 24-256-256-256-368 on tcgen05 + RQS + ladj), one flow layer",
+        out.append({"name": fused_name + " (conditioner 24-256-256-256-368 on tcgen05 + RQS + ladj), one flow layer",
                     "bound": "tensor", "achieved": tf, "peak": peak_tf, "peak_kind": peak_kind, "unit": "TFLOP/s",
-                    "frac": tf / peak_tf, "traffic": traffic.get("fused_layer_kernel"), "traffic_captured_at": traffic.get("git_sha"),
+                    "frac": tf / peak_tf, "traffic": traffic.get(info["kernel"][0] + "_cfg2", traffic.get("fused_layer_kernel") if info["kernel"][0] == "fused_layer_kernel" else None), "traffic_captured_at": traffic.get("git_sha"),
                     "ms_per_launch": t, "ms_per_step": t * T,
                     "algorithmic_flops": flops, "issued_flops": issued, "frac_issued": issued / (t * 1e-3) / 1e12 / peak_tf,
                     "algorithmic_hbm_bytes": fused_bytes, "in_step": True})  # fmt: skip
@@ -717,6 +725,28 @@ def time_kernels(flow, x, c, dev, peaks, iters: int, peak_tf: float | None = Non
          "traffic_captured_at": traffic.get("git_sha"), "ms_per_launch": t_rqs,
          "ms_per_step": t_rqs * T, "algorithmic_bytes": rqs_bytes, "in_step": not is_fused},
     ]  # fmt: skip
+    # the HBM-roofline kernel at the cfg5 shape (D = 64, K = 16: 12 548 B per sample)
+    try:
+        D5, K5, B5 = 64, 16, 1 << 19
+        P5 = 3 * K5 - 1
+        x5 = torch.randn(B5, D5, device=dev)
+        phi5 = torch.randn(B5, D5 * P5, device=dev)
+        y5 = torch.empty_like(x5)
+        l5 = torch.zeros(B5, device=dev)
+
+        def rqs5():
+            E.check(L.zk_rqs_forward(x5.data_ptr(), D5, phi5.data_ptr(), D5 * P5, B5, D5, K5, 5.0, 1e-3, y5.data_ptr(), D5, l5.data_ptr(), 1, st))
+
+        rqs5()
+        t5 = cuda_time_ms(rqs5, iters)
+        b5 = 4.0 * (D5 + D5 * P5 + D5 + 1) * B5
+        g5 = b5 / (t5 * 1e-3) / 1e9
+        out.append({"name": "uni_kernel<RQS,16> stand-alone fused RQS + ladj at the cfg5 shape (D = 64, K = 16, 2^19 rows, phi in HBM)", "bound": "hbm",
+                    "achieved": g5, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g5 / peaks["hbm_gbs"], "traffic": traffic.get("uni_kernel_rqs16"),
+                    "traffic_captured_at": traffic.get("git_sha"), "ms_per_launch": t5, "ms_per_step": 0.0, "algorithmic_bytes": b5, "in_step": False})  # fmt: skip
+        del x5, phi5, y5, l5
+    except Exception as e:  # noqa: BLE001
+        out.append({"name": "uni_kernel<RQS,16> (cfg5 shape)", "error": f"{type(e).__name__}: {e}"[:200], "in_step": False, "ms_per_step": 0.0})
     return out
 
 

@@ -212,7 +212,8 @@ void zk_set_pack_stream(zk_stream stream);
 size_t zk_layer_workspace_bytes(const zk_layer* layer, int64_t B);
 /* Bench bookkeeping: which kernel runs an autoregressive layer's forward (flows/autoregressive.py:
  * 207-215) and how much tensor-core work its issue schedule holds.  Returns 0 = per-layer GEMM
- * kernels, 1 = fused layer kernel, 2 = wide fused layer kernel (CTA pairs); out[0] = the same,
+ * kernels, 1 = fused layer kernel, 2 = wide fused layer kernel (CTA pairs), 3 = dual-tile CTA-pair
+ * kernel; out[0] = the same,
  * out[1] = schedule entries per tile, out[2] = MACs ISSUED per sample row (non-zero tiles only, all
  * split-bf16 terms), out[3] = dense MACs per sample row (what nn.py:218 executes). */
 int zk_layer_fused_info(const zk_layer* layer, double* out);
@@ -376,6 +377,10 @@ int zk_set_fused_layers(int on);
  * one for widths 384 / 512): 256 (default) or 384 — with 384, width-256 conditioners run on the
  * one-CTA-per-tile kernel as in round 1.  Applies to handles created afterwards.  Returns the previous value. */
 int zk_set_wide_min_hidden(int h);
+/* 1 (default): conditioners of (equal) hidden width 128 / 256 with D + C <= 256 run on the dual-tile
+ * CTA-pair kernel (two 128-row sub-tiles in flight per CTA: the MMAs of one overlap the epilogue of the
+ * other); 0: the one-tile kernels as before.  Applies to handles created afterwards.  Returns the previous value. */
+int zk_set_dual_tiles(int on);
 /* Profiling hook: a DEVICE buffer of >= 256 int64 that the fused layer kernel fills with clock64()
  * stamps of its pipeline events (CTA 0, third tile); NULL (default) disables it. */
 void zk_debug_timeline(long long* device_buffer);
@@ -388,6 +393,11 @@ void zk_debug_timeline(long long* device_buffer);
  * concatenated (out_perm, may be NULL).  Returns the number of entries; -1 shape not supported,
  * -2 the protocol dry run rejected the schedule, -3 max_items too small. */
 int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
+                           int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
+                           int* out_perm);
+/* Same for the dual-tile kernel (hidden width 128 / 256): the schedule of one 512-row pair tile, entries of
+ * the two sub-tiles interleaved chunk by chunk (bit 2 of the flags = sub-tile; csrc/fused_dual.cu). */
+int zk_debug_dual_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
                            int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
                            int* out_perm);
 /* Debugging aid of the wide fused kernel: every wait inside it is bounded (~2 s); a wait that

@@ -1,5 +1,5 @@
-"""cfg2 (NSF(16, 8, T4, K8, [256]^3) log_prob, 2^20 rows): the CTA-pair fused kernel against the
-one-CTA-per-tile kernel of round 1 (zk_set_wide_min_hidden), plus parity of both against each other."""
+"""cfg2 (NSF(16, 8, T4, K8, [256]^3) log_prob, 2^20 rows) on the three fused kernels: dual-tile CTA pairs
+(default), one-tile CTA pairs (zk_set_dual_tiles(0)), one CTA per tile (+ zk_set_wide_min_hidden(384))."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 import zuko_b200 as zuko
@@ -10,8 +10,8 @@ B = 1 << 20
 torch.manual_seed(1)
 x = torch.randn(B, 16, device=dev); c = torch.randn(B, 8, device=dev)
 outs = {}
-for min_h in (384, 256):
-    E.lib().zk_set_wide_min_hidden(min_h)
+for name, dual, min_h in (("narrow (one CTA per tile)", 0, 384), ("pair, one tile", 0, 256), ("pair, two sub-tiles", 1, 256)):
+    E.lib().zk_set_dual_tiles(dual); E.lib().zk_set_wide_min_hidden(min_h)
     torch.manual_seed(0)
     flow = zuko.flows.NSF(16, 8, transforms=4, bins=8, hidden_features=[256] * 3).to(dev)
     d = flow(c); lp = d.log_prob(x); torch.cuda.synchronize()
@@ -21,6 +21,7 @@ for min_h in (384, 256):
     for _ in range(20): lp = d.log_prob(x)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    outs[min_h] = lp
-    print(f"cfg2 log_prob B=2^20, kernel={'pair (wide)' if min_h == 256 else 'one CTA per tile (narrow)'}: {ms:.3f} ms/step -> {B / ms * 1e3:.4e} samples/s")
-print("max |lp_wide - lp_narrow| =", (outs[256] - outs[384]).abs().max().item())
+    outs[name] = lp
+    print(f"cfg2 log_prob B=2^20, kernel = {name}: {ms:.3f} ms/step -> {B / ms * 1e3:.4e} samples/s", flush=True)
+ref = outs["narrow (one CTA per tile)"]
+for k, v in outs.items(): print(f"max |lp[{k}] - lp[narrow]| = {(v - ref).abs().max().item():.3e}")

@@ -55,12 +55,19 @@ int64_t zk_launch_count(void) { return g_launches.load(); }
 int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
 int zk_set_wide_min_hidden(int h) { return g_wide_min_h.exchange(h); }
+int zk_set_dual_tiles(int on) { return g_dual.exchange(on ? 1 : 0); }
 static thread_local cudaStream_t g_pack_stream = nullptr;
 void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
 int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
                            int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
                            int* out_perm) {
     return zk::wide_schedule_host(n_linear, dims, masks_host, univariate, bins, features, context, out_items, max_items,
+                                  out_rd_mask, out_perm);
+}
+int zk_debug_dual_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,
+                           int features, int context, uint32_t* out_items, int max_items, uint32_t* out_rd_mask,
+                           int* out_perm) {
+    return zk::dual_schedule_host(n_linear, dims, masks_host, univariate, bins, features, context, out_items, max_items,
                                   out_rd_mask, out_perm);
 }
 int zk_debug_watchdog_read(uint32_t* out, int n_words) {
@@ -454,11 +461,11 @@ int zk_layer_fused_info(const zk_layer* l, double* out) {
     out[3] = dense;
     const TcPack* pk = tc_pack_of(m);
     if (!pk || l->circ || !fused_layer_supported(m, l->uni, l->K, l->D, l->C)) return 0;
-    const bool wide = fused_wide_shape(m, l->uni, l->K, l->D, l->C) && pk->wide.ready;
-    out[0] = wide ? 2.0 : 1.0;
-    out[1] = wide ? pk->wide.n_items : pk->fused.n_items;
-    out[2] = wide ? pk->wide.issued_macs_per_row : pk->fused.issued_macs_per_row;
-    return wide ? 2 : 1;
+    const int kind = fused_layer_kind(m, l->uni, l->K, l->D, l->C);
+    out[0] = kind;
+    out[1] = kind == 3 ? pk->dual.n_items : (kind == 2 ? pk->wide.n_items : pk->fused.n_items);
+    out[2] = kind == 3 ? pk->dual.issued_macs_per_row : (kind == 2 ? pk->wide.issued_macs_per_row : pk->fused.issued_macs_per_row);
+    return kind;
 }
 
 size_t zk_layer_workspace_bytes(const zk_layer* l, int64_t B) {

@@ -627,8 +627,21 @@ static bool wide_ready(const zk_mlp* m, int univariate, int bins, int D, int C) 
            pk->wide.bins == bins && pk->wide.D == D && pk->wide.C == C;
 }
 
+static bool dual_ready(const zk_mlp* m, int univariate, int bins, int D, int C) {
+    const TcPack* pk = (const TcPack*)m->tc;
+    return pk && fused_dual_shape(m, univariate, bins, D, C) && pk->dual.ready && pk->dual.uni == univariate &&
+           pk->dual.bins == bins && pk->dual.D == D && pk->dual.C == C;
+}
+
 bool fused_layer_supported(const zk_mlp* m, int univariate, int bins, int D, int C) {
-    return fused_narrow_shape(m, univariate, bins, D, C) || wide_ready(m, univariate, bins, D, C);
+    return fused_narrow_shape(m, univariate, bins, D, C) || wide_ready(m, univariate, bins, D, C) ||
+           dual_ready(m, univariate, bins, D, C);
+}
+
+int fused_layer_kind(const zk_mlp* m, int univariate, int bins, int D, int C) {
+    if (dual_ready(m, univariate, bins, D, C)) return 3;
+    if (wide_ready(m, univariate, bins, D, C)) return 2;
+    return fused_narrow_shape(m, univariate, bins, D, C) ? 1 : 0;
 }
 
 namespace {
@@ -758,7 +771,11 @@ zk_status fused_refresh(zk_mlp* m, cudaStream_t st) {
 }
 
 zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univariate, int bins, int D, int C) {
-    if (fused_wide_shape(m, univariate, bins, D, C)) {  // CTA-pair kernel first; hidden width 256 may fall back to this one
+    if (fused_dual_shape(m, univariate, bins, D, C)) {  // two sub-tiles in flight (hidden width 128 / 256)
+        ZK_TRY(fused_dual_prepare(m, mask_dev, univariate, bins, D, C));
+        if (dual_ready(m, univariate, bins, D, C)) return ZK_OK;
+    }
+    if (fused_wide_shape(m, univariate, bins, D, C)) {  // CTA-pair kernel; hidden width 256 may fall back to the narrow one
         ZK_TRY(fused_wide_prepare(m, mask_dev, univariate, bins, D, C));
         if (wide_ready(m, univariate, bins, D, C)) return ZK_OK;
     }
@@ -854,6 +871,7 @@ zk_status fused_layer_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int uni
 
 zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStream_t st) {
     const TcPack* pk = (const TcPack*)m->tc;
+    if (dual_ready(m, a.univariate, a.bins, a.D, a.C)) return launch_fused_dual(m, a, st);
     if (wide_ready(m, a.univariate, a.bins, a.D, a.C)) return launch_fused_wide(m, a, st);
     ZK_REQUIRE(pk && fused_narrow_shape(m, a.univariate, a.bins, a.D, a.C), "fused layer: unsupported shape");
     ZK_REQUIRE(a.B < ((int64_t)1 << 31) - FM, "fused layer: batch too large for one launch");

@@ -365,6 +365,7 @@ void tc_destroy(zk_mlp* m) {
     for (auto* q : pk->fused.dperm) cudaFree(q);
     cudaFree(pk->fused.sched);
     cudaFree(pk->wide.sched);
+    cudaFree(pk->dual.sched);
     delete pk;
     m->tc = nullptr;
 }

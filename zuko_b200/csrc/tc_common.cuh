@@ -161,6 +161,7 @@ struct TcPack {
     int max_np = 0;  // widest padded hidden activation
     FusedPack fused;
     WidePack wide;
+    WidePack dual;  // fused_dual.cu (hidden width 128 / 256, two sub-tiles in flight): same pack layout
 };
 
 inline int pad64(int v) { return (v + 63) / 64 * 64; }
