@@ -173,6 +173,40 @@ def test_wide_layers_run_as_one_kernel_each(device, name):
     assert torch.equal(lp[:300], lp_part)
 
 
+def test_the_three_fused_kernels_agree_on_cfg2(device):
+    """Hidden width 256 can run on all three fused kernels (one CTA per tile, CTA pair, CTA pair with two
+    sub-tiles in flight): same oracle parity, mutual agreement to rounding, one launch per layer each."""
+    torch.manual_seed(7)
+    ref_flow = zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 3).eval()
+    spec = O.flowspec_from_module(ref_flow)
+    g = torch.Generator().manual_seed(3)
+    x, c = torch.randn(5000, 16, generator=g), torch.randn(5000, 8, generator=g)
+    ref = spec.log_prob(x.numpy(), c.numpy())
+    outs = {}
+    import ctypes
+
+    for name, dual, min_h, kind in (("narrow", 0, 384, 1), ("pair", 0, 256, 2), ("dual", 1, 256, 3)):
+        pd, pw = E.lib().zk_set_dual_tiles(dual), E.lib().zk_set_wide_min_hidden(min_h)
+        try:
+            flow = zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 3)
+            flow.load_state_dict(ref_flow.state_dict())
+            flow = flow.to(device)
+            with torch.no_grad():
+                lp = flow(c.to(device)).log_prob(x.to(device))
+                n0 = E.lib().zk_launch_count()
+                lp = flow(c.to(device)).log_prob(x.to(device))
+                assert E.lib().zk_launch_count() - n0 == 2
+            info = (ctypes.c_double * 4)()
+            assert E.lib().zk_layer_fused_info(flow.transform.transforms[0]._zk_layer(), info) == kind
+        finally:
+            E.lib().zk_set_dual_tiles(pd)
+            E.lib().zk_set_wide_min_hidden(pw)
+        outs[name] = lp
+        assert rel_err(lp.cpu().numpy(), ref) < 1e-5, name
+    for name in ("pair", "dual"):
+        assert torch.allclose(outs[name], outs["narrow"], rtol=2e-6, atol=5e-5)
+
+
 def test_fused_layer_broadcast_context_and_launch_count(device):
     torch.manual_seed(3)
     flow = zuko.flows.NSF(16, 8, transforms=4, bins=8, hidden_features=[256] * 3).to(device)

@@ -244,3 +244,160 @@ def test_unsupported_shapes_are_reported():
     ones = lambda d: [np.ones((d[i + 1], d[i]), np.uint8) for i in range(len(d) - 1)]  # noqa: E731
     assert _schedule([16, 128, 128, 32], ones([16, 128, 128, 32]), E.ZK_UNI_AFFINE, 0, 16, 0)[0] == -1  # narrow kernel's shape
     assert _schedule([16, 512, 384, 32], ones([16, 512, 384, 32]), E.ZK_UNI_AFFINE, 0, 16, 0)[0] == -1  # unequal hidden widths
+
+
+# --------------------------------------------------------------------------- #
+# dual-tile kernel (csrc/fused_dual.cu): hidden width 128 / 256, two sub-tiles interleaved chunk by chunk
+# --------------------------------------------------------------------------- #
+
+DUAL_CASES = {
+    "cfg2_nsf": lambda: zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 3),
+    "nsf7_k16_h128": lambda: zuko.flows.NSF(7, 0, transforms=2, bins=16, hidden_features=[128, 128]),
+    "maf32_h256": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[256] * 2),
+    "nsf24_k8_h256": lambda: zuko.flows.NSF(24, 0, transforms=2, bins=8, hidden_features=[256, 256]),  # classes not aligned to chunks
+}
+
+
+def _dual_schedule(dims, masks, uni, bins, D, C):
+    L = len(masks)
+    keep = [np.ascontiguousarray(m) for m in masks]
+    ptrs = (ctypes.c_void_p * L)(*[m.ctypes.data for m in keep])
+    cdims = (ctypes.c_int * (L + 1))(*dims)
+    out = np.zeros(2 * 4096, np.uint32)
+    rd = np.zeros(8, np.uint32)
+    n = E.lib().zk_debug_dual_schedule(L, cdims, ptrs, uni, bins, D, C, out.ctypes.data, 4096, rd.ctypes.data, None)
+    return n, out[: 2 * max(n, 0)].reshape(-1, 2), rd
+
+
+@pytest.mark.parametrize("name", list(DUAL_CASES))
+def test_dual_schedule_is_two_interleaved_copies_of_the_tile_walk(name):
+    """Each sub-tile's entries, taken alone, are the same descending walk over the non-zero tiles (same
+    tiles, same order, same first / last / first-read / last-read flags); the two alternate chunk by chunk;
+    and the schedule survives a randomly interleaved replay of the three agents (MMA side, two epilogue groups)."""
+    torch.manual_seed(0)
+    flow = DUAL_CASES[name]()
+    for layer in flow.transform.transforms:
+        dims, masks = _conditioner(layer)
+        uni, bins = _layer_args(layer)
+        n, items, rd = _dual_schedule(dims, masks, uni, bins, layer.features, layer.context)
+        assert n > 0 and n % 2 == 0, n
+        flags = items[:, 0].astype(np.int64)
+        sub = (flags >> 2) & 1
+        strip = lambda f: f & ~np.int64(4) & ~np.int64(0xFF00)  # noqa: E731  (sub-tile bit, unread masks)
+        a, b = items[sub == 0], items[sub == 1]
+        assert len(a) == len(b) == n // 2
+        assert np.array_equal(strip(a[:, 0].astype(np.int64)), strip(b[:, 0].astype(np.int64))) and np.array_equal(a[:, 1], b[:, 1])
+        # chunks alternate: a run of sub-tile 0 entries (one chunk) is followed by the same chunk of sub-tile 1
+        runs = []
+        for f in flags:
+            if f & FIRST:
+                runs.append(int((f >> 2) & 1))
+        assert runs == [0, 1] * (len(runs) // 2)
+        # descending tile order per sub-tile and layer
+        layer_of = (a[:, 0].astype(np.int64) >> 16) & 7
+        for l in range(len(masks)):
+            sel = layer_of == l
+            order = [(int(y), int(f) & 3) for f, y in zip(a[sel, 0], a[sel, 1])]
+            assert order == sorted(order, reverse=True)
+        L, nch, KB0 = len(masks), dims[1] // 128, (dims[0] + 63) // 64
+        DPC = (4 if bins == 8 else 2) if uni == E.ZK_UNI_RQS else 64
+        n_last = (layer.features + DPC - 1) // DPC
+        for seed in range(20):
+            _replay_dual(items, rd, L, nch, KB0, n_last, seed)
+
+
+def _replay_dual(items, rd, L, nch, KB0, n_last, seed, tiles=3):
+    rng = random.Random(seed)
+    n = len(items)
+    keys = [("df", u) for u in range(2)] + [("de", u) for u in range(2)] + [("ar", k) for k in range(8)] + [("af", k) for k in range(8)]
+    done, seen = dict.fromkeys(keys, 0), dict.fromkeys(keys, 0)
+
+    def complete(key):
+        assert done[key] == seen[key], f"{key} would run two phases ahead of its waiter"
+        done[key] += 1
+
+    st = {"mi": 0, "cnt": [0, 0], "pending": []}
+
+    def mma_issue():
+        if st["mi"] >= tiles * n:
+            return False
+        f = int(items[st["mi"] % n][0])
+        u = (f >> 2) & 1
+        if f & FIRST and done[("de", u)] < st["cnt"][u]:
+            return False
+        unread = [k for k in range(8) if (f >> (8 + k)) & 1]
+        if any(done[("ar", k)] <= seen[("ar", k)] for k in unread):
+            return False
+        kb8 = 4 * u + (f & 3)
+        if f & AWAIT and done[("ar", kb8)] <= seen[("ar", kb8)]:
+            return False
+        if f & FIRST:
+            seen[("de", u)] = st["cnt"][u]
+            st["cnt"][u] += 1
+        for k in unread:
+            seen[("ar", k)] += 1
+        if f & AWAIT:
+            seen[("ar", kb8)] += 1
+        ev = ([("af", kb8)] if f & AFREE else []) + ([("df", u)] if f & LAST else [])
+        st["pending"].append(ev)
+        st["mi"] += 1
+        return True
+
+    def mma_complete():
+        if not st["pending"]:
+            return False
+        for key in st["pending"].pop(0):
+            complete(key)
+        return True
+
+    steps = [[], []]
+    for u in range(2):
+        chunk = 0
+        for _ in range(tiles):
+            steps[u].append(("stage",))
+            for l in range(L - 1):
+                for ch in range(nch - 1, -1, -1):
+                    steps[u] += [("wait_df", chunk), ("drain",)]
+                    steps[u] += [("wait_af", kb) for kb in (2 * ch, 2 * ch + 1) if (int(rd[l]) >> kb) & 1]
+                    steps[u].append(("write", ch))
+                    chunk += 1
+            for ch in range(n_last - 1, -1, -1):
+                steps[u] += [("wait_df", chunk), ("drain",)]
+                chunk += 1
+            steps[u] += [("wait_af", kb) for kb in range(4) if (int(rd[L - 1]) >> kb) & 1]
+    ei = [0, 0]
+
+    def epi(u):
+        def run():
+            if ei[u] >= len(steps[u]):
+                return False
+            s = steps[u][ei[u]]
+            if s[0] == "stage":
+                for kb in range(KB0):
+                    complete(("ar", 4 * u + kb))
+            elif s[0] == "wait_df":
+                if done[("df", u)] < s[1] + 1:
+                    return False
+                seen[("df", u)] = s[1] + 1
+            elif s[0] == "drain":
+                complete(("de", u))
+            elif s[0] == "wait_af":
+                k = ("af", 4 * u + s[1])
+                if done[k] <= seen[k]:
+                    return False
+                seen[k] += 1
+            elif s[0] == "write":
+                complete(("ar", 4 * u + 2 * s[1]))
+                complete(("ar", 4 * u + 2 * s[1] + 1))
+            ei[u] += 1
+            return True
+
+        return run
+
+    agents = [mma_issue, mma_complete, epi(0), epi(1)]
+    while True:
+        order = agents[:]
+        rng.shuffle(order)
+        if not any(a() for a in order):
+            break
+    assert st["mi"] == tiles * n and not st["pending"] and ei[0] == len(steps[0]) and ei[1] == len(steps[1]), "deadlock"

@@ -110,7 +110,7 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
     uint64_t* a_ready = bars + 20;  // [8]  index 4 sub-tile + kb, leader's: 2 x 8 epilogue warps
     uint64_t* a_free = bars + 28;   // [8]  index 4 sub-tile + kb, each CTA its own
     uint32_t* tmem_slot = (uint32_t*)(bars + 36);
-    uint32_t* s_ready = tmem_slot + 1;
+    uint32_t* s_ready = tmem_slot + 2;  // [0] entries whose operands are ready, [1] entries whose weights landed (two scouts -> issuer)
     float* s_part = (float*)(bars + D_BAR_SLOTS);  // [2 sub-tiles][2 parities][128]
     float* s_bias = (float*)((uint8_t*)bars + D_AUX_BYTES);
 
@@ -128,7 +128,8 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
         for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], 2 * D_GROUP_WARPS); }
         for (int k = 0; k < 8; ++k) { mbar_init(&a_ready[k], 2 * D_GROUP_WARPS); mbar_init(&a_free[k], 1); }
-        *s_ready = 0u;
+        s_ready[0] = 0u;
+        s_ready[1] = 0u;
         fence_mbar_init();
     }
     for (int l = 0; l < L; ++l)
@@ -165,6 +166,8 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                 const int n0 = (int)e.y + (int)(rows * rank);
                 tma_load_3d_2sm(st, &p.mapW[l], full0 + 8u * (uint32_t)ws, kb * DK, n0, 0);
                 if (planes == 2u) tma_load_3d_2sm(st + D_WPLANE, &p.mapW[l], full0 + 8u * (uint32_t)ws, kb * DK, n0, 1);
+                if constexpr (DBG)
+                    if (p.dbg != nullptr && blockIdx.x == 0 && (i / n_items == min(2, n_iter - 1)) && j < 64) p.dbg[448 + j] = clock64();
                 if (++j == n_items) j = 0;
                 if (++ws == NW) { ws = 0; wph ^= 1u; }
             }
@@ -174,7 +177,7 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
         if (rank == 0) {
             const uint32_t idesc_h = umma_idesc_bf16(2 * DM, 128), idesc_o = umma_idesc_bf16(2 * DM, N_LAST);
             int ws = 0, j = 0;
-            uint32_t seen = 0;
+            uint32_t seen = 0, seen_w = 0;  // cached s_ready[0] / s_ready[1]
             uint32_t cur = (total > 0) ? __ldg(&p.sched[0].x) : 0u;
             for (int i = 0; i < total; ++i) {
                 const bool stamp_on = DBG && (i / n_items == min(2, n_iter - 1)) && (lane == 0);
@@ -191,12 +194,15 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                 {
                     uint32_t _n = 0;
                     long long _t0 = 0;
-                    while (seen <= (uint32_t)i) {
-                        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_ready)) : "memory");
+                    while (seen <= (uint32_t)i || seen_w <= (uint32_t)i) {
+                        if (seen <= (uint32_t)i)
+                            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(s_ready)) : "memory");
+                        if (seen_w <= (uint32_t)i)
+                            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen_w) : "r"(smem_u32(s_ready + 1)) : "memory");
                         if ((++_n & 4095u) == 0u) {
                             const long long _t = clock64();
                             if (_t0 == 0) _t0 = _t;
-                            else if (_t - _t0 > W_WD_CYCLES) wd_report(p.watch, 0x20, i, seen);
+                            else if (_t - _t0 > W_WD_CYCLES) wd_report(p.watch, 0x20, i, (seen << 16) | (seen_w & 0xffffu));
                         }
                     }
                 }
@@ -217,17 +223,23 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                 }
                 __syncwarp();
                 if constexpr (DBG)
-                    if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on && j < 256) p.dbg[256 + j] = clock64();
+                    if (p.dbg != nullptr && blockIdx.x == 0 && stamp_on && j < 64) p.dbg[256 + j] = clock64();
                 cur = nxt;
                 j = jn;
                 if (++ws == NW) ws = 0;
             }
         }
     } else if (warp == 2) {
-        // ======================= scout (leader CTA) =======================
+        // ======================= operand scout (leader CTA) =======================
+        // A probe of an mbarrier costs ~300 cycles even when its phase completed long ago (profiles/
+        // r02_dual_timeline_v1.txt: one scout doing up to three probes per entry published one entry per
+        // ~1000 cycles, less than the tensor pipe consumes).  So two lanes in two warps walk the schedule
+        // independently, each with its own parity state: this one waits for what the EPILOGUE produces
+        // (accumulator drained, A blocks written), warp 3 for what the TMA produces (weights landed);
+        // the issuer reads both counters.
         if (rank == 0 && lane == 0) {
-            int ws = 0, j = 0;
-            uint32_t wph = 0, a_par = 0;     // a_par: bit (4 u + kb) = parity of a_ready
+            int j = 0;
+            uint32_t a_par = 0;              // bit (4 u + kb) = parity of a_ready
             uint32_t cnt[2] = {0u, 0u};      // chunks issued so far per sub-tile (its accumulator is single-buffered)
             for (int i = 0; i < total; ++i) {
                 const uint32_t it = __ldg(&p.sched[j].x);
@@ -248,9 +260,22 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                     WD_SPIN(mbar_try_wait_cluster(&a_ready[kb8], (a_par >> kb8) & 1u), 0x32, i, kb8);
                     a_par ^= 1u << kb8;
                 }
-                WD_SPIN(mbar_try_wait_cluster(&w_full[ws], wph), 0x33, i, ws);
                 asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_ready)), "r"((uint32_t)(i + 1)) : "memory");
+                if constexpr (DBG)
+                    if (p.dbg != nullptr && blockIdx.x == 0 && (i / n_items == min(2, n_iter - 1)) && j < 64) p.dbg[384 + j] = clock64();
                 if (++j == n_items) j = 0;
+            }
+        }
+    } else if (warp == 3) {
+        // ======================= weight scout (leader CTA) =======================
+        if (rank == 0 && lane == 0) {
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int i = 0; i < total; ++i) {
+                WD_SPIN(mbar_try_wait_cluster(&w_full[ws], wph), 0x33, i, ws);
+                asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_ready + 1)), "r"((uint32_t)(i + 1)) : "memory");
+                if constexpr (DBG)
+                    if (p.dbg != nullptr && blockIdx.x == 0 && (i / n_items == min(2, n_iter - 1)) && (i % n_items) < 64) p.dbg[320 + (i % n_items)] = clock64();
                 if (++ws == NW) { ws = 0; wph ^= 1u; }
             }
         }
@@ -344,6 +369,7 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(d_empty_r);  // this sub-tile's accumulator is drained
+                    if (l < 4) W_STAMP(sbase + 100 + 2 * l + ch);
                     for (int kb = 2 * ch; kb < 2 * ch + 2; ++kb)
                         if ((rd >> kb) & 1u) {
                             WD_SPIN(mbar_try_wait(&my_a_free[kb], (f_par >> kb) & 1u), 0x41, (uint32_t)(l * 16 + ch), kb);
