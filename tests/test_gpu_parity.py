@@ -316,7 +316,9 @@ def test_rsample_and_log_prob(device):
     torch.manual_seed(0)
     x, lp = dist.rsample_and_log_prob((512,))
     assert x.shape == (512, 3) and lp.shape == (512,)
-    assert torch.allclose(lp, dist.log_prob(x), rtol=1e-6, atol=1e-5)
+    # the inverse sweep accumulates the ladj itself (fp32 FMA conditioner of ar_inverse.cu); log_prob(x) runs the
+    # forward kernels: two arithmetics, each within 1e-5 of the oracle (test_gpu_inverse.py) -> 2e-5 of each other
+    assert rel_err(cpu(lp), cpu(dist.log_prob(x))) < 2e-5
 
 
 def test_chunked_workspace_matches_single_chunk(device):
