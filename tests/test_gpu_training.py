@@ -151,7 +151,11 @@ def test_standalone_conditioner_refuses_to_drop_gradients(device):
     net = zuko.nn.MLP(4, 3, [32]).to(device)
     x = torch.randn(8, 4, device=device)
     with pytest.raises(NotImplementedError, match="forward-only"):
-        net(x)
+        net(x.clone().requires_grad_(True))
+    zuko.nn._EngineMLP._warned_detached = False
+    with pytest.warns(RuntimeWarning, match="NOT connected"):
+        y = net(x)  # parameters still carry requires_grad: allowed for inference, said out loud once
+    assert not y.requires_grad
     with torch.no_grad():
         assert net(x).shape == (8, 3)
 

@@ -15,6 +15,7 @@ from __future__ import annotations
 __all__ = ["MLP", "Linear", "MaskedLinear", "MaskedMLP", "Residual"]
 
 import ctypes
+import warnings
 from collections.abc import Callable, Sequence
 
 import torch
@@ -140,6 +141,8 @@ class _EngineMLP(nn.Sequential):
                 res.append(0)
         return acts, res
 
+    _warned_detached = False
+
     def _activation_code(self) -> int:
         acts = [k for m in self for k in (m if isinstance(m, Residual) else [m]) if not hasattr(k, "weight")]
         codes = {activation_code(m) for m in acts}
@@ -223,13 +226,22 @@ class _EngineMLP(nn.Sequential):
 
     def forward(self, x: Tensor) -> Tensor:
         E.require_cuda(x, "conditioner input")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # the stand-alone conditioner call has no autograd seam (gradients flow through the flow-level
-            # calls, _ops._FlowFunction): refuse rather than return a tensor that silently drops them
-            raise NotImplementedError(
-                "zuko_b200: MLP / MaskedMLP called on its own is forward-only; wrap the call in torch.no_grad(), "
-                "or differentiate through flow(c).log_prob / transform.call_and_ladj / rsample"
-            )
+        if torch.is_grad_enabled():
+            # the stand-alone conditioner call has no autograd seam (gradients flow through the flow-level calls,
+            # _ops._FlowFunction).  An input that asks for gradients is refused; parameters that merely still
+            # carry requires_grad (the default of a freshly built module used for inference) get one warning.
+            if x.requires_grad:
+                raise NotImplementedError(
+                    "zuko_b200: MLP / MaskedMLP called on its own is forward-only; differentiate through "
+                    "flow(c).log_prob / transform.call_and_ladj / rsample, or detach the input"
+                )
+            if not _EngineMLP._warned_detached and any(p.requires_grad for p in self.parameters()):
+                _EngineMLP._warned_detached = True
+                warnings.warn(
+                    "zuko_b200: MLP / MaskedMLP called on its own returns a tensor that is NOT connected to its "
+                    "parameters in the autograd graph (forward-only); use torch.no_grad() to silence this",
+                    RuntimeWarning, stacklevel=2,
+                )  # fmt: skip
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         B = x2.shape[0]
