@@ -92,6 +92,34 @@ def test_nll_ring_gloo_world2():
     assert np.allclose(got[0], expect, rtol=1e-12)
 
 
+def _ring_reuse_worker(rank: int, world: int, port: int, out):
+    """Constant count, banks reused many times: the count column must not accumulate earlier reductions."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ring = NllRing("cpu", slots=2)
+        vals = []
+        for rnd in range(4):
+            for step in range(5):
+                ring.slot(8).fill_(-8.0 * (rank + 1) * (step + 1))
+            vals.append(ring.means().tolist())
+        out[rank] = vals
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nll_ring_bank_reuse_gloo_world2():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_ring_reuse_worker, args=(2, port, out), nprocs=2, join=True)
+        got = dict(out)
+    expect = [(8.0 * 1 * (s + 1) + 8.0 * 2 * (s + 1)) / 16.0 for s in range(5)]
+    assert got[0] == got[1]
+    for rnd in got[0]:
+        assert np.allclose(rnd, expect, rtol=1e-12)
+
+
 def test_nll_ring_without_process_group():
     ring = NllRing("cpu", slots=2)
     for step in range(5):

@@ -57,10 +57,11 @@ class NllRing:
     def __init__(self, device: torch.device | str, slots: int = 32, group: dist.ProcessGroup | None = None) -> None:
         self.device = torch.device(device)
         self.slots, self.group = int(slots), group
-        self.banks = torch.zeros(2, self.slots, 2, dtype=torch.float64, device=self.device)
+        self.sums = torch.zeros(2, self.slots, dtype=torch.float64, device=self.device)    # written by the engine
+        self.counts = torch.zeros(2, self.slots, dtype=torch.float64, device=self.device)  # rewritten only when a count changes
         self._counts = [[None] * self.slots, [None] * self.slots]
         self.bank, self.i = 0, 0
-        self._inflight: list = [None, None]  # per bank: (work | None, event | None, n)
+        self._inflight: list = [None, None]  # per bank: (work | None, packet {sum, count} that is being reduced)
         self._done: list[Tensor] = []
         self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
 
@@ -73,39 +74,43 @@ class NllRing:
             self.flush()
         b, i = self.bank, self.i
         if self._inflight[b] is not None and i == 0:
-            self._collect(b)  # the bank's previous reduction must have landed before it is rewritten
+            self._collect(b)  # the bank's previous reduction is retired before the bank is reused
         if self._counts[b][i] != count:  # constant across steps in practice: written once
-            self.banks[b, i, 1] = float(count)
+            self.counts[b, i] = float(count)
             self._counts[b][i] = count
         self.i += 1
-        return self.banks[b, i, 0:1]
+        return self.sums[b, i : i + 1]
 
     def flush(self) -> None:
-        """Reduces the steps recorded since the last flush (asynchronously) and switches banks."""
+        """Reduces the steps recorded since the last flush (asynchronously) and switches banks.  The
+        collective works on a COPY {sum, count} of the bank (one small kernel per flush, not per step):
+        the bank itself — in particular its count column — stays local and reusable."""
         n = self.i
         if n == 0:
             return
         b = self.bank
-        view = self.banks[b, :n]
-        work = event = None
-        if self._world() > 1:
-            if self.side is not None:
-                self.side.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(self.side):
-                    work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            else:
-                work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        elif self.side is not None:
-            event = torch.cuda.Event()
-            event.record(torch.cuda.current_stream(self.device))
-        self._inflight[b] = (work, event, n)
+        work = None
+        if self._world() > 1 and self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side):
+                packet = torch.stack((self.sums[b, :n], self.counts[b, :n]), dim=1)
+                work = dist.all_reduce(packet, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            packet = torch.stack((self.sums[b, :n], self.counts[b, :n]), dim=1)
+            if self._world() > 1:
+                work = dist.all_reduce(packet, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight[b] = (work, packet)
         self.bank, self.i = 1 - b, 0
 
     def _collect(self, b: int) -> None:
-        work, event, n = self._inflight[b]
+        work, packet = self._inflight[b]
         if work is not None:
             work.wait()  # orders the current stream after the collective
-        self._done.append(-(self.banks[b, :n, 0] / self.banks[b, :n, 1]).clone())
+        elif self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        if self.side is not None:
+            packet.record_stream(torch.cuda.current_stream(self.device))
+        self._done.append(-(packet[:, 0] / packet[:, 1]))
         self._inflight[b] = None
 
     def means(self) -> Tensor:
