@@ -179,3 +179,16 @@ def test_accelerate_after_move_to_device(device):
     c = torch.from_numpy(g["c"]).to(device)
     with torch.no_grad():
         assert_log_prob_parity(acc(c).log_prob(x).cpu().numpy(), g, rtol=1e-5)
+
+
+def test_accelerate_leaves_the_global_rng_alone():
+    """The mirror's constructors draw initial weights that are thrown away: the caller's RNG stream must
+    not move."""
+    torch.manual_seed(123)
+    flow = zuko_b200.flows.NSF(3, 2, transforms=2, hidden_features=[16])
+    torch.manual_seed(7)
+    a = torch.rand(3)
+    torch.manual_seed(7)
+    zuko_b200.accelerate(flow)
+    b = torch.rand(3)
+    assert torch.equal(a, b)

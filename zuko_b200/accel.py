@@ -240,5 +240,8 @@ def accelerate(flow: nn.Module) -> AcceleratedFlow:
     for name, t in list(flow.named_parameters()) + list(flow.named_buffers()):
         if t.is_floating_point() and t.dtype != torch.float32:
             raise TypeError(f"zuko_b200.accelerate: {name} is {t.dtype}; the engine computes in float32")
-    mirror = _convert(flow, passthrough=False)
+    # the mirror's constructors draw fresh initial weights (rebound to the reference's right after): keep
+    # the caller's global RNG stream untouched
+    with torch.random.fork_rng(devices=[]):
+        mirror = _convert(flow, passthrough=False)
     return AcceleratedFlow(mirror, flow)
