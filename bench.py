@@ -417,9 +417,10 @@ def time_config(cfg, dev, rank, world, peaks, steps, nvml=None) -> dict:
                            "frac_issued": 2.0 * info["issued_macs_per_row"] * rows / (ms_per_step * 1e-3) / 1e12 / peak,
                            "traffic": None, "algorithmic_hbm_bytes": 4.0 * (D + C + 1) * rows}  # fmt: skip
         tj = ncu_traffic().get(f"{cfg['name']}_layer")
-        if tj:  # one `ncu --set full` capture of one flow layer of this config: bytes per launch and the rows it covered
+        if tj:  # one `ncu --set full` capture of ONE flow layer launch of this config (bytes, and the rows that launch covered)
             out["roofline"]["traffic"] = tj.get("bytes")
             out["roofline"]["traffic_rows"] = tj.get("rows")
+            out["roofline"]["traffic_note"] = "per layer launch over traffic_rows rows; algorithmic: 4 (2 D + C + 1) bytes per row"
             out["roofline"]["traffic_captured_at"] = ncu_traffic().get("git_sha")
     else:
         # every weight of the masked conditioner is visited once per sample (ar_inverse.cu): 2 FLOP per
@@ -432,6 +433,11 @@ def time_config(cfg, dev, rank, world, peaks, steps, nvml=None) -> dict:
         out["roofline"] = {"bound": "fma", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_kind": "nominal fp32 FMA (148 SMs x 128 lanes x 2 x max SM clock)",
                            "kernel": ["ar_inverse_kernel<RQS,16>"], "algorithmic_flops_per_step": flops, "traffic": None,
                            "algorithmic_hbm_bytes": 4.0 * 2 * D * rows}  # fmt: skip
+        tj = ncu_traffic().get(f"{cfg['name']}_layer")
+        if tj:
+            out["roofline"]["traffic"] = tj.get("bytes")
+            out["roofline"]["traffic_rows"] = tj.get("rows")
+            out["roofline"]["traffic_captured_at"] = ncu_traffic().get("git_sha")
     del xs, cs, flow
     torch.cuda.empty_cache()
     return out
