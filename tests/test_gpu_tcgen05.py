@@ -106,8 +106,14 @@ FUSED_FLOWS = {
     "nsf24_k8_h512": lambda: zuko.flows.NSF(24, 0, transforms=2, bins=8, hidden_features=[512, 512]),  # degree classes not aligned to chunks
     "nsf10c3_h384": lambda: zuko.flows.NSF(10, 3, transforms=3, bins=8, hidden_features=[384, 384]),   # 3 chunks / 6 K blocks
     "maf100c28_h512": lambda: zuko.flows.MAF(100, 28, transforms=2, hidden_features=[512] * 2),        # K0 = 128, 2 affine chunks
+    # ---- non-ReLU activations on the fused pair kernels (nn.py:264-265; general-activation instantiation) ----
+    "maf32_h512_elu": lambda: zuko.flows.MAF(32, 0, transforms=2, hidden_features=[512] * 2, activation=torch.nn.ELU),
+    "nsf16c8_h256_silu": lambda: zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 2, activation=torch.nn.SiLU),
+    "nsf12_h256_tanh": lambda: zuko.flows.NSF(12, 0, transforms=2, bins=8, hidden_features=[256, 256], activation=torch.nn.Tanh),
+    "maf24c4_h384_gelu": lambda: zuko.flows.MAF(24, 4, transforms=2, hidden_features=[384] * 2, activation=torch.nn.GELU),
 }
-WIDE_FLOWS = ["maf32_h512x4", "nsf64c16_k16_h512", "nsf24_k8_h512", "nsf10c3_h384", "maf100c28_h512"]
+WIDE_FLOWS = ["maf32_h512x4", "nsf64c16_k16_h512", "nsf24_k8_h512", "nsf10c3_h384", "maf100c28_h512",
+              "maf32_h512_elu", "nsf16c8_h256_silu", "nsf12_h256_tanh", "maf24c4_h384_gelu"]
 
 
 @pytest.fixture

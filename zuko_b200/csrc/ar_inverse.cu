@@ -39,13 +39,14 @@
 #include <algorithm>
 #include <vector>
 
+#include "activations.cuh"
 #include "ar_inverse.cuh"
 #include "bijector_math.cuh"
 
 namespace zk {
 
 struct ArInvPack {
-    int D = 0, C = 0, P = 0, uni = 0, bins = 0, passes = 0;
+    int D = 0, C = 0, P = 0, uni = 0, bins = 0, passes = 0, act = 1;
     int n_linear = 0;
     std::vector<int> dims;         // n_linear + 1
     std::vector<int> sec_off;      // state section offsets (floats): IN, H1 .. H_{L-1}, end
@@ -73,6 +74,7 @@ struct InvParams {
     float* x; int64_t ldx;
     int64_t B;
     float bound, aw, ad;
+    int act;           // activation between the linear layers: 1 = ReLU, else ZK_ACT_*
     int circ;          // circular RQS (NCSF): CircularShiftTransform(bound) applied to the solved dimension
     float* ladj;       // nullable: per-sample sum of the FORWARD log-derivatives at the solution
     int accumulate;    // ladj += (else =)
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
 #pragma unroll
                         for (int j = 0; j < R; ++j) {
                             const float v = (i & 1) ? acc[j][i >> 1].y : acc[j][i >> 1].x;
-                            So[u * S + j * T] = fmaxf(v, 0.f);
+                            So[u * S + j * T] = (p.act == 1) ? fmaxf(v, 0.f) : act_apply(v, p.act);
                         }
                     }
                 }
@@ -320,7 +322,7 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
     *out = nullptr;
     const int L = m->n_linear;
     if (!order || L < 1 || L > 7) return ZK_OK;
-    if (m->act != 1 || !m->plain) return ZK_OK;  // ReLU MLPs only: other activations / residual blocks use the sweeps
+    if (!m->plain) return ZK_OK;  // residual blocks use the sweeps
     if (uni == ZK_UNI_RQS && bins != 8 && bins != 16) return ZK_OK;
     if (m->dims[0] != D + C) return ZK_OK;
     const int P = (uni == ZK_UNI_RQS) ? 3 * bins - 1 : 2;
@@ -362,6 +364,7 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
 
     ArInvPack* pk = new ArInvPack();
     pk->D = D; pk->C = C; pk->P = P; pk->uni = uni; pk->bins = bins; pk->passes = passes; pk->n_linear = L;
+    pk->act = m->act;
     pk->dims = m->dims;
     int off = 0;
     pk->sec_off.push_back(off);
@@ -495,6 +498,7 @@ zk_status launch_ar_inverse(const ArInvPack* pk, const ArInvArgs& a, cudaStream_
     p.y = a.y; p.ldy = a.ldy; p.c = a.c; p.ldc = a.ldc; p.x = a.x; p.ldx = a.ldx; p.B = a.B;
     p.bound = a.bound;
     p.circ = a.circular ? 1 : 0;
+    p.act = pk->act;
     const float absL = fabsf(logf(a.slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;

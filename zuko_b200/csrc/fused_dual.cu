@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <atomic>
 
+#include "activations.cuh"
 #include "fused_common.cuh"
 #include "pair_common.cuh"
 
@@ -78,6 +79,7 @@ struct DualParams {
     int in_vec;
     int n_wstages;
     int base_off;
+    int act;            // activation between the linear layers: 1 = ReLU, else ZK_ACT_* (GACT instantiation)
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
     float* y; int64_t ldy;
@@ -88,7 +90,7 @@ struct DualParams {
     uint32_t* watch;
 };
 
-template <int UNI, int KT, bool FAST, bool DBG>
+template <int UNI, int KT, bool FAST, bool DBG, bool GACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D_THREADS, 1)
 fused_dual_kernel(const __grid_constant__ DualParams p) {
     using Cfg = LastCfg<UNI, KT>;
@@ -357,6 +359,18 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                         uint32_t ra[16];
                         tmem_ld_x16(t_lane + d_col0 + (uint32_t)(s * 64 + 16 * g), ra);
                         tmem_ld_wait();
+                        if constexpr (GACT) {  // any ZK_ACT_* (nn.py:264-265): one switch per 16 columns
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bb = b4[j >> 2];
+                                v[j] = __uint_as_float(ra[j]) + bb.x; v[j + 1] = __uint_as_float(ra[j + 1]) + bb.y;
+                                v[j + 2] = __uint_as_float(ra[j + 2]) + bb.z; v[j + 3] = __uint_as_float(ra[j + 3]) + bb.w;
+                            }
+                            if constexpr (FAST) act_apply_n_fast<16>(v, p.act); else act_apply_n<16>(v, p.act);
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], ph[8 * g + (j >> 1)], pl[8 * g + (j >> 1)]);
+                        } else {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 bb = b4[j >> 2];
@@ -364,6 +378,7 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                                         ph[8 * g + (j >> 1)], pl[8 * g + (j >> 1)]);
                             split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
                                         ph[8 * g + (j >> 1) + 1], pl[8 * g + (j >> 1) + 1]);
+                        }
                         }
                     }
                     tc_fence_before();
@@ -535,9 +550,10 @@ zk_status launch_dual_t(const DualParams& p, bool fast, int grid, size_t smem, c
         kern<<<grid, D_THREADS, smem, st>>>(p);
         return check_launch("fused_dual_kernel");
     };
-    if (p.dbg != nullptr) return fast ? go(fused_dual_kernel<UNI, KT, true, true>) : go(fused_dual_kernel<UNI, KT, false, true>);
-    if (fast) return go(fused_dual_kernel<UNI, KT, true, false>);
-    return go(fused_dual_kernel<UNI, KT, false, false>);
+    if (p.act != 1) return fast ? go(fused_dual_kernel<UNI, KT, true, false, true>) : go(fused_dual_kernel<UNI, KT, false, false, true>);
+    if (p.dbg != nullptr) return fast ? go(fused_dual_kernel<UNI, KT, true, true, false>) : go(fused_dual_kernel<UNI, KT, false, true, false>);
+    if (fast) return go(fused_dual_kernel<UNI, KT, true, false, false>);
+    return go(fused_dual_kernel<UNI, KT, false, false, false>);
 }
 
 struct DualShape {
@@ -655,7 +671,7 @@ static bool dual_dims_ok(const int* dims, int L, int univariate, int bins, int D
 bool fused_dual_shape(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
     if (!pk || m->gemm_mode == ZK_GEMM_FP32) return false;
-    if (m->act != 1 || !m->plain) return false;
+    if (!m->plain) return false;  // residual blocks: see fused_wide.cu
     return dual_dims_ok(m->dims.data(), m->n_linear, univariate, bins, D, C);
 }
 
@@ -824,6 +840,7 @@ zk_status launch_fused_dual(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
     p.dbg = g_timeline;
+    p.act = m->act;
     p.sched = wp.sched;
     p.n_items = wp.n_items;
     const bool x_ok = (a.ldx % 4 == 0) && (a.D % 4 == 0) && (((uintptr_t)a.x) % 16 == 0);

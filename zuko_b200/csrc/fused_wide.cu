@@ -49,6 +49,7 @@
 #include <algorithm>
 #include <atomic>
 
+#include "activations.cuh"
 #include "fused_common.cuh"
 #include "pair_common.cuh"
 
@@ -101,6 +102,7 @@ struct WideParams {
     int in_vec;         // x / c rows can be read with 16-byte loads
     int n_wstages;
     int alo_blocks;     // K blocks of the A lo plane kept in shared memory: max(KB0, H / 64)
+    int act;            // activation between the linear layers: 1 = ReLU, else ZK_ACT_* (GACT instantiation)
     int base_off;       // offset (floats, after the bias copy) of the base table [3][D]: loc, 1/scale, log scale + log sqrt(2 pi)
     const float* x; int64_t ldx;
     const float* c; int64_t ldc;
@@ -112,7 +114,7 @@ struct WideParams {
     uint32_t* watch;  // watchdog report buffer (mapped host memory) or null
 };
 
-template <int UNI, int KT, bool FAST, bool DBG>
+template <int UNI, int KT, bool FAST, bool DBG, bool GACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W_THREADS, 1)
 fused_wide_kernel(const __grid_constant__ WideParams p) {
     using Cfg = LastCfg<UNI, KT>;
@@ -355,6 +357,18 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
                             uint32_t ra[16];
                             tmem_ld_x16(t_lane + TMW_D + buf * 128u + (uint32_t)(s * 32 + 16 * half), ra);
                             tmem_ld_wait();
+                            if constexpr (GACT) {  // any ZK_ACT_* (nn.py:264-265): one switch per 16 columns
+                                float v[16];
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 bb = b4[4 * half + (j >> 2)];
+                                    v[j] = __uint_as_float(ra[j]) + bb.x; v[j + 1] = __uint_as_float(ra[j + 1]) + bb.y;
+                                    v[j + 2] = __uint_as_float(ra[j + 2]) + bb.z; v[j + 3] = __uint_as_float(ra[j + 3]) + bb.w;
+                                }
+                                if constexpr (FAST) act_apply_n_fast<16>(v, p.act); else act_apply_n<16>(v, p.act);
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], ph[8 * half + (j >> 1)], pl[8 * half + (j >> 1)]);
+                            } else {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 bb = b4[4 * half + (j >> 2)];
@@ -362,6 +376,7 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
                                             ph[8 * half + (j >> 1)], pl[8 * half + (j >> 1)]);
                                 split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
                                             ph[8 * half + (j >> 1) + 1], pl[8 * half + (j >> 1) + 1]);
+                            }
                             }
                         }
                     }
@@ -535,9 +550,10 @@ zk_status launch_wide_t(const WideParams& p, bool fast, int grid, size_t smem, c
         kern<<<grid, W_THREADS, smem, st>>>(p);
         return check_launch("fused_wide_kernel");
     };
-    if (p.dbg != nullptr) return fast ? go(fused_wide_kernel<UNI, KT, true, true>) : go(fused_wide_kernel<UNI, KT, false, true>);
-    if (fast) return go(fused_wide_kernel<UNI, KT, true, false>);
-    return go(fused_wide_kernel<UNI, KT, false, false>);
+    if (p.act != 1) return fast ? go(fused_wide_kernel<UNI, KT, true, false, true>) : go(fused_wide_kernel<UNI, KT, false, false, true>);
+    if (p.dbg != nullptr) return fast ? go(fused_wide_kernel<UNI, KT, true, true, false>) : go(fused_wide_kernel<UNI, KT, false, true, false>);
+    if (fast) return go(fused_wide_kernel<UNI, KT, true, false, false>);
+    return go(fused_wide_kernel<UNI, KT, false, false, false>);
 }
 
 // ---------------------------------------------------------------------------
@@ -678,7 +694,7 @@ static bool wide_dims_ok(const int* dims, int L, int univariate, int bins, int D
 bool fused_wide_shape(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
     if (!pk || m->gemm_mode == ZK_GEMM_FP32) return false;
-    if (m->act != 1 || !m->plain) return false;  // the hidden epilogue implements ReLU MLPs only
+    if (!m->plain) return false;  // residual blocks need the input of two layers back, which the in-place update overwrote
     return wide_dims_ok(m->dims.data(), m->n_linear, univariate, bins, D, C);
 }
 
@@ -851,6 +867,7 @@ zk_status launch_fused_wide(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     // shared memory: A lo + aux are fixed; the weight ring gets what is left after the bias copy of
     // the OUTPUT layer (47 reads per dim and thread) and as many hidden-layer biases as still fit
     p.alo_blocks = std::max(p.KB0, p.H / WK);
+    p.act = m->act;
     const uint32_t alo_bytes = (uint32_t)p.alo_blocks * W_APLANE;
     const uint32_t avail = W_SMEM_MAX - 1024u - alo_bytes - W_AUX_BYTES;
     p.n_wstages = (int)std::min<uint32_t>(W_MAX_WSTAGES, avail / W_WSTAGE);
