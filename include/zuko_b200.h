@@ -217,6 +217,9 @@ size_t zk_layer_workspace_bytes(const zk_layer* layer, int64_t B);
  * out[1] = schedule entries per tile, out[2] = MACs ISSUED per sample row (non-zero tiles only, all
  * split-bf16 terms), out[3] = dense MACs per sample row (what nn.py:218 executes). */
 int zk_layer_fused_info(const zk_layer* layer, double* out);
+/* 1 when the layer's inverse runs as the dimension-sequential kernel (one launch, emits the ladj): the
+ * precondition for using it as an inverted member of a zk_flow_desc. */
+int zk_layer_sequential_inverse(const zk_layer* layer);
 /* t(c).call_and_ladj(x): y (B, D), ladj (B) summed over the event dim; y must not alias x. */
 zk_status zk_layer_forward(const zk_layer* layer, const float* x, int64_t ldx, const float* c,
                            int64_t ldc, int64_t B, float* y, int64_t ldy, float* ladj,
@@ -239,6 +242,11 @@ typedef struct {
     const float* base_loc;   /* DEVICE (D) or NULL (0)   — BoxUniform: lower bounds (required) */
     const float* base_scale; /* DEVICE (D) or NULL (1)   — BoxUniform: upper bounds (required) */
     int base_kind;           /* ZK_BASE_* */
+    const int* inverted;     /* host (n_layers) or NULL: != 0 = this member is the INVERSE of its layer — LazyInverse
+                                (zuko/lazy.py:81-98: IAF-style flows, cheap sampling / sequential density).  Supported for
+                                autoregressive layers with a dimension-sequential inverse (zk_layer_sequential_inverse);
+                                zk_flow_forward / zk_flow_log_prob / zk_flow_inverse (without log_prob) honour it, the
+                                backward entry points refuse such flows (ZK_EUNSUPPORTED). */
 } zk_flow_desc;
 
 /* bytes of workspace that let a batch of B rows run in a single chunk; any

@@ -93,6 +93,7 @@ class FlowDesc(ctypes.Structure):
         ("base_loc", c_void_p),
         ("base_scale", c_void_p),
         ("base_kind", c_int),
+        ("inverted", POINTER(c_int)),
     ]
 
 
@@ -132,6 +133,7 @@ _SIGNATURES = {
     "zk_layer_destroy": (c_int, [_P]),
     "zk_layer_workspace_bytes": (c_size_t, [_P, c_int64]),
     "zk_layer_fused_info": (c_int, [_P, c_void_p]),
+    "zk_layer_sequential_inverse": (c_int, [_P]),
     "zk_layer_update_weights": (c_int, [_P, c_void_p, c_void_p, _P]),
     "zk_set_pack_stream": (None, [_P]),
     "zk_layer_forward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_int, _P, c_size_t, _P]),

@@ -161,8 +161,11 @@ class FlowCall:
     """A ``zk_flow_desc`` over packed layers + DiagNormal / BoxUniform base, ready to be invoked."""
 
     def __init__(self, handles: Sequence, D: int, C: int, loc: Tensor | None, scale: Tensor | None,
-                 sources: Sequence[dict] | None = None, keep: Sequence | None = None, base_kind: int = 0) -> None:  # fmt: skip
+                 sources: Sequence[dict] | None = None, keep: Sequence | None = None, base_kind: int = 0,
+                 inverted: Sequence[bool] | None = None) -> None:  # fmt: skip
         self.D, self.C = D, C
+        # members that are the INVERSE of their layer (LazyInverse, zuko/lazy.py:81-98); forward-only in the engine
+        self._inverted = [bool(v) for v in inverted] if inverted is not None and any(inverted) else None
         self.base_kind = base_kind  # E.ZK_BASE_*: DiagNormal(loc, scale) or BoxUniform(lower=loc, upper=scale)
         self._handles = list(handles)
         # per layer: the tensors its parameter gradients belong to ({"weights", "biases"} of the
@@ -191,7 +194,8 @@ class FlowCall:
         if self._loc is not None:
             E.require_cuda(self._loc, "base loc")
             E.require_cuda(self._scale, "base scale")
-        self.desc = E.FlowDesc(len(handles), self._arr, D, C, _ptr(self._loc), _ptr(self._scale), base_kind)
+        self._inv_arr = None if self._inverted is None else (ctypes.c_int * len(handles))(*[int(v) for v in self._inverted])
+        self.desc = E.FlowDesc(len(handles), self._arr, D, C, _ptr(self._loc), _ptr(self._scale), base_kind, self._inv_arr)
 
     def _ws(self, device, B: int):
         L = E.lib()
@@ -212,8 +216,22 @@ class FlowCall:
     def _wants_grad(self, x2: Tensor, c2: Tensor | None) -> bool:
         if not torch.is_grad_enabled():
             return False
+        if self._inverted is not None:  # forward-only members: callers route differentiable calls to the unfused chain
+            return False
         return (x2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
                 or bool(self._base_src))  # fmt: skip
+
+    def usable(self, x: Tensor, c: Tensor | None, inverse_log_prob: bool = False) -> bool:
+        """False when this call must go to the unfused chain instead: a flow with inverted members
+        (LazyInverse) is forward-only in the engine — no autograd seam, no fused log-density of samples."""
+        if self._inverted is None:
+            return True
+        if inverse_log_prob:
+            return False
+        if not torch.is_grad_enabled():
+            return True
+        return not (x.requires_grad or (c is not None and c.requires_grad) or any(p.requires_grad for p in self._params)
+                    or bool(self._base_src))  # fmt: skip
 
     def _generations(self) -> tuple:
         return tuple(getattr(r, "generation", 0) for r in self._keep)

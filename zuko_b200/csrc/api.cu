@@ -451,6 +451,10 @@ zk_status zk_layer_update_weights(zk_layer* l, const float* const* weight, const
     return ZK_OK;
 }
 
+int zk_layer_sequential_inverse(const zk_layer* l) {
+    return (l && l->kind == ZK_LAYER_AUTOREGRESSIVE && (l->inv != nullptr || l->inv_dirty)) ? 1 : 0;
+}
+
 int zk_layer_fused_info(const zk_layer* l, double* out) {
     if (!l || !out) return -1;
     out[0] = out[1] = out[2] = out[3] = 0.0;
@@ -601,7 +605,7 @@ zk_status layer_forward_impl(const zk_layer* l, const float* x, int64_t ldx, con
 zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, const float* c,
                              int64_t ldc, int64_t B, float* x, int64_t ldx, void* ws,
                              size_t ws_bytes, cudaStream_t st, float* ladj, int accumulate, bool base_lp,
-                             const float* base_loc, const float* base_scale, bool* ladj_done) {
+                             const float* base_loc, const float* base_scale, bool* ladj_done, bool as_member = false) {
     if (ladj_done) *ladj_done = false;
     if (B == 0) return ZK_OK;
     ZK_REQUIRE(l->C == 0 || c != nullptr, "layer needs a context of %d features", l->C);
@@ -637,6 +641,7 @@ zk_status layer_inverse_impl(const zk_layer* l, const float* y, int64_t ldy, con
                 ia.bound = l->bound; ia.slope = l->slope; ia.fast = g_fast_math.load() != 0; ia.circular = l->circ;
                 if (ladj) {
                     ia.ladj = ladj; ia.accumulate = accumulate; ia.base = base_lp; ia.base_loc = base_loc; ia.base_scale = base_scale;
+                    ia.as_inverse_member = as_member;
                     if (ladj_done) *ladj_done = true;
                 }
                 return launch_ar_inverse(l->inv, ia, st);
@@ -756,6 +761,8 @@ zk_status flow_check(const zk_flow_desc* f) {
         ZK_REQUIRE(l, "flow: layer %d is null", i);
         ZK_REQUIRE(l->D == f->features, "flow: layer %d has %d features, flow has %d", i, l->D, f->features);
         ZK_REQUIRE(l->C == 0 || l->C == f->context, "flow: layer %d expects context %d, flow has %d", i, l->C, f->context);
+        if (f->inverted && f->inverted[i])
+            ZK_REQUIRE(zk_layer_sequential_inverse(l), "flow: member %d is inverted but its layer has no dimension-sequential inverse", i);
     }
     return ZK_OK;
 }
@@ -778,6 +785,30 @@ zk_status flow_forward_chunk(const zk_flow_desc* f, const float* x, int64_t ldx,
         const zk_layer* l = f->layers[i];
         const bool last = (i == T - 1);
         const float* cc = l->C ? c : nullptr;
+        if (f->inverted && f->inverted[i]) {
+            // LazyInverse member (lazy.py:81-98): forward of the member = the layer's dimension-sequential
+            // inverse; its ladj = - ladj_layer at the solution, accumulated by the same kernel, which also adds
+            // the DiagNormal density of its OUTPUT when it closes a log_prob call
+            const bool fuse_base = last && log_prob && f->base_kind == ZK_BASE_DIAG_NORMAL;
+            float* dst = (last && z) ? z : buf[i & 1];
+            const int64_t ldd = (last && z) ? ldz : D;
+            float* acc = ladj;
+            if (fuse_base) {  // the closing kernel writes log_prob itself: hand it what the earlier members summed
+                if (i > 0) ZK_CUDA(cudaMemcpyAsync(log_prob, ladj, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+                acc = log_prob;
+            }
+            bool done = false;
+            ZK_TRY(layer_inverse_impl(l, cur, ldcur, cc, ldc, B, dst, ldd, lws, lws_bytes, st, acc, i > 0 ? 1 : 0,
+                                      fuse_base, f->base_loc, f->base_scale, &done, true));
+            ZK_REQUIRE(done, "flow: member %d is inverted but its layer has no dimension-sequential inverse", i);
+            cur = dst;
+            ldcur = ldd;
+            if (fuse_base) {
+                fused = true;
+                break;
+            }
+            continue;
+        }
         if (last && log_prob && layer_can_fuse_base(l) && f->base_kind == ZK_BASE_DIAG_NORMAL) {
             ZK_TRY(layer_forward_impl(l, cur, ldcur, cc, ldc, B, nullptr, 0, ladj, i > 0, log_prob,
                                       f->base_loc, f->base_scale, lws, lws_bytes, st));
@@ -827,6 +858,15 @@ zk_status flow_inverse_chunk(const zk_flow_desc* f, const float* z, int64_t ldz,
         const bool last = (i == 0);
         float* dst = last ? x : buf[i & 1];
         const int64_t ldd = last ? ldx : D;
+        if (f->inverted && f->inverted[i]) {
+            // inverse of a LazyInverse member = the layer's forward (its y; the ladj is not needed without log_prob)
+            ZK_REQUIRE(!want, "flow_inverse: log_prob of a flow with inverted members is not fused (use log_prob(x) of the result)");
+            ZK_TRY(layer_forward_impl(l, cur, ldcur, l->C ? c : nullptr, ldc, B, dst, ldd, nullptr, 0, nullptr, nullptr, nullptr,
+                                      lws, lws_bytes, st));
+            cur = dst;
+            ldcur = ldd;
+            continue;
+        }
         bool done = false;
         // the DiagNormal term of z can ride in the first inverted layer's kernel; a BoxUniform base is seeded apart
         const bool can_seed = want && !seeded && i == T - 1 && f->base_kind != ZK_BASE_BOX_UNIFORM;
@@ -1018,6 +1058,12 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* f, const float* xh, int64_t 
     const size_t stage_row = (size_t)(D + (bc ? 0 : C) + 1) * 4;
     // pick the chunk: at most B/4 rows (so the pipeline overlaps), at least 4096, bounded by memory
     int64_t Bc = std::max<int64_t>(4096, ceil_div(B, 8));
+    {   // whole waves of the persistent fused kernels: one wave = (SMs / 2) CTA pairs x 512 rows (dual-tile kernel;
+        // 256 for the other two, which divide it): a chunk of 3.46 waves runs as 4 (profiles/r02_bench_v2_dual.json:
+        // e2e 4.7 ms against 3.6 ms of compute and 2.2 ms of PCIe time for the same step)
+        const int64_t wave = (int64_t)(sm_count() / 2) * 512;
+        if (Bc > wave) Bc = std::max<int64_t>(1, (Bc + wave / 2) / wave) * wave;
+    }
     Bc = std::min(Bc, B);
     auto need = [&](int64_t n) {
         return 2 * (a256((size_t)n * D * 4) + a256((size_t)n * C * 4) + a256((size_t)n * 4)) + a256((size_t)C * 4) +

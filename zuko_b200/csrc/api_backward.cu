@@ -698,6 +698,9 @@ zk_status zk_flow_backward(const zk_flow_desc* f, const float* x, int64_t ldx, c
                            const zk_layer_grads* const* grads, void* ws, size_t ws_bytes,
                            zk_stream stream) {
     ZK_TRY(flow_check(f));
+    if (f->inverted)
+        for (int i = 0; i < f->n_layers; ++i)
+            if (f->inverted[i]) return fail(ZK_EUNSUPPORTED, "backward through inverted flow members (LazyInverse) is not implemented");
     ZK_REQUIRE(x, "flow_backward: null x");
     ZK_REQUIRE(B >= 0 && ldx >= f->features, "flow_backward: bad shape");
     ZK_REQUIRE(!grad_z || ldgz >= f->features, "flow_backward: bad ldgz");
@@ -736,6 +739,9 @@ zk_status zk_flow_inverse_backward(const zk_flow_desc* f, const float* x, int64_
                                    int64_t ldgc, const zk_layer_grads* const* grads, void* ws, size_t ws_bytes,
                                    zk_stream stream) {
     ZK_TRY(flow_check(f));
+    if (f->inverted)
+        for (int i = 0; i < f->n_layers; ++i)
+            if (f->inverted[i]) return fail(ZK_EUNSUPPORTED, "backward through inverted flow members (LazyInverse) is not implemented");
     ZK_REQUIRE(x, "flow_inverse_backward: null x");
     ZK_REQUIRE(B >= 0 && ldx >= f->features, "flow_inverse_backward: bad shape");
     ZK_REQUIRE(!grad_x || ldgx >= f->features, "flow_inverse_backward: bad ldgx");

@@ -78,7 +78,8 @@ struct InvParams {
     int circ;          // circular RQS (NCSF): CircularShiftTransform(bound) applied to the solved dimension
     float* ladj;       // nullable: per-sample sum of the FORWARD log-derivatives at the solution
     int accumulate;    // ladj += (else =)
-    int base;          // 1: also add DiagNormal(loc, scale).log_prob of the input y (distributions.py:129-138)
+    int base;          // 1: also add DiagNormal(loc, scale).log_prob of the input y (distributions.py:129-138); 2: of the output x
+    float sign;        // +1: accumulate the forward ladj at the solution; -1: the layer is an inverted flow member
     const float* base_loc; const float* base_scale;
 };
 
@@ -252,8 +253,9 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
                         xv = zdiv<FAST>(yv[j] - phi[j][0], zexp<FAST>(ls));
                         lj = ls;
                     }
+                    lj *= p.sign;
                     if (p.base) {
-                        const float u = (yv[j] - mu) * isg;
+                        const float u = ((p.base == 2 ? xv : yv[j]) - mu) * isg;
                         lj += -0.5f * u * u - lsg;
                     }
                     lsum[j] += lj;
@@ -502,7 +504,8 @@ zk_status launch_ar_inverse(const ArInvPack* pk, const ArInvArgs& a, cudaStream_
     const float absL = fabsf(logf(a.slope));
     p.aw = 2.f / absL;
     p.ad = 1.f / absL;
-    p.ladj = a.ladj; p.accumulate = a.accumulate; p.base = a.base ? 1 : 0;
+    p.ladj = a.ladj; p.accumulate = a.accumulate; p.base = a.base ? (a.as_inverse_member ? 2 : 1) : 0;
+    p.sign = a.as_inverse_member ? -1.f : 1.f;
     p.base_loc = a.base_loc; p.base_scale = a.base_scale;
     const int64_t grid = ceil_div(a.B, (int64_t)T * R);
     ZK_REQUIRE(grid <= 0x7fffffff, "ar_inverse: batch too large for one launch");

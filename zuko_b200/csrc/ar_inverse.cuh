@@ -27,6 +27,9 @@ struct ArInvArgs {
     // `accumulate`; with `base` the DiagNormal(loc, scale) log-density of y is added as well
     float* ladj = nullptr; int accumulate = 0;
     bool base = false; const float* base_loc = nullptr; const float* base_scale = nullptr;
+    // the layer as an INVERTED member of a flow (LazyInverse): the member's own ladj is minus the forward
+    // ladj at the solution, and the base density (if fused here) is evaluated on the OUTPUT x
+    bool as_inverse_member = false;
 };
 zk_status launch_ar_inverse(const ArInvPack* pk, const ArInvArgs& a, cudaStream_t stream);
 

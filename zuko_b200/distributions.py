@@ -217,13 +217,14 @@ class NormalizingFlow(Distribution):
             if fused is not None:
                 call, ctx = fused
                 fc = (_ops.FlowCall(call._handles, call.D, call.C, first, second, sources=call._sources, keep=call._keep,
-                                    base_kind=E.ZK_BASE_BOX_UNIFORM if box else E.ZK_BASE_DIAG_NORMAL), ctx)  # fmt: skip
+                                    base_kind=E.ZK_BASE_BOX_UNIFORM if box else E.ZK_BASE_DIAG_NORMAL,
+                                    inverted=call._inverted), ctx)  # fmt: skip
         self.__dict__["_fc"] = fc
         return fc
 
     def log_prob(self, x: Tensor) -> Tensor:
         fc = self._flow_call()
-        if fc is not None:
+        if fc is not None and fc[0].usable(x, fc[1]):
             call, ctx = fc
             lp = call.log_prob(x, ctx)
             return lp.expand(torch.broadcast_shapes(lp.shape, self.batch_shape)) if self.batch_shape else lp
@@ -237,7 +238,7 @@ class NormalizingFlow(Distribution):
         the mean NLL, produced by a fixed-order reduction inside the same engine call (written
         into ``sum_out``, e.g. ``dist.NllRing.slot(count)``, when given)."""
         fc = self._flow_call()
-        if fc is None:
+        if fc is None or not fc[0].usable(x, fc[1]):
             lp = self.log_prob(x)
             total = lp.detach().double().sum().reshape(1)
             if sum_out is not None:
@@ -250,7 +251,7 @@ class NormalizingFlow(Distribution):
     def rsample(self, shape: Size = ()) -> Tensor:
         z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
         fc = self._flow_call()
-        if fc is not None:
+        if fc is not None and fc[0].usable(z, fc[1]):
             call, ctx = fc
             return call.inverse(z, ctx)
         return self.transform.inv(z)
@@ -262,7 +263,7 @@ class NormalizingFlow(Distribution):
     def rsample_and_log_prob(self, shape: Size = ()) -> tuple[Tensor, Tensor]:
         z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
         fc = self._flow_call()
-        if fc is not None:
+        if fc is not None and fc[0].usable(z, fc[1], inverse_log_prob=True):
             call, ctx = fc
             return call.inverse(z, ctx, with_log_prob=True)
         x, ladj = self.transform.inv.call_and_ladj(z)

@@ -584,10 +584,17 @@ class ComposedTransform(EngineTransform):
             return self.__dict__[key]
         call = None
         ctx = None
-        handles, refs, sources = [], [], []
+        handles, refs, sources, inverted = [], [], [], []
         ok = self.domain_dim == 1 and self.codomain_dim == 1
         C = 0
         for t in self.transforms if ok else ():
+            inv = isinstance(t, _InverseOf) and isinstance(t._t, AutoregressiveTransform)
+            if inv:  # LazyInverse of an autoregressive layer (zuko/lazy.py:81-98): an inverted member of the engine call
+                t = t._t
+                if not E.lib().zk_layer_sequential_inverse(t._layer_handle()):
+                    ok = False
+                    break
+            inverted.append(inv)
             if isinstance(t, _PackedLayerTransform):
                 if t.features != D:
                     ok = False
@@ -608,13 +615,13 @@ class ComposedTransform(EngineTransform):
                 break
         if ok:
             handles = [r.handle for r in refs]
-            call = (_ops.FlowCall(handles, D, C, None, None, sources=sources, keep=refs), ctx)
+            call = (_ops.FlowCall(handles, D, C, None, None, sources=sources, keep=refs, inverted=inverted), ctx)
         self.__dict__[key] = call
         return call
 
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
         fused = self._fused(x.shape[-1]) if x.dim() >= 1 else None
-        if fused is not None:
+        if fused is not None and fused[0].usable(x, fused[1]):
             call, ctx = fused
             return call.forward(x, ctx)
         event_dim = self.domain_dim
@@ -627,7 +634,7 @@ class ComposedTransform(EngineTransform):
 
     def _inverse(self, y: Tensor) -> Tensor:
         fused = self._fused(y.shape[-1]) if y.dim() >= 1 else None
-        if fused is not None:
+        if fused is not None and fused[0].usable(y, fused[1]):
             call, ctx = fused
             return call.inverse(y, ctx)
         for t in reversed(self.transforms):
