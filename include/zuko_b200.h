@@ -364,6 +364,25 @@ zk_status zk_flow_inverse_backward(const zk_flow_desc* flow, const float* x, int
                                    const zk_layer_grads* const* grads, void* workspace,
                                    size_t workspace_bytes, zk_stream stream);
 
+/* ------------------------------------------------------------------------- *
+ * Multi-GPU: the path shards by rows with no data-path collective (every op is row-wise: nn.py:217-218,
+ * transforms.py:554-567, distributions.py:115-119); the ONLY exchange is the all-reduce(sum) of the
+ * per-device {sum log p, count} doubles for the scalar mean NLL.  Single-process form over
+ * NCCL (resolved with dlopen at run time); the Python mirror uses torch.distributed with one process per
+ * GPU (zuko_b200/dist.py).
+ * ------------------------------------------------------------------------- */
+typedef struct zk_comm zk_comm;
+/* one communicator over devices 0 .. ndev-1 of this process (ncclCommInitAll) */
+zk_status zk_comm_init_all(int ndev, zk_comm** out);
+zk_status zk_comm_destroy(zk_comm* comm);
+int zk_comm_size(const zk_comm* comm);
+/* buf[0..n) (DEVICE doubles on device `dev`) <- element-wise sum over all devices, asynchronously on `stream`
+ * (a stream of device `dev`).  One thread driving several devices brackets its calls — one per device — with
+ * zk_comm_group_begin / zk_comm_group_end (ncclGroupStart / ncclGroupEnd). */
+zk_status zk_comm_group_begin(zk_comm* comm);
+zk_status zk_allreduce_sum(zk_comm* comm, int dev, double* buf, int n, zk_stream stream);
+zk_status zk_comm_group_end(zk_comm* comm);
+
 /* 1 (default): the conditioner GEMMs of the backward pass (forward recompute, dgrad, wgrad) of a
  * handle packed for tcgen05 run on the tensor cores (split-bf16, fp32 accumulate); 0: fp32 FMA on
  * CUDA cores (exact-order arbitration path).  Returns the previous value. */

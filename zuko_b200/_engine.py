@@ -134,6 +134,12 @@ _SIGNATURES = {
     "zk_layer_workspace_bytes": (c_size_t, [_P, c_int64]),
     "zk_layer_fused_info": (c_int, [_P, c_void_p]),
     "zk_layer_sequential_inverse": (c_int, [_P]),
+    "zk_comm_init_all": (c_int, [c_int, POINTER(c_void_p)]),
+    "zk_comm_destroy": (c_int, [_P]),
+    "zk_comm_size": (c_int, [_P]),
+    "zk_comm_group_begin": (c_int, [_P]),
+    "zk_comm_group_end": (c_int, [_P]),
+    "zk_allreduce_sum": (c_int, [_P, c_int, _P, c_int, _P]),
     "zk_layer_update_weights": (c_int, [_P, c_void_p, c_void_p, _P]),
     "zk_set_pack_stream": (None, [_P]),
     "zk_layer_forward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_int, _P, c_size_t, _P]),
