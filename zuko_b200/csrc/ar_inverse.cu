@@ -116,7 +116,7 @@ __device__ __forceinline__ void tile_dot(const float* __restrict__ w, const floa
 //   dims    per dim of this class: feature index d, state position of x_d   (2 words each, padded to 4)
 //   tiles   hidden tiles: K_l x 8 weights (k-major over the section's ready prefix) + 8 biases each;
 //           then per dim ONE block of its PT tiles: K x (PT * 8) weights k-major + PT * 8 biases
-template <int UNI, int KT, bool FAST, int R>
+template <int UNI, int KT, bool FAST, int R, bool GACT>
 __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
     constexpr int P = (UNI == ZK_UNI_RQS) ? 3 * KT - 1 : 2;
     constexpr int PT = (P + TILE - 1) / TILE;  // tiles per dim
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
 #pragma unroll
                         for (int j = 0; j < R; ++j) {
                             const float v = (i & 1) ? acc[j][i >> 1].y : acc[j][i >> 1].x;
-                            So[u * S + j * T] = (p.act == 1) ? fmaxf(v, 0.f) : act_apply(v, p.act);
+                            if constexpr (GACT) So[u * S + j * T] = act_apply(v, p.act);  // any ZK_ACT_* (nn.py:264-265)
+                            else So[u * S + j * T] = fmaxf(v, 0.f);
                         }
                     }
                 }
@@ -281,12 +282,16 @@ zk_status launch_inv_t(const InvParams& p, bool fast, int R, int grid, int T, si
         kern<<<grid, T, smem, st>>>(p);
         return check_launch("ar_inverse_kernel");
     };
-    if (R == 2) {
-        if (fast) return go(ar_inverse_kernel<UNI, KT, true, 2>);
-        return go(ar_inverse_kernel<UNI, KT, false, 2>);
+    if (p.act != 1) {  // general activation: one instantiation per sample tiling (IEEE math in the activation)
+        if (R == 2) return fast ? go(ar_inverse_kernel<UNI, KT, true, 2, true>) : go(ar_inverse_kernel<UNI, KT, false, 2, true>);
+        return fast ? go(ar_inverse_kernel<UNI, KT, true, 1, true>) : go(ar_inverse_kernel<UNI, KT, false, 1, true>);
     }
-    if (fast) return go(ar_inverse_kernel<UNI, KT, true, 1>);
-    return go(ar_inverse_kernel<UNI, KT, false, 1>);
+    if (R == 2) {
+        if (fast) return go(ar_inverse_kernel<UNI, KT, true, 2, false>);
+        return go(ar_inverse_kernel<UNI, KT, false, 2, false>);
+    }
+    if (fast) return go(ar_inverse_kernel<UNI, KT, true, 1, false>);
+    return go(ar_inverse_kernel<UNI, KT, false, 1, false>);
 }
 
 // threads per CTA, samples per thread and shared memory for a pack.  ZK_INV_GEOM=TxR overrides the
