@@ -111,8 +111,10 @@ __device__ __forceinline__ void tile_dot(const float* __restrict__ w, const floa
 }
 
 // step block (32-bit words, 16-byte aligned sections):
-//   header  [n_tiles_0 .. n_tiles_{L-2}] [n_dims] [K_0 .. K_{L-1}]      padded to 4
-//   dest    per hidden tile 8 state positions (or -1)
+//   header  [n8_0 .. n8_{L-2}] [n_dims] [K_0 .. K_{L-1}] [n2_0 .. n2_{L-2}]      padded to 4
+//           n8 / n2: 8-wide and 2-wide hidden tiles of the layer (a fully autoregressive conditioner
+//           finalises ONE unit per layer and step: an 8-wide tile would spend 7/8 of its FMAs on padding)
+//   dest    per layer: 8 state positions per 8-wide tile, then 2 per 2-wide tile (or -1); padded to 4
 //   dims    per dim of this class: feature index d, state position of x_d   (2 words each, padded to 4)
 //   tiles   hidden tiles: K_l x 8 weights (k-major over the section's ready prefix) + 8 biases each;
 //           then per dim ONE block of its PT tiles: K x (PT * 8) weights k-major + PT * 8 biases
@@ -159,21 +161,21 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
         __syncthreads();
         const float* blk = wbuf;
         const int* hdr = reinterpret_cast<const int*>(blk);
-        const int HW = (2 * L + 3) & ~3;
+        const int HW = (3 * L + 3) & ~3;
         const int n_dims = hdr[L - 1];
-        int total_hidden_tiles = 0;
-        for (int l = 0; l < L - 1; ++l) total_hidden_tiles += hdr[l];
+        int dest_words = 0;
+        for (int l = 0; l < L - 1; ++l) dest_words += hdr[l] * TILE + hdr[2 * L + l] * 2;
+        dest_words = (dest_words + 3) & ~3;
         const int* dest = hdr + HW;
-        const int* dim_ids = dest + total_hidden_tiles * TILE;
-        const float* wp = blk + HW + total_hidden_tiles * TILE + ((2 * n_dims + 3) & ~3);
+        const int* dim_ids = dest + dest_words;
+        const float* wp = blk + HW + dest_words + ((2 * n_dims + 3) & ~3);
         // ---- hidden units that become final at this step ----
-        int tile_idx = 0;
         for (int l = 0; l < L - 1; ++l) {
             const int K = hdr[L + l];
             const float* Sl = state + (size_t)p.sec_off[l] * S + tid;
             float* So = state + (size_t)p.sec_off[l + 1] * S + tid;
-            const int nt = hdr[l];
-            for (int t = 0; t < nt; ++t, ++tile_idx) {
+            const int n8 = hdr[l], n2 = hdr[2 * L + l];
+            for (int t = 0; t < n8; ++t, dest += TILE) {
                 float2 acc[R][4];
                 const float4 b0 = *reinterpret_cast<const float4*>(wp + K * TILE);  // bias follows the tile
                 const float4 b1 = *reinterpret_cast<const float4*>(wp + K * TILE + 4);
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
                 wp += (K + 1) * TILE;
 #pragma unroll
                 for (int i = 0; i < TILE; ++i) {
-                    const int u = dest[tile_idx * TILE + i];
+                    const int u = dest[i];
                     if (u >= 0) {
 #pragma unroll
                         for (int j = 0; j < R; ++j) {
@@ -197,12 +199,40 @@ __global__ void __launch_bounds__(256) ar_inverse_kernel(const InvParams p) {
                     }
                 }
             }
+            for (int t = 0; t < n2; ++t, dest += 2) {  // 2-wide tiles: K x 2 weights (k-major) + 2 biases, padded to 16 bytes
+                float2 acc[R];
+                const float2 bb = *reinterpret_cast<const float2*>(wp + K * 2);
+#pragma unroll
+                for (int j = 0; j < R; ++j) acc[j] = bb;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const float2 wv = *reinterpret_cast<const float2*>(wp + 2 * k);
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const float sv = Sl[k * S + j * T];
+                        acc[j] = __ffma2_rn(make_float2(sv, sv), wv, acc[j]);
+                    }
+                }
+                wp += ((K + 1) * 2 + 3) & ~3;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int u = dest[i];
+                    if (u >= 0) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j) {
+                            const float v = i ? acc[j].y : acc[j].x;
+                            if constexpr (GACT) So[u * S + j * T] = act_apply(v, p.act);
+                            else So[u * S + j * T] = fmaxf(v, 0.f);
+                        }
+                    }
+                }
+            }
             // a later layer of this step reads what this layer just wrote — same thread, same
             // column of the state: no barrier needed
         }
         // ---- dims of this order class: parameters -> inverse bijector (+ forward log-derivative) ----
         {
-            const int K = hdr[2 * L - 1];
+            const int K = hdr[2 * L - 1];  // K_{L-1}
             const float* Sl = state + (size_t)p.sec_off[L - 1] * S + tid;
             for (int i = 0; i < n_dims; ++i) {
                 const int d = dim_ids[2 * i], pos = dim_ids[2 * i + 1];
@@ -338,14 +368,14 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
         if (order[d] < 0 || order[d] >= passes) return ZK_OK;
 
     // host copies of the masked weights, biases and masks
-    std::vector<std::vector<float>> W(L), Bv(L);
+    std::vector<std::vector<float>> W_(L), Bv(L);
     std::vector<std::vector<uint8_t>> Mk(L);
     for (int l = 0; l < L; ++l) {
         const size_t n = (size_t)m->dims[l + 1] * m->dims[l];
-        W[l].resize(n);
+        W_[l].resize(n);
         Bv[l].resize(m->dims[l + 1]);
         Mk[l].assign(n, 1);
-        ZK_CUDA(cudaMemcpy(W[l].data(), m->w[l], n * 4, cudaMemcpyDeviceToHost));
+        ZK_CUDA(cudaMemcpy(W_[l].data(), m->w[l], n * 4, cudaMemcpyDeviceToHost));
         ZK_CUDA(cudaMemcpy(Bv[l].data(), m->b[l], (size_t)m->dims[l + 1] * 4, cudaMemcpyDeviceToHost));
         if (mask_dev && mask_dev[l]) ZK_CUDA(cudaMemcpy(Mk[l].data(), mask_dev[l], n, cudaMemcpyDeviceToHost));
     }
@@ -417,50 +447,69 @@ zk_status ar_inverse_pack(const zk_mlp* m, const uint8_t* const* mask_dev, const
             if (order[d] == step) dims_p.push_back(d);
         std::vector<int> Kl(L);
         for (int l = 0; l < L; ++l) Kl[l] = avail(l, step);
-        // header
-        std::vector<int> hdr((2 * L + 3) & ~3, 0);
-        int total_tiles = 0;
-        for (int l = 0; l < L - 1; ++l) { hdr[l] = ((int)rows[l].size() + TILE - 1) / TILE; total_tiles += hdr[l]; }
+        // header: 8-wide tiles for full groups of 8 units (and remainders of 5..7), 2-wide tiles for remainders of 1..4
+        std::vector<int> hdr((3 * L + 3) & ~3, 0);
+        std::vector<int> n8(L, 0), n2(L, 0);
+        for (int l = 0; l < L - 1; ++l) {
+            const int n = (int)rows[l].size(), rem = n % TILE;
+            n8[l] = n / TILE + (rem > 4 ? 1 : 0);
+            n2[l] = (rem >= 1 && rem <= 4) ? (rem + 1) / 2 : 0;
+            hdr[l] = n8[l];
+            hdr[2 * L + l] = n2[l];
+        }
         hdr[L - 1] = (int)dims_p.size();
         for (int l = 0; l < L; ++l) hdr[L + l] = Kl[l];
         for (int v : hdr) stream.push_back(as_float(v));
-        for (int l = 0; l < L - 1; ++l)
-            for (int t = 0; t < hdr[l]; ++t)
-                for (int j = 0; j < TILE; ++j) {
-                    const size_t i = (size_t)t * TILE + j;
-                    stream.push_back(as_float(i < rows[l].size() ? pos[l + 1][rows[l][i]] : -1));
+        auto unit = [&](int l, size_t i) { return i < rows[l].size() ? rows[l][i] : -1; };
+        size_t dest_words = 0;
+        for (int l = 0; l < L - 1; ++l) {
+            for (int t = 0; t < n8[l]; ++t)
+                for (int j = 0; j < TILE; ++j, ++dest_words) {
+                    const int r = unit(l, (size_t)t * TILE + j);
+                    stream.push_back(as_float(r >= 0 ? pos[l + 1][r] : -1));
                 }
+            for (int t = 0; t < n2[l]; ++t)
+                for (int j = 0; j < 2; ++j, ++dest_words) {
+                    const int r = unit(l, (size_t)n8[l] * TILE + (size_t)t * 2 + j);
+                    stream.push_back(as_float(r >= 0 ? pos[l + 1][r] : -1));
+                }
+        }
+        for (; dest_words % 4; ++dest_words) stream.push_back(as_float(-1));
         for (size_t i = 0; i < dims_p.size(); ++i) {
             stream.push_back(as_float(dims_p[i]));
             stream.push_back(as_float(pos[0][dims_p[i]]));
         }
         while (stream.size() % 4) stream.push_back(as_float(-1));
-        // tile data: K_l x 8 weights (k-major over the ready prefix of the sorted section) + 8 biases
-        auto emit_tile = [&](int l, const int* row_ids) {
+        // tile data: K_l x W weights (k-major over the ready prefix of the sorted section) + W biases
+        auto emit_tile = [&](int l, const int* row_ids, int W) {
             const int K = m->dims[l];
             for (int k = 0; k < Kl[l]; ++k) {
                 const int src = slot[l][k];
-                for (int j = 0; j < TILE; ++j)
-                    stream.push_back(row_ids[j] >= 0 && Mk[l][(size_t)row_ids[j] * K + src] ? W[l][(size_t)row_ids[j] * K + src] : 0.f);
+                for (int j = 0; j < W; ++j)
+                    stream.push_back(row_ids[j] >= 0 && Mk[l][(size_t)row_ids[j] * K + src] ? W_[l][(size_t)row_ids[j] * K + src] : 0.f);
             }
-            for (int j = 0; j < TILE; ++j) stream.push_back(row_ids[j] >= 0 ? Bv[l][row_ids[j]] : 0.f);
+            for (int j = 0; j < W; ++j) stream.push_back(row_ids[j] >= 0 ? Bv[l][row_ids[j]] : 0.f);
+            while (stream.size() % 4) stream.push_back(0.f);
         };
-        for (int l = 0; l < L - 1; ++l)
-            for (int t = 0; t < hdr[l]; ++t) {
+        for (int l = 0; l < L - 1; ++l) {
+            for (int t = 0; t < n8[l]; ++t) {
                 int ids[TILE];
-                for (int j = 0; j < TILE; ++j) {
-                    const size_t i = (size_t)t * TILE + j;
-                    ids[j] = i < rows[l].size() ? rows[l][i] : -1;
-                }
-                emit_tile(l, ids);
+                for (int j = 0; j < TILE; ++j) ids[j] = unit(l, (size_t)t * TILE + j);
+                emit_tile(l, ids, TILE);
             }
+            for (int t = 0; t < n2[l]; ++t) {
+                int ids[2];
+                for (int j = 0; j < 2; ++j) ids[j] = unit(l, (size_t)n8[l] * TILE + (size_t)t * 2 + j);
+                emit_tile(l, ids, 2);
+            }
+        }
         for (int d : dims_p) {  // one block per dim: K x (PT * 8) weights k-major, then PT * 8 biases
             const int l = L - 1, K = m->dims[l];
             for (int k = 0; k < Kl[l]; ++k) {
                 const int src = slot[l][k];
                 for (int q = 0; q < PT * TILE; ++q) {
                     const int row = d * P + q;
-                    stream.push_back(q < P && Mk[l][(size_t)row * K + src] ? W[l][(size_t)row * K + src] : 0.f);
+                    stream.push_back(q < P && Mk[l][(size_t)row * K + src] ? W_[l][(size_t)row * K + src] : 0.f);
                 }
             }
             for (int q = 0; q < PT * TILE; ++q) stream.push_back(q < P ? Bv[l][d * P + q] : 0.f);
