@@ -101,6 +101,12 @@ def test_schedule_covers_every_nonzero_tile(name):
                 last_idx[kb] = i
             for i, (ch, kb) in enumerate(order):
                 assert bool(fl[i] & AFREE) == (last_idx[kb] == i)
+            # issued 16-column MMA steps: exactly up to the last column of the block that any row of the chunk reads
+            for i, (ch, kb) in enumerate(order):
+                blk = M[ch * width : (ch + 1) * width, kb * 64 : (kb + 1) * 64]
+                used = np.nonzero(blk.any(axis=0))[0]
+                steps = 4 - ((int(fl[i]) >> 20) & 3)
+                assert steps == (int(used.max()) // 16 + 1 if used.size else 1), (l, ch, kb)
 
 
 def _replay(items, rd, L, nch, KB0, n_last, seed, tiles=3):

@@ -58,7 +58,7 @@ constexpr uint32_t TMD_D = 256;                                    // first accu
 //   x [1:0] K block | [2] sub-tile | [3] first K block of its chunk | [4] last K block of its chunk |
 //     [5] first read of this sub-tile's A block in this layer (wait a_ready) | [6] last read (commit a_free) |
 //     [7] output layer | [15:8] a_ready phases (index = 4 sub-tile + kb) consumed without reading |
-//     [18:16] layer
+//     [18:16] layer | [21:20] trailing 16-column MMA steps that are all-zero for this chunk (not issued)
 constexpr uint32_t DS_FIRST = 8u, DS_LAST = 16u, DS_AWAIT = 32u, DS_AFREE = 64u, DS_OUT = 128u;
 
 struct DualParams {
@@ -209,9 +209,11 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                     }
                 }
                 tc_fence_after();
+                const int nk = 4 - (int)((cur >> 20) & 3u);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < DK / 16; ++k) {
+                        if (k >= nk) break;
                         const uint32_t acol = (uint32_t)k * 8u;
                         umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
                         if (p.n_terms == 3) {
@@ -686,11 +688,13 @@ bool dual_build_schedule(const int* dims, int L, const std::vector<std::vector<u
     sh.L = L; sh.nch = H / 128; sh.KB0 = pad64(dims[0]) / 64; sh.KBH = H / 64;
     sh.n_last = (D + DPC - 1) / DPC;
     std::vector<std::vector<uint32_t>> kbmask(L);
+    std::vector<std::vector<int>> kmax(L);  // [ch * 8 + kb]: last K column of the block any row of the chunk reads
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         const int K = dims[l], N = dims[l + 1];
         const int nch = last ? sh.n_last : sh.nch;
         kbmask[l].assign(nch, 0);
+        kmax[l].assign((size_t)nch * 8, 0);
         for (int ch = 0; ch < nch; ++ch) {
             const int n0 = last ? ch * DPC * P : ch * 128;
             const int n1 = std::min(N, last ? n0 + DPC * P : n0 + 128);
@@ -700,7 +704,10 @@ bool dual_build_schedule(const int* dims, int L, const std::vector<std::vector<u
                 const uint8_t* mrow = &Mk[l][(size_t)sn * K];
                 for (int k = 0; k < K; ++k) {
                     const int sk = (l > 0) ? perm[l - 1][k] : k;
-                    if (mrow[sk]) bits |= 1u << (k / 64);
+                    if (mrow[sk]) {
+                        bits |= 1u << (k / 64);
+                        kmax[l][(size_t)ch * 8 + k / 64] = std::max(kmax[l][(size_t)ch * 8 + k / 64], k % 64);
+                    }
                 }
             }
             if (bits == 0) bits = 1;
@@ -736,6 +743,7 @@ bool dual_build_schedule(const int* dims, int L, const std::vector<std::vector<u
                     if (!((waited[u] >> kb) & 1u)) { it |= DS_AWAIT; waited[u] |= 1u << kb; }
                     if (last_reader[kb] == ch) it |= DS_AFREE;
                     if (last) it |= DS_OUT;
+                    it |= (uint32_t)(3 - kmax[l][(size_t)ch * 8 + kb] / 16) << 20;  // trailing all-zero 16-column steps of the block are not issued
                     if (layer_first[u] == (size_t)-1) layer_first[u] = items.size();
                     items.push_back(make_uint2(it, (uint32_t)(last ? ch * DPC * P : ch * 128)));
                     first = false;
@@ -797,7 +805,7 @@ zk_status fused_dual_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univ
     for (int l = 0; l < 8; ++l) wp.rd_mask[l] = (uint8_t)rdm[l];
     {
         double macs = 0;
-        for (const uint2& it : items) macs += 64.0 * ((it.x & DS_OUT) ? N_LAST : 128);
+        for (const uint2& it : items) macs += 16.0 * (4 - (int)((it.x >> 20) & 3u)) * ((it.x & DS_OUT) ? N_LAST : 128);
         wp.issued_macs_per_row = macs / 2 * pk->n_terms;  // the schedule covers two sub-tiles
     }
     cudaFree(wp.sched);

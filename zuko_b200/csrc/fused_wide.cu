@@ -81,7 +81,8 @@ constexpr int W_WATCH_WORDS = 1024;
 //   x [2:0] K block | [3] first K block of its chunk | [4] last K block of its chunk |
 //     [5] first read of A block kb in this layer (wait a_ready[kb]) | [6] last read of A block kb in this
 //     layer (commit a_free[kb]) | [7] output layer | [15:8] a_ready phases the layer consumes without
-//     reading (on the layer's first entry) | [18:16] layer
+//     reading (on the layer's first entry) | [18:16] layer |
+//     [21:20] trailing 16-column MMA steps of the K block that are all-zero for this chunk (not issued)
 constexpr uint32_t WS_FIRST = 8u, WS_LAST = 16u, WS_AWAIT = 32u, WS_AFREE = 64u, WS_OUT = 128u;
 
 struct WideParams {
@@ -232,9 +233,11 @@ fused_wide_kernel(const __grid_constant__ WideParams p) {
                     }
                 }
                 tc_fence_after();
+                const int nk = 4 - (int)((cur >> 20) & 3u);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < WK / 16; ++k) {
+                        if (k >= nk) break;
                         const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
                         umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
                         if (p.n_terms == 3) {
@@ -711,11 +714,13 @@ bool wide_build_schedule(const int* dims, int L, const std::vector<std::vector<u
     sh.n_last = (D + DPC - 1) / DPC; sh.DPC = DPC; sh.P = P;
     // ---- which (chunk, K block) tiles of the permuted masked matrices are non-zero ----
     std::vector<std::vector<uint32_t>> kbmask(L);
+    std::vector<std::vector<int>> kmax(L);  // [ch * 8 + kb]: last K column of the block any row of the chunk reads
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         const int K = dims[l], N = dims[l + 1];
         const int nch = last ? sh.n_last : sh.nch;
         kbmask[l].assign(nch, 0);
+        kmax[l].assign((size_t)nch * 8, 0);
         for (int ch = 0; ch < nch; ++ch) {
             const int n0 = last ? ch * DPC * P : ch * 128;
             const int n1 = std::min(N, last ? n0 + DPC * P : n0 + 128);
@@ -725,7 +730,10 @@ bool wide_build_schedule(const int* dims, int L, const std::vector<std::vector<u
                 const uint8_t* mrow = &Mk[l][(size_t)sn * K];
                 for (int k = 0; k < K; ++k) {
                     const int sk = (l > 0) ? perm[l - 1][k] : k;
-                    if (mrow[sk]) bits |= 1u << (k / 64);
+                    if (mrow[sk]) {
+                        bits |= 1u << (k / 64);
+                        kmax[l][(size_t)ch * 8 + k / 64] = std::max(kmax[l][(size_t)ch * 8 + k / 64], k % 64);
+                    }
                 }
             }
             if (bits == 0) bits = 1;  // the accumulator still has to be defined (bias-only outputs)
@@ -761,6 +769,7 @@ bool wide_build_schedule(const int* dims, int L, const std::vector<std::vector<u
                 if (!((waited >> kb) & 1u)) { it |= WS_AWAIT; waited |= 1u << kb; }
                 if (last_reader[kb] == ch) it |= WS_AFREE;
                 if (last) it |= WS_OUT;
+                it |= (uint32_t)(3 - kmax[l][(size_t)ch * 8 + kb] / 16) << 20;  // trailing all-zero 16-column steps of the block are not issued
                 items.push_back(make_uint2(it, (uint32_t)(last ? ch * DPC * P : ch * 128)));
                 first = false;
             }
@@ -816,7 +825,7 @@ zk_status fused_wide_prepare(zk_mlp* m, const uint8_t* const* mask_dev, int univ
     for (int l = 0; l < 8; ++l) wp.rd_mask[l] = (uint8_t)rdm[l];
     {
         double macs = 0;
-        for (const uint2& it : items) macs += 64.0 * ((it.x & WS_OUT) ? N_LAST : 128);
+        for (const uint2& it : items) macs += 16.0 * (4 - (int)((it.x >> 20) & 3u)) * ((it.x & WS_OUT) ? N_LAST : 128);
         wp.issued_macs_per_row = macs * pk->n_terms;
     }
     cudaFree(wp.sched);
