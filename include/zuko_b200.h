@@ -253,6 +253,13 @@ typedef struct {
  * workspace >= zk_flow_min_workspace_bytes() is accepted (the batch is then
  * processed in row chunks). */
 size_t zk_flow_workspace_bytes(const zk_flow_desc* flow, int64_t B);
+/* Workspace that lets zk_flow_log_prob_host run its preferred chunk plan for a batch of B rows (first chunk one
+   wave of the persistent kernels, later chunks growing; two staging slots of the largest chunk + the flow's own
+   scratch).  A smaller workspace still works: the plan is capped to what fits. */
+size_t zk_flow_host_workspace_bytes(const zk_flow_desc* flow, int64_t B);
+/* Test hook: the row chunks zk_flow_log_prob_host would use for B rows with the given wave size (rows one wave
+   of the persistent kernels covers) and chunk cap; returns their number. */
+int64_t zk_debug_host_chunk_plan(int64_t B, int64_t wave, int64_t max_chunk, int64_t* out, int64_t cap);
 size_t zk_flow_min_workspace_bytes(const zk_flow_desc* flow);
 
 /* transform.call_and_ladj(x) — transforms.py:141-150: z (B, D), ladj (B). */

@@ -356,6 +356,38 @@ def test_host_buffer_entry_point(device):
     assert abs(total - ref.double().sum().item()) < 1e-6 * abs(total)
 
 
+def test_host_buffer_entry_point_growing_chunks(device):
+    """Past four waves the host pipeline runs growing chunks (1, 2, 3, 5, ... waves; api.cu:host_chunk_plan):
+    a ragged 2^18 + 777-row batch, with the preferred workspace and with one that caps the chunks, equals the
+    device-resident call bit for bit; the sum is the same fixed-order reduction of per-chunk sums to 1e-9."""
+    import ctypes
+
+    g = load("flow_cfg2_nsf")
+    flow = build_flow("cfg2_nsf", g).to(device)
+    B = (1 << 18) + 777
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 16, generator=gen).pin_memory()
+    c = torch.randn(B, 8, generator=gen).pin_memory()
+    dist = flow(c.to(device))
+    ref = dist.log_prob(x.to(device)).cpu()
+    fc = dist._flow_call()[0]
+    out, total = fc.log_prob_host(x, c, device)
+    assert torch.equal(out, ref)
+    assert abs(total - ref.double().sum().item()) < 1e-9 * abs(total)
+    # a workspace far below the preferred size: chunks capped, same answer
+    L = E.lib()
+    small = L.zk_flow_host_workspace_bytes(ctypes.byref(fc.desc), 60000)
+    assert small < L.zk_flow_host_workspace_bytes(ctypes.byref(fc.desc), B)
+    ws = torch.empty(small, dtype=torch.uint8, device=device)
+    out2 = torch.empty(B, dtype=torch.float32).pin_memory()
+    tot2 = ctypes.c_double(0.0)
+    with torch.cuda.device(device):
+        E.check(L.zk_flow_log_prob_host(ctypes.byref(fc.desc), x.data_ptr(), 16, c.data_ptr(), 8, B, out2.data_ptr(),
+                                        ctypes.byref(tot2), ws.data_ptr(), ws.numel(), E.stream_ptr(device)))
+    assert torch.equal(out2, ref)
+    assert abs(tot2.value - total) < 1e-9 * abs(total)
+
+
 def test_circular_shift_and_box_uniform(device):
     """CircularShiftTransform (transforms.py:319-351) and BoxUniform.log_prob (distributions.py:366-396)
     against the reference's golden vectors: the shift is bit-exact in fp32."""

@@ -190,3 +190,35 @@ def test_product_does_not_import_oracle():
     for path in (ROOT / "zuko_b200").rglob("*.py"):
         src = path.read_text()
         assert "oracle" not in src.replace("no CPU", ""), f"{path} mentions the oracle"
+
+
+def test_host_pipeline_chunk_plan():
+    """zk_flow_log_prob_host's row chunks (api.cu:host_chunk_plan): they cover the batch exactly, start with one
+    wave, are whole waves except the last, never grow by more than 2x (the copy of chunk k has to fit inside the
+    compute of chunk k-1), respect the cap the workspace imposes, and small batches keep the eight-equal-chunks plan."""
+    import numpy as np
+
+    from zuko_b200 import _engine as E
+
+    wave = 74 * 512
+
+    def plan(B, cap=None):
+        out = np.zeros(4096, np.int64)
+        n = E.lib().zk_debug_host_chunk_plan(B, wave, cap or B, out.ctypes.data, 4096)
+        assert 0 <= n <= 4096
+        return out[:n].tolist()
+
+    assert plan(0) == []
+    assert plan(1) == [1]
+    assert plan(5000) == [4096, 904]
+    assert plan(100000) == [12500] * 8
+    for B in (1 << 18, 1 << 20, (1 << 20) + 12345, 1 << 21, 1 << 24):
+        p = plan(B)
+        assert sum(p) == B and p[0] == wave
+        assert all(n % wave == 0 for n in p[:-1])
+        assert all(b <= 2 * a for a, b in zip(p, p[1:-1]))
+        assert p[-1] >= wave // 2 or len(p) == 1
+        assert max(p) <= 32 * wave + wave // 2
+    p = plan(1 << 20, cap=200000)
+    assert sum(p) == 1 << 20 and max(p) <= 200000 and p[0] == wave
+    assert sum(plan(1 << 20, cap=1000)) == 1 << 20 and max(plan(1 << 20, cap=1000)) <= 1000

@@ -145,6 +145,8 @@ _SIGNATURES = {
     "zk_layer_forward": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_int, _P, c_size_t, _P]),
     "zk_layer_inverse": (c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "zk_flow_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),
+    "zk_flow_host_workspace_bytes": (c_size_t, [POINTER(FlowDesc), c_int64]),
+    "zk_debug_host_chunk_plan": (c_int64, [c_int64, c_int64, c_int64, c_void_p, c_int64]),
     "zk_flow_min_workspace_bytes": (c_size_t, [POINTER(FlowDesc)]),
     "zk_flow_forward": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
     "zk_flow_log_prob": (c_int, [POINTER(FlowDesc), _P, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),

@@ -487,8 +487,7 @@ class FlowCall:
         total = ctypes.c_double(0.0)
         with torch.cuda.device(device):
             L = E.lib()
-            chunk = max(4096, -(-B // 8))
-            want = L.zk_flow_workspace_bytes(ctypes.byref(self.desc), chunk) + 2 * chunk * (self.D + self.C + 1) * 4 + (1 << 20)
+            want = L.zk_flow_host_workspace_bytes(ctypes.byref(self.desc), B) + (1 << 20)
             ws = E.Workspace.get(device, want, want)
             E.check(
                 L.zk_flow_log_prob_host(

@@ -1038,6 +1038,57 @@ zk_status get_pipe(HostPipe** out) {
 }
 }  // namespace zkapi
 
+}  // extern "C"
+
+/* Row chunks of the host pipeline.  The H2D copies run ahead of the compute (47 GB/s against ~30 GB/s of
+   input consumed by cfg2, less for every heavier flow), so a call costs copy(first chunk) + compute(all) +
+   a per-launch ramp per chunk: the first chunk is ONE wave of the persistent kernels (a wave = SMs/2 CTA pairs x
+   512 rows; chunks are whole waves, a 3.46-wave chunk runs as 4), the later ones grow by <= 1.7x — with two
+   staging slots the copy of chunk k starts when chunk k-2 is done and has to finish within the compute of
+   chunk k-1 — up to `max_chunk` (what the workspace holds).  Small batches: eight equal chunks as before. */
+std::vector<int64_t> host_chunk_plan(int64_t B, int64_t wave, int64_t max_chunk) {
+    std::vector<int64_t> plan;
+    if (B <= 0) return plan;
+    max_chunk = std::max<int64_t>(1, max_chunk);
+    if (B <= 4 * wave || max_chunk < wave) {
+        const int64_t Bc = std::min(std::min(max_chunk, B), std::max<int64_t>(4096, ceil_div(B, 8)));
+        for (int64_t i = 0; i < B; i += Bc) plan.push_back(std::min(Bc, B - i));
+        return plan;
+    }
+    const int64_t cap = std::max<int64_t>(wave, (max_chunk / wave) * wave);
+    int64_t left = B, w = 1;  // w: next chunk in waves
+    while (left > 0) {
+        int64_t n = std::min(std::min(w * wave, cap), left);
+        if (left - n < wave / 2 && left <= cap) n = left;  // a sliver is not worth its own launches
+        plan.push_back(n);
+        left -= n;
+        w = std::min<int64_t>(32, (w * 3 + 1) / 2);  // 1 2 3 5 8 12 18 27 32 32 ...: past ~1 M rows a chunk's ramp is noise, its staging is not
+    }
+    return plan;
+}
+
+static size_t host_pipe_need(const zk_flow_desc* f, int64_t n) {
+    const size_t D = (size_t)f->features, C = (size_t)f->context;
+    return 2 * (a256((size_t)n * D * 4) + a256((size_t)n * C * 4) + a256((size_t)n * 4)) + a256(C * 4) +
+           a256(4096 * sizeof(double)) + flow_ws_for(f, n);
+}
+
+extern "C" {
+
+size_t zk_flow_host_workspace_bytes(const zk_flow_desc* f, int64_t B) {
+    if (!f || B <= 0) return 1024;
+    const int64_t wave = (int64_t)(sm_count() / 2) * 512;
+    int64_t big = 0;
+    for (int64_t n : host_chunk_plan(B, wave, B)) big = std::max(big, n);
+    return host_pipe_need(f, big) + 4096;
+}
+
+int64_t zk_debug_host_chunk_plan(int64_t B, int64_t wave, int64_t max_chunk, int64_t* out, int64_t cap) {
+    const std::vector<int64_t> plan = host_chunk_plan(B, wave, max_chunk);
+    for (size_t i = 0; i < plan.size() && (int64_t)i < cap; ++i) out[i] = plan[i];
+    return (int64_t)plan.size();
+}
+
 zk_status zk_flow_log_prob_host(const zk_flow_desc* f, const float* xh, int64_t ldx, const float* ch,
                                 int64_t ldc, int64_t B, float* lph, double* sum_host, void* ws,
                                 size_t ws_bytes, zk_stream stream) {
@@ -1056,24 +1107,19 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* f, const float* xh, int64_t 
     const bool bc = (C > 0 && ldc == 0);  // one broadcast context row
     // staging per row: x + c + lp, two slots; the rest of the workspace runs the flow
     const size_t stage_row = (size_t)(D + (bc ? 0 : C) + 1) * 4;
-    // pick the chunk: at most B/4 rows (so the pipeline overlaps), at least 4096, bounded by memory
-    int64_t Bc = std::max<int64_t>(4096, ceil_div(B, 8));
-    {   // whole waves of the persistent fused kernels: one wave = (SMs / 2) CTA pairs x 512 rows (dual-tile kernel;
-        // 256 for the other two, which divide it): a chunk of 3.46 waves runs as 4 (profiles/r02_bench_v2_dual.json:
-        // e2e 4.7 ms against 3.6 ms of compute and 2.2 ms of PCIe time for the same step)
-        const int64_t wave = (int64_t)(sm_count() / 2) * 512;
-        if (Bc > wave) Bc = std::max<int64_t>(1, (Bc + wave / 2) / wave) * wave;
-    }
-    Bc = std::min(Bc, B);
-    auto need = [&](int64_t n) {
-        return 2 * (a256((size_t)n * D * 4) + a256((size_t)n * C * 4) + a256((size_t)n * 4)) + a256((size_t)C * 4) +
-               a256(4096 * sizeof(double)) + flow_ws_for(f, n);
-    };
-    while (Bc > 1 && need(Bc) > ws_bytes) Bc = (Bc + 1) / 2;
-    ZK_REQUIRE(need(Bc) <= ws_bytes, "flow_log_prob_host: workspace too small (%zu < %zu)", ws_bytes, need(1));
+    // chunk plan (host_chunk_plan): the step's time is the FIRST chunk's copy plus the compute of all of them,
+    // so the first chunk is one wave and the later ones grow; bounded by the workspace
+    const int64_t wave = (int64_t)(sm_count() / 2) * 512;
+    auto need = [&](int64_t n) { return host_pipe_need(f, n); };
+    int64_t Bmax = B;
+    while (Bmax > 1 && need(Bmax) > ws_bytes) Bmax = (Bmax > wave) ? std::max<int64_t>(wave, (Bmax / 2 / wave) * wave) : (Bmax + 1) / 2;
+    ZK_REQUIRE(need(Bmax) <= ws_bytes, "flow_log_prob_host: workspace too small (%zu < %zu)", ws_bytes, need(1));
     (void)stage_row;
-    const int64_t nchunks = ceil_div(B, Bc);
+    const std::vector<int64_t> plan = host_chunk_plan(B, wave, Bmax);
+    const int64_t nchunks = (int64_t)plan.size();
     ZK_REQUIRE(nchunks <= 4096, "flow_log_prob_host: too many chunks; pass a larger workspace");
+    int64_t Bc = 0;
+    for (int64_t n : plan) Bc = std::max(Bc, n);
     Arena ar(ws, ws_bytes);
     float* xd[2] = {ar.take<float>((size_t)Bc * D), ar.take<float>((size_t)Bc * D)};
     float* cd[2] = {nullptr, nullptr};
@@ -1091,9 +1137,10 @@ zk_status zk_flow_log_prob_host(const zk_flow_desc* f, const float* xh, int64_t 
     ZK_CUDA(cudaStreamWaitEvent(p.h2d, p.ev_comp[0], 0));
     ZK_CUDA(cudaStreamWaitEvent(p.d2h, p.ev_comp[0], 0));
     if (bc) ZK_CUDA(cudaMemcpyAsync(cb, ch, (size_t)C * 4, cudaMemcpyHostToDevice, p.h2d));
-    for (int64_t k = 0; k < nchunks; ++k) {
+    int64_t i0 = 0;
+    for (int64_t k = 0; k < nchunks; i0 += plan[(size_t)k], ++k) {
         const int s = (int)(k & 1);
-        const int64_t i0 = k * Bc, n = std::min(Bc, B - i0);
+        const int64_t n = plan[(size_t)k];
         if (k >= 2) {  // slot reuse: chunk k-2 must have been computed and read back
             ZK_CUDA(cudaStreamWaitEvent(p.h2d, p.ev_comp[s], 0));
         }
