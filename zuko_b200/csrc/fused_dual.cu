@@ -235,9 +235,9 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
         }
     } else if (warp == 2) {
         // ======================= operand scout (leader CTA) =======================
-        // A probe of an mbarrier costs ~300 cycles even when its phase completed long ago (profiles/
-        // r02_dual_timeline_v1.txt: one scout doing up to three probes per entry published one entry per
-        // ~1000 cycles, less than the tensor pipe consumes).  So two lanes in two warps walk the schedule
+        // A probe of an mbarrier costs ~300 cycles even when its phase completed long ago (one scout doing up
+        // to three probes per entry published one entry per ~1000 cycles, less than the tensor pipe consumes;
+        // DESIGN.md 5b).  So two lanes in two warps walk the schedule
         // independently, each with its own parity state: this one waits for what the EPILOGUE produces
         // (accumulator drained, A blocks written), warp 3 for what the TMA produces (weights landed);
         // the issuer reads both counters.
