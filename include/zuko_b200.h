@@ -157,7 +157,8 @@ typedef struct {
      * arrays of n_linear ints or NULL for the plain pattern (activation after every layer but the last):
      * layer_act[i] = 0 none / 1 ReLU / ZK_ACT_* applied to the output of layer i; layer_res[i] != 0 adds the
      * INPUT of layer i-1 to the output of layer i (second layer of a residual block; needs i >= 2 and equal
-     * widths).  Such handles run on the fp32 CUDA-core path. */
+     * widths).  Such handles run the per-layer GEMM kernels (tensor cores or fp32 by gemm_mode), never the
+     * fused layer kernels; their backward pass runs the fp32 kernels. */
     const int* layer_act;
     const int* layer_res;
 } zk_mlp_desc;

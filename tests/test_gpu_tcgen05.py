@@ -1,6 +1,8 @@
 """GPU tests of the tcgen05 (tensor-core) conditioner path against the fp64 oracle and the
 fp32 CUDA-core path."""
 
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -80,6 +82,77 @@ def test_flow_parity_on_tensor_cores(device, name):
     lp = flow(c).log_prob(torch.from_numpy(g["x"]).to(device))
     assert E.lib().zk_mlp_gemm_mode(flow.transform.transforms[0].hyper._handle()) == E.ZK_GEMM_BF16X3
     assert_log_prob_parity(lp.detach().cpu().numpy(), g, rtol=1e-5)
+
+
+RES_SHAPES = [
+    ((368, 24), [256, 256, 256], torch.nn.ReLU),   # cfg2's conditioner with residual blocks: L, R(L a L), R, R, L
+    ((64, 40), [512, 512], torch.nn.ELU),          # two N chunks per layer, general activation inside the block
+    ((69, 8), [96, 160, 160], torch.nn.SiLU),      # widths change: Linear 96, Linear 160 + block, block (padded K 192)
+]
+
+
+@pytest.mark.parametrize("shape,hidden,act", RES_SHAPES)
+@pytest.mark.parametrize("B", [1, 129, 5000])
+def test_residual_mlp_on_tensor_cores(device, shape, hidden, act, B):
+    """MaskedMLP(residual=True) (zuko/nn.py:195-199, 297-309) on the tcgen05 GEMM kernels: the second layer of a
+    block adds the block's input, read back from the bf16 hi / lo planes the kernel overwrites in place."""
+    def make():
+        torch.manual_seed(5)
+        adjacency = torch.rand(*shape) < 0.6
+        adjacency[:, 0] = True
+        return zuko.nn.MaskedMLP(adjacency, hidden, activation=act, residual=True)
+
+    net = make()
+    assert any(isinstance(m, zuko.nn.Residual) for m in net)
+    net.gemm_mode = "bf16x3"
+    x = torch.randn(B, shape[1], generator=torch.Generator().manual_seed(B))
+    ref = _oracle_mlp(net, x)
+    out = net.to(device)(x.to(device)).detach().cpu().numpy().astype(np.float64)
+    assert E.lib().zk_mlp_gemm_mode(net._handle()) == E.ZK_GEMM_BF16X3
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() / scale < 3e-5
+    net32 = make()
+    net32.gemm_mode = "fp32"
+    out32 = net32.to(device)(x.to(device)).detach().cpu().numpy().astype(np.float64)
+    assert np.abs(out32 - ref).max() / scale < 2e-6
+
+
+@pytest.mark.parametrize("name", ["res_nsf_relu", "res_nsf_mixed"])
+def test_residual_goldens_on_tensor_cores(device, name):
+    """The reference's residual flows (tests/golden/make_golden_res.py) with the conditioner forced onto
+    tcgen05: log_prob within 1e-5 of the reference, gradients still flow (fp32 backward kernels)."""
+    g = load(f"flow_{name}")
+    flow = build_flow(name, g)
+    for t in flow.transform.transforms:
+        t.hyper.gemm_mode = "bf16x3"
+    flow = flow.to(device)
+    c = None if "c" not in g else torch.from_numpy(g["c"]).to(device)
+    x = torch.from_numpy(g["x"]).to(device)
+    lp = flow(c).log_prob(x)
+    assert E.lib().zk_mlp_gemm_mode(flow.transform.transforms[0].hyper._handle()) == E.ZK_GEMM_BF16X3
+    assert_log_prob_parity(lp.detach().cpu().numpy(), g, rtol=1e-5)
+    (-lp.mean()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in flow.parameters())
+
+
+def test_wide_residual_flow_vs_oracle(device):
+    """A residual MAF wide enough for `auto` to pick the tensor cores (hidden 256): per-layer GEMM kernels (the
+    fused layer kernels refuse residual blocks), log_prob and the sweep inverse against the fp64 oracle."""
+    torch.manual_seed(21)
+    flow_cpu = zuko.flows.MAF(12, 4, transforms=2, hidden_features=[256, 256], residual=True)
+    spec = O.flowspec_from_module(flow_cpu)
+    gen = torch.Generator().manual_seed(2)
+    x, c = torch.randn(3000, 12, generator=gen), torch.randn(3000, 4, generator=gen)
+    flow = flow_cpu.to(device)
+    with torch.no_grad():
+        lp = flow(c.to(device)).log_prob(x.to(device))
+        assert E.lib().zk_mlp_gemm_mode(flow.transform.transforms[0].hyper._handle()) == E.ZK_GEMM_BF16X3
+        info = (ctypes.c_double * 4)()
+        assert E.lib().zk_layer_fused_info(flow.transform.transforms[0]._zk_layer(), info) == 0  # per-layer GEMM kernels
+        ref = spec.log_prob(x.numpy(), c.numpy())
+        assert rel_err(lp.cpu().numpy(), ref) < 1e-5
+        xr = flow(c.to(device)).transform.inv(flow(c.to(device)).transform(x.to(device)))
+        assert (xr.cpu() - x).abs().max().item() < 1e-4
 
 
 def test_auto_mode_picks_tensor_cores_for_wide_layers(device):

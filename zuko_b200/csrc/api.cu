@@ -240,10 +240,7 @@ zk_status zk_mlp_create(const zk_mlp_desc* d, zk_mlp** out) {
         if (i < d->n_linear - 1) m->max_hidden = std::max(m->max_hidden, m->dims[i + 1]);
     }
     if (st == ZK_OK) {
-        if (!m->plain && (d->gemm_mode == ZK_GEMM_BF16X3 || d->gemm_mode == ZK_GEMM_BF16X1))
-            st = fail(ZK_EUNSUPPORTED, "mlp_create: residual conditioners run on the fp32 path only");
-        else
-            st = tc_pack(m, m->plain ? d->gemm_mode : ZK_GEMM_FP32);  // resolves m->gemm_mode
+        st = tc_pack(m, d->gemm_mode);  // resolves m->gemm_mode (residual blocks: per-layer GEMM kernels, never the fused ones)
     }
     if (st == ZK_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(ZK_ECUDA, "mlp_create: sync failed");
     if (st != ZK_OK) {

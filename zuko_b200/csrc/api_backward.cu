@@ -37,7 +37,7 @@ zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
         if (!m->bwd_dirty) return ZK_OK;
         // the weights were refreshed in place (zk_layer_update_weights): same buffers, new transposes
         for (int i = 0; i < m->n_linear; ++i) ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], m->wt[i], st));
-        if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1) ZK_TRY(tc_pack_backward(m, st));
+        if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1 && m->plain) ZK_TRY(tc_pack_backward(m, st));
         m->bwd_dirty = false;
         return ZK_OK;
     }
@@ -49,7 +49,7 @@ zk_status mlp_ensure_backward(const zk_mlp* cm, cudaStream_t st) {
         m->wt.push_back(t);
         ZK_TRY(launch_transpose(m->w[i], m->dims[i + 1], m->dims[i], t, st));
     }
-    if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1) ZK_TRY(tc_pack_backward(m, st));
+    if (m->gemm_mode != ZK_GEMM_FP32 && m->tc != nullptr && m->act == 1 && m->plain) ZK_TRY(tc_pack_backward(m, st));
     ZK_CUDA(cudaStreamSynchronize(st));
     return ZK_OK;
 }

@@ -59,6 +59,10 @@ struct TcParams {
     int Np;                     // padded width of the next layer's K
     // backward pass (tc_gemm): ReLU gate and batch-sliced weight operand
     const __nv_bfloat16* gate;  // [M][Np] hi plane of a ReLU output: out = gate > 0 ? out : 0 (planes output only)
+    // second layer of a residual block (zuko/nn.py:195-199; GENERAL_ACT instantiation, planes output only):
+    // hi + lo of these planes [2][M][Np] is added to the output.  May alias out_planes: every element is read
+    // by the thread that then overwrites it.
+    const __nv_bfloat16* res;
     int slice_m;                // > 0: rows [s * slice_m, (s + 1) * slice_m) of A pair with W rows s * w_slice_rows + n
     int w_slice_rows;
 };
@@ -234,6 +238,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 const int j = q4 * 8 + u * 2;
                                 if (!((b0 & 0x7fffu) != 0u && (b0 & 0x8000u) == 0u)) v[j] = 0.f;
                                 if (!((b1 & 0x7fffu) != 0u && (b1 & 0x8000u) == 0u)) v[j + 1] = 0.f;
+                            }
+                        }
+                    }
+                    if constexpr (GENERAL_ACT) {
+                        if (p.res != nullptr) {
+                            const uint4* rh = reinterpret_cast<const uint4*>(p.res + (int64_t)row * p.Np + n0 + c0);
+                            const uint4* rl = reinterpret_cast<const uint4*>(p.res + (int64_t)p.M * p.Np + (int64_t)row * p.Np + n0 + c0);
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                const uint4 a = rh[q4], b = rl[q4];  // plain loads: the planes may be the ones written below
+                                const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, al[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int j = q4 * 8 + u * 2;
+                                    v[j] += __uint_as_float(ah[u] << 16) + __uint_as_float(al[u] << 16);
+                                    v[j + 1] += __uint_as_float(ah[u] & 0xffff0000u) + __uint_as_float(al[u] & 0xffff0000u);
+                                }
                             }
                         }
                     }
@@ -466,20 +487,22 @@ zk_status tc_forward(const zk_mlp* m, const float* x, int64_t ldx, int dx, const
         p.M = (int)B; p.N = L.N; p.Kp = L.Kp;
         p.n_chunks = (L.N + BN - 1) / BN;
         p.n_terms = pk->n_terms;
-        p.relu = last ? 0 : m->act;
+        p.relu = m->lact[i];  // per layer: the plain pattern is act ... act 0, residual blocks are act 0 pairs
         p.bias = m->b[i];
         p.out_f32 = last ? out : nullptr;
         p.ldo = ldo;
         p.out_planes = last ? nullptr : hid[i & 1];
         p.Np = last ? 0 : pk->layers[i + 1].Kp;
         p.gate = nullptr; p.slice_m = 0; p.w_slice_rows = 0;
+        // residual block: the input of layer i-1 is what layer i-2 left in the ping-pong buffer this layer writes
+        p.res = (!last && m->lres[i]) ? hid[i & 1] : nullptr;
         if (!last) {
             // the next layer reads columns [0, Np): they are all written when the chunks cover Np
             ZK_REQUIRE(p.n_chunks * BN >= p.Np, "tc_forward: internal padding error");
         }
         const int64_t tiles = ceil_div(B, BM) * p.n_chunks;
         const int grid = (int)std::min<int64_t>(tiles, sms);
-        if (p.relu > 1) linear_tc_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
+        if (p.relu > 1 || p.res != nullptr) linear_tc_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
         else linear_tc_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(mapA, L.mapW, p);
         ZK_TRY(check_launch("linear_tc_kernel"));
         a = p.out_planes;
@@ -675,6 +698,7 @@ zk_status tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
     p.out_f32 = a.out_f32; p.ldo = a.ldo;
     p.out_planes = a.out_planes; p.Np = a.Np;
     p.gate = a.gate; p.slice_m = a.slice_m; p.w_slice_rows = a.w_slice_rows;
+    p.res = nullptr;
     if (a.out_planes) ZK_REQUIRE(p.n_chunks * BN >= p.Np && a.Np % 64 == 0, "tc_gemm: internal padding error");
     if (a.slice_m) ZK_REQUIRE(a.slice_m % BM == 0, "tc_gemm: slice_m must be a multiple of %d", BM);
     const int64_t tiles = ceil_div(a.M, BM) * p.n_chunks;
