@@ -416,12 +416,6 @@ int zk_set_wide_min_hidden(int h);
  * CTA-pair kernel (two 128-row sub-tiles in flight per CTA: the MMAs of one overlap the epilogue of the
  * other); 0: the one-tile kernels as before.  Applies to handles created afterwards.  Returns the previous value. */
 int zk_set_dual_tiles(int on);
-/* Order in which the pair kernels issue the split-bf16 MMAs of one schedule entry (bench / test knob; returns the
- * previous value): 0 = per 16-column step hi*hi, hi*lo, lo*hi (the A operand alternates between tensor and shared
- * memory: +31 % pipe time per MMA, profiles/micro/mma_rate_pair.txt), 1 = all tensor-memory MMAs then all
- * shared-memory ones, 2 (default) = 1 with odd entries reversed.  Results differ in the last bits only (the fp32
- * accumulation order). */
-int zk_set_mma_order(int order);
 /* Profiling hook: a DEVICE buffer of >= 256 int64 that the fused layer kernel fills with clock64()
  * stamps of its pipeline events (CTA 0, third tile); NULL (default) disables it. */
 void zk_debug_timeline(long long* device_buffer);

@@ -107,7 +107,6 @@ _SIGNATURES = {
     "zk_set_fused_layers": (c_int, [c_int]),
     "zk_set_wide_min_hidden": (c_int, [c_int]),
     "zk_set_dual_tiles": (c_int, [c_int]),
-    "zk_set_mma_order": (c_int, [c_int]),
     "zk_debug_dual_schedule": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "zk_set_tc_backward": (c_int, [c_int]),
     "zk_debug_timeline": (None, [c_void_p]),

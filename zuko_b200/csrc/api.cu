@@ -56,7 +56,6 @@ int zk_set_fast_math(int on) { return g_fast_math.exchange(on ? 1 : 0); }
 int zk_set_fused_layers(int on) { return g_fused.exchange(on ? 1 : 0); }
 int zk_set_wide_min_hidden(int h) { return g_wide_min_h.exchange(h); }
 int zk_set_dual_tiles(int on) { return g_dual.exchange(on ? 1 : 0); }
-int zk_set_mma_order(int order) { return g_mma_order.exchange(order < 0 || order > 2 ? 2 : order); }
 static thread_local cudaStream_t g_pack_stream = nullptr;
 void zk_debug_timeline(long long* device_buffer) { zk::g_timeline = device_buffer; }
 int zk_debug_wide_schedule(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins,

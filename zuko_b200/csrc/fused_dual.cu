@@ -75,7 +75,6 @@ struct DualParams {
     int D, C;
     int n_last_chunks;
     int n_terms;
-    int mma_order;      // 0 interleaved, 1 TS block then SS block, 2 alternating per entry (g_mma_order)
     int M;
     int in_vec;
     int n_wstages;
@@ -212,49 +211,15 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                 tc_fence_after();
                 const int nk = 4 - (int)((cur >> 20) & 3u);
                 if (elect_one()) {
-// A from tensor memory ("TS": hi*hi, hi*lo-plane) and A from shared memory ("SS": lo*hi) do not mix
-                    // for free: the pipe runs either kind at 256 N / 512 cycles per MMA, but 83.7 instead of 64 cycles
-                    // (N = 128; 67.7 instead of 48 at N = 96) when every third MMA switches the A source
-                    // (profiles/micro/mma_rate_pair.txt).  So: all TS MMAs of the entry, then all SS ones
-                    // (mma_order 1), odd entries the other way round so that entry boundaries do not switch
-                    // either (2); 0 = the interleaved order of the first version.
-                    const bool ss_first = (p.mma_order == 2) && (i & 1);
-                    bool fresh = first;  // the chunk's first MMA overwrites the accumulator
-                    auto ts_block = [&]() {
 #pragma unroll
-                        for (int k = 0; k < DK / 16; ++k) {
-                            if (k >= nk) break;
-                            const uint32_t acol = (uint32_t)k * 8u;  // 16 bf16 = 8 TMEM columns
-                            umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, fresh ? 0u : 1u);
-                            fresh = false;
-                            if (p.n_terms == 3) umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
+                    for (int k = 0; k < DK / 16; ++k) {
+                        if (k >= nk) break;
+                        const uint32_t acol = (uint32_t)k * 8u;
+                        umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
+                        if (p.n_terms == 3) {
+                            umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
+                            umma2_bf16_ss(d_tmem, umma_desc_advance(da_lo, k), umma_desc_advance(dw_hi, k), idesc, 1u);
                         }
-                    };
-                    auto ss_block = [&]() {
-#pragma unroll
-                        for (int k = 0; k < DK / 16; ++k) {
-                            if (k >= nk) break;
-                            umma2_bf16_ss(d_tmem, umma_desc_advance(da_lo, k), umma_desc_advance(dw_hi, k), idesc, fresh ? 0u : 1u);
-                            fresh = false;
-                        }
-                    };
-                    if (p.mma_order == 0 || p.n_terms != 3) {
-#pragma unroll
-                        for (int k = 0; k < DK / 16; ++k) {
-                            if (k >= nk) break;
-                            const uint32_t acol = (uint32_t)k * 8u;
-                            umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_hi, k), idesc, (!first || k > 0) ? 1u : 0u);
-                            if (p.n_terms == 3) {
-                                umma2_bf16_ts(d_tmem, a_hi + acol, umma_desc_advance(dw_lo, k), idesc, 1u);
-                                umma2_bf16_ss(d_tmem, umma_desc_advance(da_lo, k), umma_desc_advance(dw_hi, k), idesc, 1u);
-                            }
-                        }
-                    } else if (ss_first) {
-                        ss_block();
-                        ts_block();
-                    } else {
-                        ts_block();
-                        ss_block();
                     }
                     umma2_commit_mc(&w_empty[ws]);
                     if (cur & DS_AFREE) umma2_commit_mc(&a_free[kb8]);
@@ -692,7 +657,6 @@ bool dual_dry_run(const std::vector<uint2>& items, const uint32_t* rd_mask, cons
 }  // namespace
 
 std::atomic<int> g_dual{1};  // zk_set_dual_tiles
-std::atomic<int> g_mma_order{2};
 
 static bool dual_dims_ok(const int* dims, int L, int univariate, int bins, int D, int C) {
     if (!g_dual.load()) return false;
@@ -875,7 +839,6 @@ zk_status launch_fused_dual(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
     p.D = a.D; p.C = a.C;
     p.n_last_chunks = (a.D + DPC - 1) / DPC;
     p.n_terms = pk->n_terms;
-    p.mma_order = g_mma_order.load();
     p.M = (int)a.B;
     p.x = a.x; p.ldx = a.ldx; p.c = a.c; p.ldc = a.ldc;
     p.y = a.y; p.ldy = a.ldy; p.ladj = a.ladj; p.accumulate = a.accumulate;

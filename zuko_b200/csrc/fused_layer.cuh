@@ -45,7 +45,6 @@ zk_status launch_fused_dual(const zk_mlp* m, const FusedLayerArgs& a, cudaStream
 int dual_schedule_host(int n_linear, const int* dims, const uint8_t* const* masks_host, int univariate, int bins, int D,
                        int C, uint32_t* out_items, int max_items, uint32_t* out_rd_mask, int* out_perm);
 extern std::atomic<int> g_dual;
-extern std::atomic<int> g_mma_order;  // zk_set_mma_order: issue order of TS / SS MMAs inside a schedule entry
 extern std::atomic<int> g_wide_min_h;
 extern uint32_t* g_watch_host;  // watchdog report buffer of the wide kernel (pinned host memory) or null
 zk_status fused_refresh(zk_mlp* m, cudaStream_t stream);  // weights changed in place: re-split into the fused packs
