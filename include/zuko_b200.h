@@ -402,7 +402,7 @@ int zk_set_tc_backward(int on);
 int zk_set_fast_math(int on);
 /* 1 (default): an autoregressive layer whose conditioner fits a fused kernel (hidden widths
  * equal; multiple of 64 and <= 256 with D + C <= 256, or 384 / 512 with D + C <= 512; RQS with
- * 8 / 16 bins or affine; tensor-core GEMM mode; ReLU, no residual blocks) runs as ONE kernel —
+ * 8 / 16 bins or affine; tensor-core GEMM mode; any supported activation, no residual blocks) runs as ONE kernel —
  * conditioner + bijector + ladj, activations and phi stay on chip (nn.py:217-218,
  * flows/autoregressive.py:207-215, transforms.py:554-567 in one launch).
  * 0: always one GEMM kernel per linear layer + the stand-alone bijector kernel.  Returns the

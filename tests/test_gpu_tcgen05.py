@@ -184,9 +184,14 @@ FUSED_FLOWS = {
     "nsf16c8_h256_silu": lambda: zuko.flows.NSF(16, 8, transforms=2, bins=8, hidden_features=[256] * 2, activation=torch.nn.SiLU),
     "nsf12_h256_tanh": lambda: zuko.flows.NSF(12, 0, transforms=2, bins=8, hidden_features=[256, 256], activation=torch.nn.Tanh),
     "maf24c4_h384_gelu": lambda: zuko.flows.MAF(24, 4, transforms=2, hidden_features=[384] * 2, activation=torch.nn.GELU),
+    # ---- ... and on the one-CTA-per-tile kernel (hidden width 64 - 192, the library's default widths) ----
+    "maf8_h64_tanh": lambda: zuko.flows.MAF(8, 0, transforms=2, activation=torch.nn.Tanh),
+    "nsf5c3_h192_elu": lambda: zuko.flows.NSF(5, 3, transforms=2, bins=8, hidden_features=[192, 192], activation=torch.nn.ELU),
+    "nsf20_k16_h64_silu": lambda: zuko.flows.NSF(20, 0, transforms=2, bins=16, activation=torch.nn.SiLU),
 }
 WIDE_FLOWS = ["maf32_h512x4", "nsf64c16_k16_h512", "nsf24_k8_h512", "nsf10c3_h384", "maf100c28_h512",
               "maf32_h512_elu", "nsf16c8_h256_silu", "nsf12_h256_tanh", "maf24c4_h384_gelu"]
+ONE_LAUNCH_FLOWS = WIDE_FLOWS + ["maf8_h64_tanh", "nsf5c3_h192_elu", "nsf20_k16_h64_silu"]
 
 
 @pytest.fixture
@@ -232,9 +237,10 @@ def test_fused_layer_matches_unfused_and_oracle(device, unfused, name, B):
     assert torch.allclose(ladj_f, ladj_u, rtol=2e-6, atol=2e-5)
 
 
-@pytest.mark.parametrize("name", WIDE_FLOWS)
+@pytest.mark.parametrize("name", ONE_LAUNCH_FLOWS)
 def test_wide_layers_run_as_one_kernel_each(device, name):
-    """Hidden width 384 / 512: ONE launch per flow layer (no per-layer GEMM fallback), and a ragged
+    """Hidden width 384 / 512, and non-ReLU conditioners of every fused width: ONE launch per flow layer (no
+    per-layer GEMM fallback), and a ragged
     batch (partial pair tile, odd number of tiles) gives the rows of the full batch bit for bit."""
     torch.manual_seed(5)
     flow = FUSED_FLOWS[name]().to(device)

@@ -42,6 +42,7 @@
 #include <utility>
 #include <vector>
 
+#include "activations.cuh"
 #include "fused_common.cuh"
 
 namespace zk {
@@ -81,6 +82,7 @@ struct FusedParams {
     int D, C;
     int n_last_chunks;  // ceil(D / DPC)
     int n_terms;        // 3 (split bf16) or 1
+    int act;            // hidden activation: 1 ReLU, else ZK_ACT_* (GACT instantiation)
     int M;
     int in_tma;         // 1: x / c rows are staged through shared memory by 1-D TMA bulk copies
     int n_wstages;      // depth of the W ring (32 KB per stage)
@@ -104,7 +106,7 @@ struct FusedParams {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <int UNI, int KT, bool FAST, bool DBG>
+template <int UNI, int KT, bool FAST, bool DBG, bool GACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 fused_layer_kernel(const __grid_constant__ FusedParams p) {
     using Cfg = LastCfg<UNI, KT>;
@@ -419,6 +421,18 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                             uint32_t ra[16];
                             tmem_ld_x16(t_lane + TM_D + buf * 128u + (uint32_t)(col0 + 16 * half), ra);
                             tmem_ld_wait();
+                            if constexpr (GACT) {  // any ZK_ACT_* (nn.py:264-265): one switch per 16 columns
+                                float v[16];
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 bb = b4[4 * half + (j >> 2)];
+                                    v[j] = __uint_as_float(ra[j]) + bb.x; v[j + 1] = __uint_as_float(ra[j + 1]) + bb.y;
+                                    v[j + 2] = __uint_as_float(ra[j + 2]) + bb.z; v[j + 3] = __uint_as_float(ra[j + 3]) + bb.w;
+                                }
+                                if constexpr (FAST) act_apply_n_fast<16>(v, p.act); else act_apply_n<16>(v, p.act);
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], ph[8 * half + (j >> 1)], pl[8 * half + (j >> 1)]);
+                            } else {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 bb = b4[4 * half + (j >> 2)];  // one broadcast 16-byte load per 4 columns
@@ -426,6 +440,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
                                             ph[8 * half + (j >> 1)], pl[8 * half + (j >> 1)]);
                                 split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
                                             ph[8 * half + (j >> 1) + 1], pl[8 * half + (j >> 1) + 1]);
+                            }
                             }
                         }
                     }
@@ -598,9 +613,10 @@ zk_status launch_fused_t(const FusedParams& p, bool fast, int grid, size_t smem,
         kern<<<grid, F_THREADS, smem, st>>>(p);
         return check_launch("fused_layer_kernel");
     };
-    if (p.dbg != nullptr) return fast ? go(fused_layer_kernel<UNI, KT, true, true>) : go(fused_layer_kernel<UNI, KT, false, true>);
-    if (fast) return go(fused_layer_kernel<UNI, KT, true, false>);
-    return go(fused_layer_kernel<UNI, KT, false, false>);
+    if (p.act > 1) return fast ? go(fused_layer_kernel<UNI, KT, true, false, true>) : go(fused_layer_kernel<UNI, KT, false, false, true>);
+    if (p.dbg != nullptr) return fast ? go(fused_layer_kernel<UNI, KT, true, true, false>) : go(fused_layer_kernel<UNI, KT, false, true, false>);
+    if (fast) return go(fused_layer_kernel<UNI, KT, true, false, false>);
+    return go(fused_layer_kernel<UNI, KT, false, false, false>);
 }
 
 }  // namespace
@@ -610,7 +626,7 @@ long long* g_timeline = nullptr;
 static bool fused_narrow_shape(const zk_mlp* m, int univariate, int bins, int D, int C) {
     const TcPack* pk = (const TcPack*)m->tc;
     if (!pk || m->gemm_mode == ZK_GEMM_FP32) return false;
-    if (m->act != 1 || !m->plain) return false;  // the hidden epilogue implements ReLU MLPs only
+    if (m->act < 1 || !m->plain) return false;  // plain MLPs only (residual blocks need the input of two layers back)
     if (m->n_linear < 2 || m->n_linear > ZK_FUSED_MAX_LINEAR) return false;
     const int H = m->dims[1];
     if (H % 64 != 0 || H < 64 || H > 256) return false;
@@ -900,6 +916,7 @@ zk_status launch_fused_layer(const zk_mlp* m, const FusedLayerArgs& a, cudaStrea
     p.CW = (p.H % 128 == 0) ? 128 : 64;
     p.D = a.D; p.C = a.C;
     p.n_terms = pk->n_terms;
+    p.act = m->act;
     p.M = (int)a.B;
     p.x = a.x; p.ldx = a.ldx; p.c = a.c; p.ldc = a.ldc;
     p.y = a.y; p.ldy = a.ldy; p.ladj = a.ladj; p.accumulate = a.accumulate;
