@@ -312,13 +312,16 @@ def build_config_model(cfg):
 
 
 def tensor_peak(peaks: dict, clocks: dict) -> tuple[float, str]:
-    """Burst peak when the run held the maximum SM clock without a power cap (a kernel-bound step of
-    milliseconds), else the sustained figure (MEASURED_PEAKS.json holds both)."""
+    """The denominator of a tensor-bound roofline: the measured cuBLAS burst figure (taken at the maximum SM clock) when
+    the run held >= 98 % of that clock, else the same figure scaled to the clock the run actually held — the pipe's
+    capacity under the power cap the timed region saw.  (MEASURED_PEAKS.json's own "sustained" figure was taken at one
+    particular capped clock, 1305 MHz in round 1: dividing a run at 1935 MHz by it flatters, a run at 1680 MHz reads
+    above 1.  It is reported next to the fraction as `peak_sustained`.)"""
     sm, smax = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
-    capped = "sw_power_cap" in (clocks.get("reasons") or [])
-    if sm and smax and sm >= 0.98 * smax and not capped:
-        return peaks["bf16_tflops"], "burst"
-    return peaks["bf16_tflops_sustained"], "sustained"
+    burst = peaks["bf16_tflops"]
+    if not sm or not smax or sm >= 0.98 * smax:
+        return burst, "burst"
+    return burst * sm / smax, f"burst x {sm / smax:.3f} (SM clock held {sm:.0f} of {smax:.0f} MHz)"
 
 
 def fused_info(flow) -> dict:
@@ -415,7 +418,7 @@ def time_config(cfg, dev, rank, world, peaks, steps, nvml=None) -> dict:
         out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "peak_kind": kind,
                            "kernel": info["kernel"], "algorithmic_flops_per_step": flops, "issued_flops_per_step": 2.0 * info["issued_macs_per_row"] * rows,
                            "frac_issued": 2.0 * info["issued_macs_per_row"] * rows / (ms_per_step * 1e-3) / 1e12 / peak,
-                           "traffic": None, "algorithmic_hbm_bytes": 4.0 * (D + C + 1) * rows}  # fmt: skip
+                           "traffic": None, "algorithmic_hbm_bytes": 4.0 * (D + C + 1) * rows, "peak_sustained": peaks["bf16_tflops_sustained"]}  # fmt: skip
         tj = ncu_traffic().get(f"{cfg['name']}_layer")
         if tj:  # one `ncu --set full` capture of ONE flow layer launch of this config (bytes, and the rows that launch covered)
             out["roofline"]["traffic"] = tj.get("bytes")
@@ -566,6 +569,8 @@ def run_ours(args) -> None:
                 roofline["kernel"] = dom["name"]
                 roofline["peak_source"] = peaks["source"]
                 roofline["peak_kind"] = dom.get("peak_kind")
+                if dom.get("bound") == "tensor":
+                    roofline["peak_sustained"] = peaks["bf16_tflops_sustained"]
                 roofline["traffic_captured_at"] = dom.get("traffic_captured_at")
             except Exception as e:  # noqa: BLE001
                 kernels, roofline = [], {"error": f"{type(e).__name__}: {e}"[:300]}
