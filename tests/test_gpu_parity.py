@@ -388,6 +388,70 @@ def test_host_buffer_entry_point_growing_chunks(device):
     assert abs(tot2.value - total) < 1e-9 * abs(total)
 
 
+def test_permutations_fold_into_autoregressive_layers(device):
+    """A classic MAF stack with explicit PermutationTransform members (zuko/transforms.py:1193-1214 between
+    flows/autoregressive.py layers): when no gradient is needed, the permutations are folded into re-indexed
+    layer handles (ComposedTransform._folded) — fewer launches, same bijection: log_prob / z / inverse against the
+    fp64 oracle and against the member-by-member engine call that the autograd path takes."""
+    from functools import partial
+
+    from zuko_b200.flows import MaskedAutoregressiveTransform
+    from zuko_b200.lazy import Flow, UnconditionalDistribution, UnconditionalTransform
+    from zuko_b200.transforms import MonotonicRQSTransform
+
+    D, C = 6, 2
+    torch.manual_seed(31)
+    layers = [
+        MaskedAutoregressiveTransform(D, C, hidden_features=[64, 64]),
+        UnconditionalTransform(PermutationTransform, torch.arange(D).flip(0), buffer=True),
+        MaskedAutoregressiveTransform(D, C, univariate=partial(MonotonicRQSTransform, slope=1e-3),
+                                      shapes=[(8,), (8,), (7,)], hidden_features=[64, 64]),  # fmt: skip
+        UnconditionalTransform(SoftclipTransform, bound=9.0),
+        UnconditionalTransform(PermutationTransform, torch.randperm(D), buffer=True),
+        MaskedAutoregressiveTransform(D, C, hidden_features=[32], order=torch.randperm(D)),
+        UnconditionalTransform(PermutationTransform, torch.randperm(D), buffer=True),
+    ]
+    base = UnconditionalDistribution(zuko.distributions.DiagNormal, torch.linspace(-0.5, 0.5, D), torch.linspace(0.7, 1.6, D), buffer=True)
+    flow_cpu = Flow(layers, base).eval()
+    spec = O.flowspec_from_module(flow_cpu)
+    gen = torch.Generator().manual_seed(5)
+    x, c = torch.randn(3000, D, generator=gen), torch.randn(3000, C, generator=gen)
+    ref_lp = spec.log_prob(x.numpy(), c.numpy())
+    flow = flow_cpu.to(device)
+    xd, cd = x.to(device), c.to(device)
+    L = E.lib()
+    with torch.no_grad():
+        dist = flow(cd)
+        fc = dist._flow_call()[0]
+        assert fc.folded is not None and len(fc.folded._handles) < len(fc._handles) == 7
+        lp = dist.log_prob(xd)  # packs the re-indexed handles
+        n0 = L.zk_launch_count()
+        lp = dist.log_prob(xd)
+        n_folded = L.zk_launch_count() - n0
+        z, ladj = dist.transform.call_and_ladj(xd)
+        x_back = dist.transform.inv(z)
+    lp_reg = flow(cd).log_prob(xd)  # parameters require grad: the member-by-member call with the autograd seam
+    assert lp_reg.requires_grad
+    with torch.no_grad():
+        prev_best = type(fc).best
+        try:  # the unfolded call, forward-only, for the launch count
+            type(fc).best = lambda self, x, c: self
+            flow(cd).log_prob(xd)
+            n0 = L.zk_launch_count()
+            flow(cd).log_prob(xd)
+            n_plain = L.zk_launch_count() - n0
+            z_reg, ladj_reg = flow(cd).transform.call_and_ladj(xd)
+        finally:
+            type(fc).best = prev_best
+    assert n_folded < n_plain
+    assert rel_err(cpu(lp), ref_lp) < 1e-5 and rel_err(cpu(lp_reg.detach()), ref_lp) < 1e-5
+    assert torch.allclose(lp, lp_reg.detach(), rtol=1e-5, atol=2e-5)
+    assert torch.allclose(z, z_reg, rtol=1e-5, atol=1e-5) and torch.allclose(ladj, ladj_reg, rtol=1e-5, atol=2e-5)
+    assert (x_back - xd).abs().max().item() < 1e-4
+    (-lp_reg.mean()).backward()  # the autograd path is untouched by the fold
+    assert all(p.grad is not None for p in flow.parameters())
+
+
 def test_circular_shift_and_box_uniform(device):
     """CircularShiftTransform (transforms.py:319-351) and BoxUniform.log_prob (distributions.py:366-396)
     against the reference's golden vectors: the shift is bit-exact in fp32."""

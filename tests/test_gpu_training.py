@@ -179,3 +179,26 @@ def test_engine_calls_on_two_streams_do_not_share_scratch(device):
         torch.cuda.synchronize()
     assert all(torch.equal(o, ref) for o in outs)
     assert np.isfinite(b.cpu().numpy()).all()
+
+
+def test_fast_and_ieee_bijector_gradients_agree(device):
+    """zk_set_fast_math switches the RQS backward pair math between MUFU reciprocal / ex2 and IEEE division / expf
+    (bijector_grad.cuh); both are held to the reference's gradients elsewhere — here: they agree with each other
+    far inside that bar."""
+    torch.manual_seed(14)
+    flow = zuko.flows.NSF(6, 2, transforms=2, bins=8, hidden_features=[64, 64]).to(device)
+    x = torch.randn(4096, 6, device=device)
+    c = torch.randn(4096, 2, device=device)
+    grads = {}
+    for fast in (1, 0):
+        prev = E.lib().zk_set_fast_math(fast)
+        try:
+            for p in flow.parameters():
+                p.grad = None
+            (-flow(c).log_prob(x).mean()).backward()
+            grads[fast] = [p.grad.detach().clone() for p in flow.parameters()]
+        finally:
+            E.lib().zk_set_fast_math(prev)
+    for a, b in zip(grads[1], grads[0]):
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() < 1e-5 * scale

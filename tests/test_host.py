@@ -222,3 +222,48 @@ def test_host_pipeline_chunk_plan():
     p = plan(1 << 20, cap=200000)
     assert sum(p) == 1 << 20 and max(p) <= 200000 and p[0] == wave
     assert sum(plan(1 << 20, cap=1000)) == 1 << 20 and max(plan(1 << 20, cap=1000)) <= 1000
+
+
+@pytest.mark.parametrize("rqs", [False, True])
+def test_folding_a_permutation_into_an_autoregressive_layer(rqs):
+    """The algebra behind ComposedTransform._folded, on the CPU with the oracle: for (P x)_j = x[q[j]] and the layer
+    T~ re-indexed by flows.autoregressive.reindex_conditioner (+ order~[q] = order),  T(P x) = P T~(x) with equal
+    ladj — for the forward and the inverse direction."""
+    import copy
+    from functools import partial
+
+    import numpy as np
+
+    from oracle import oracle as O
+    from zuko_b200.flows import MaskedAutoregressiveTransform
+    from zuko_b200.flows.autoregressive import reindex_conditioner
+    from zuko_b200.lazy import Flow, UnconditionalDistribution
+    from zuko_b200.transforms import MonotonicRQSTransform
+
+    D, C = 6, 2
+    torch.manual_seed(17)
+    kw = dict(univariate=partial(MonotonicRQSTransform, slope=1e-3), shapes=[(4,), (4,), (3,)]) if rqs else {}
+    t = MaskedAutoregressiveTransform(D, C, hidden_features=[16, 16], order=torch.randperm(D), **kw)
+    q = torch.randperm(D)
+    t2 = copy.deepcopy(t)
+    lins, lins2 = t.hyper._linears(), t2.hyper._linears()
+    with torch.no_grad():
+        for i, (a, b) in enumerate(zip(lins, lins2)):
+            w, bias, mask = reindex_conditioner(i, len(lins), a.weight.detach(), a.bias.detach(), a.mask, qi=q, D=D, P=t.total)
+            b.weight.copy_(w)
+            b.bias.copy_(bias)
+            b.mask = mask
+        ro = torch.empty_like(t.order)
+        ro[q] = t.order
+        t2.order = ro
+    base = lambda: UnconditionalDistribution(zuko.distributions.DiagNormal, torch.zeros(D), torch.ones(D), buffer=True)  # noqa: E731
+    s1, s2 = O.flowspec_from_module(Flow([t], base()).eval()), O.flowspec_from_module(Flow([t2], base()).eval())
+    g = np.random.default_rng(0)
+    x, c = g.standard_normal((64, D)), g.standard_normal((64, C))
+    qn = q.numpy()
+    y1, l1 = s1.forward(x[:, qn], c)      # T(P x)
+    y2, l2 = s2.forward(x, c)             # T~(x)
+    assert np.allclose(y1, y2[:, qn], rtol=1e-12, atol=1e-12) and np.allclose(l1, l2, rtol=1e-12, atol=1e-12)
+    # inverse: T^-1(P z) = P T~^-1(z)
+    z = g.standard_normal((64, D)) * 0.5
+    assert np.allclose(s1.inverse(z[:, qn], c), s2.inverse(z, c)[:, qn], rtol=1e-9, atol=1e-9)

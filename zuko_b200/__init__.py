@@ -27,5 +27,5 @@ def invalidate(module) -> None:
     for m in mods:
         if hasattr(m, "_release"):  # conditioner used on its own: it owns (and destroys) its zk_mlp handle
             m._release()
-        for key in ("_zk_cache", "_built"):
+        for key in ("_zk_cache", "_zk_reindexed", "_built"):
             m.__dict__.pop(key, None)

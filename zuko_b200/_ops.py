@@ -221,6 +221,20 @@ class FlowCall:
         return (x2.requires_grad or (c2 is not None and c2.requires_grad) or any(p.requires_grad for p in self._params)
                 or bool(self._base_src))  # fmt: skip
 
+    folded = None  # the same bijection with permutations folded into the autoregressive layers (forward-only), or None
+
+    def _needs_grad(self, x: Tensor, c: Tensor | None) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return (x.requires_grad or (c is not None and c.requires_grad) or any(p.requires_grad for p in self._params)
+                or bool(self._base_src))  # fmt: skip
+
+    def best(self, x: Tensor, c: Tensor | None) -> "FlowCall":
+        """The permutation-folded sibling when the call does not have to be differentiable, else this call."""
+        if self.folded is not None and not self._needs_grad(x, c):
+            return self.folded
+        return self
+
     def usable(self, x: Tensor, c: Tensor | None, inverse_log_prob: bool = False) -> bool:
         """False when this call must go to the unfused chain instead: a flow with inverted members
         (LazyInverse) is forward-only in the engine — no autograd seam, no fused log-density of samples."""

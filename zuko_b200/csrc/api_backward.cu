@@ -311,6 +311,7 @@ zk_status layer_backward_impl(const zk_layer* l, const float* x, int64_t ldx, co
     Arena ar(ws, ws_bytes);
     UniBwdArgs u;
     u.univariate = l->uni; u.B = B; u.K = l->K; u.bound = l->bound; u.slope = l->slope; u.circular = l->circ;
+    u.fast_math = g_fast_math.load() != 0;
     u.x = x; u.ldx = ldx; u.gy = gy; u.ldgy = ldgy; u.gl = gl; u.gx = gx; u.ldgx = ldgx;
     switch (l->kind) {
         case ZK_LAYER_AUTOREGRESSIVE:
@@ -615,6 +616,7 @@ zk_status uni_backward_entry(int uni, const float* x, int64_t ldx, const float* 
     const int P = (uni == ZK_UNI_RQS) ? 3 * K - 1 : 2;
     UniBwdArgs u;
     u.univariate = uni; u.K = K; u.bound = bound; u.slope = slope; u.D = D;
+    u.fast_math = g_fast_math.load() != 0;
     u.phi = phi; u.phi_ld = phi_ld;
     if (phi_ld != 0 || gphi == nullptr) {
         u.x = x; u.ldx = ldx; u.gy = gy; u.ldgy = ldgy; u.gl = gl; u.gx = gx; u.ldgx = ldgx; u.gphi = gphi; u.B = B;

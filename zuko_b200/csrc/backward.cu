@@ -40,7 +40,7 @@ __device__ __forceinline__ float circ_shift_b(float x, float bound) {  // biject
 // thread = (sample row, dim) pair; the tile's parameter block is staged in shared memory, every
 // pair rewrites its P slots with the parameter gradients, and the tile is written back with
 // coalesced stores (per-sample gradients (B, D*P); a shared table is reduced by the caller).
-template <int UNI, int KT>
+template <int UNI, int KT, bool FAST>
 __global__ void __launch_bounds__(kBwdThreads) uni_bwd_kernel(const UniBwdParams a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kBwdThreads) uni_bwd_kernel(const UniBwdParams
         float* out = s_out + p * P;
         float gxv;
         if constexpr (UNI == ZK_UNI_RQS) {
-            bijgrad::rqs_backward_pair<KT>(pp, a.K, xv, gyv, glv, a.bound, a.aw, a.ad, gxv, out);
+            bijgrad::rqs_backward_pair<KT, FAST>(pp, a.K, xv, gyv, glv, a.bound, a.aw, a.ad, gxv, out);
         } else {
             bijgrad::affine_backward_pair(pp, xv, gyv, glv, a.ad, gxv, out);
         }
@@ -296,12 +296,15 @@ int wgrad_slices_max(int N, int K) {
 }
 
 template <int UNI, int KT>
-zk_status launch_uni_bwd_t(const UniBwdParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = uni_bwd_kernel<UNI, KT>;
-    if (smem > 40 * 1024)
-        ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kBwdThreads, smem, st>>>(p);
-    return check_launch("uni_bwd_kernel");
+zk_status launch_uni_bwd_t(const UniBwdParams& p, bool fast, int grid, size_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> zk_status {
+        if (smem > 40 * 1024)
+            ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kBwdThreads, smem, st>>>(p);
+        return check_launch("uni_bwd_kernel");
+    };
+    if (fast && UNI == ZK_UNI_RQS) return go(uni_bwd_kernel<UNI, KT, true>);  // affine: one expf per pair, not worth a variant
+    return go(uni_bwd_kernel<UNI, KT, false>);
 }
 
 }  // namespace
@@ -340,11 +343,11 @@ zk_status launch_univariate_backward(const UniBwdArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)R * row_bytes + table;
     const int64_t grid = ceil_div(a.B, R);
     ZK_REQUIRE(grid <= 0x7fffffff, "univariate backward: batch too large for one launch");
-    if (a.univariate == ZK_UNI_AFFINE) return launch_uni_bwd_t<ZK_UNI_AFFINE, 0>(p, (int)grid, smem, stream);
+    if (a.univariate == ZK_UNI_AFFINE) return launch_uni_bwd_t<ZK_UNI_AFFINE, 0>(p, a.fast_math, (int)grid, smem, stream);
     switch (a.K) {
-        case 8: return launch_uni_bwd_t<ZK_UNI_RQS, 8>(p, (int)grid, smem, stream);
-        case 16: return launch_uni_bwd_t<ZK_UNI_RQS, 16>(p, (int)grid, smem, stream);
-        default: return launch_uni_bwd_t<ZK_UNI_RQS, 0>(p, (int)grid, smem, stream);
+        case 8: return launch_uni_bwd_t<ZK_UNI_RQS, 8>(p, a.fast_math, (int)grid, smem, stream);
+        case 16: return launch_uni_bwd_t<ZK_UNI_RQS, 16>(p, a.fast_math, (int)grid, smem, stream);
+        default: return launch_uni_bwd_t<ZK_UNI_RQS, 0>(p, a.fast_math, (int)grid, smem, stream);
     }
 }
 

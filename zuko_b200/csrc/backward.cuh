@@ -32,6 +32,7 @@ struct UniBwdArgs {
     int D = 0, K = 0;
     float bound = 5.f, slope = 1e-3f;
     bool circular = false;  // RQS: CircularShiftTransform(bound) in front (d shift / dx = 1)
+    bool fast_math = false; // MUFU reciprocal / ex2 in the RQS pair math (zk_set_fast_math)
 };
 zk_status launch_univariate_backward(const UniBwdArgs& a, cudaStream_t stream);
 

@@ -33,9 +33,35 @@ ZK_HD float dsc(float v, float a) {
     return 1.0f / (d * d);
 }
 
+// FAST = true (device only, zk_set_fast_math(1)): MUFU reciprocal / ex2 instead of IEEE division / expf — the
+// same approximations the forward kernels use (bijector_math.cuh); ~1e-6 relative on values bounded by the soft
+// clip, against a 5e-5 bar on the gradients.  Host builds (tests/native) always take the IEEE forms.
+template <bool FAST>
+ZK_HD float rcp_(float v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (FAST) return __fdividef(1.0f, v);
+#endif
+    return 1.0f / v;
+}
+template <bool FAST>
+ZK_HD float div_(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (FAST) return __fdividef(a, b);
+#endif
+    return a / b;
+}
+template <bool FAST>
+ZK_HD float exp_(float v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (FAST) return __expf(v);
+#endif
+    return expf(v);
+}
+
 // soft clip u = v / (1 + |v| a) and its derivative d = 1 / (1 + |v| a)^2 from ONE reciprocal
+template <bool FAST = false>
 ZK_HD void sc_parts(float v, float a, float& u, float& d) {
-    const float r = 1.0f / fmaf(fabsf(v), a, 1.0f);
+    const float r = rcp_<FAST>(fmaf(fabsf(v), a, 1.0f));
     u = v * r;
     d = r * r;
 }
@@ -51,7 +77,7 @@ ZK_HD void sc_parts(float v, float a, float& u, float& d) {
 // 2^18 x 16 pairs); the code path is kept for reference, both give bit-identical results.
 constexpr bool kCacheNumerators = false;
 
-template <int KT_>
+template <int KT_, bool FAST = false>
 ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float gl, float bound,
                              float aw, float ad, float& gx, float* gp) {
     constexpr int KT = kCacheNumerators ? KT_ : 0;  // 0 = recompute path
@@ -62,17 +88,17 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     float sw = 0.f, sh = 0.f;
     for (int k = 0; k < K; ++k) {
         float u0, d0_, u1, d1_;
-        sc_parts(p[k], aw, u0, d0_);
-        sc_parts(p[K + k], aw, u1, d1_);
-        const float e0 = expf(u0), e1 = expf(u1);
+        sc_parts<FAST>(p[k], aw, u0, d0_);
+        sc_parts<FAST>(p[K + k], aw, u1, d1_);
+        const float e0 = exp_<FAST>(u0), e1 = exp_<FAST>(u1);
         if constexpr (KT > 0) {
             ew[k] = e0; eh[k] = e1; dw[k] = d0_; dh[k] = d1_;
         }
         sw += e0;
         sh += e1;
     }
-    const float gxs = 2.f * bound / sw;  // numerator -> width
-    const float gys = 2.f * bound / sh;
+    const float gxs = div_<FAST>(2.f * bound, sw);  // numerator -> width
+    const float gys = div_<FAST>(2.f * bound, sh);
     // bin search on the horizontal knots (strict <, transforms.py:521-523)
     float cw = 0.f, ch = 0.f, xl = -bound, yl = -bound;
     int kb = 0;
@@ -84,10 +110,10 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
             e1 = eh[j];
         } else {
             float u, d;
-            sc_parts(p[j], aw, u, d);
-            e0 = expf(u);
-            sc_parts(p[K + j], aw, u, d);
-            e1 = expf(u);
+            sc_parts<FAST>(p[j], aw, u, d);
+            e0 = exp_<FAST>(u);
+            sc_parts<FAST>(p[K + j], aw, u, d);
+            e1 = exp_<FAST>(u);
         }
         const bool take = (j == 0) || (xl < x);
         if (take) {
@@ -106,11 +132,11 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     }
     const float dx = ewk * gxs, dy = ehk * gys;
     float ur0 = 0.f, dr0 = 0.f, ur1 = 0.f, dr1 = 0.f;  // soft-clipped derivatives of the bin's two knots
-    if (kb > 0) sc_parts(p[2 * K + kb - 1], ad, ur0, dr0);
-    if (kb < K - 1) sc_parts(p[2 * K + kb], ad, ur1, dr1);
-    const float d0 = (kb > 0) ? expf(ur0) : 1.f;  // pad (1, 1) with 0 -> exp(0) = 1
-    const float d1 = (kb < K - 1) ? expf(ur1) : 1.f;
-    const float rdx = 1.f / dx;
+    if (kb > 0) sc_parts<FAST>(p[2 * K + kb - 1], ad, ur0, dr0);
+    if (kb < K - 1) sc_parts<FAST>(p[2 * K + kb], ad, ur1, dr1);
+    const float d0 = (kb > 0) ? exp_<FAST>(ur0) : 1.f;  // pad (1, 1) with 0 -> exp(0) = 1
+    const float d1 = (kb < K - 1) ? exp_<FAST>(ur1) : 1.f;
+    const float rdx = rcp_<FAST>(dx);
     const float s = dy * rdx;
     const float z = (x - x0) * rdx;
     const float omz = 1.f - z;
@@ -119,14 +145,14 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     const float num = fmaf(s * z, z, d0 * q);
     const float den = fmaf(t, q, s);
     const float m = 2.f * s * q + d0 * omz * omz + d1 * z * z;
-    const float rden = 1.f / den, rm = 1.f / m;
+    const float rden = rcp_<FAST>(den), rm = rcp_<FAST>(m);
     const float rden2 = rden * rden;
     // y = y0 + dy num / den,  ladj = 2 log s + log m - 2 log den
     const float dy_dz = dy * s * m * rden2;  // (num_z den - num den_z) = s m
     const float dy_ds = dy * (z * z * den - num * (1.f - 2.f * q)) * rden2;
     const float dy_dd0 = dy * q * (den - num) * rden2;
     const float dy_dd1 = -dy * num * q * rden2;
-    const float dl_ds = 2.f / s + 2.f * q * rm - 2.f * (1.f - 2.f * q) * rden;
+    const float dl_ds = div_<FAST>(2.f, s) + 2.f * q * rm - 2.f * (1.f - 2.f * q) * rden;
     const float dl_dz = (2.f * s * (1.f - 2.f * z) - 2.f * d0 * omz + 2.f * d1 * z) * rm -
                         2.f * t * (1.f - 2.f * z) * rden;
     const float dl_dd0 = omz * omz * rm - 2.f * q * rden;
@@ -141,8 +167,8 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
     const float Gx0 = -Gz * rdx;
     const float Gy0 = gy;
     // sum_j W_j dL/dW_j, divided by 2B
-    const float dotw = (Gx0 * (cwk * gxs) + Gdx * dx) / (2.f * bound);
-    const float doth = (Gy0 * (chk * gys) + Gdy * dy) / (2.f * bound);
+    const float dotw = div_<FAST>(Gx0 * (cwk * gxs) + Gdx * dx, 2.f * bound);
+    const float doth = div_<FAST>(Gy0 * (chk * gys) + Gdy * dy, 2.f * bound);
     const float gd0 = Gd0 * d0 * dr0, gd1 = Gd1 * d1 * dr1;  // gradients of the two raw derivative parameters
     for (int i = 0; i < K; ++i) {
         float e0, e1, c0, c1;
@@ -150,10 +176,10 @@ ZK_HD void rqs_backward_pair(const float* p, int Krt, float x, float gy, float g
             e0 = ew[i]; e1 = eh[i]; c0 = dw[i]; c1 = dh[i];
         } else {
             float u;
-            sc_parts(p[i], aw, u, c0);
-            e0 = expf(u);
-            sc_parts(p[K + i], aw, u, c1);
-            e1 = expf(u);
+            sc_parts<FAST>(p[i], aw, u, c0);
+            e0 = exp_<FAST>(u);
+            sc_parts<FAST>(p[K + i], aw, u, c1);
+            e1 = exp_<FAST>(u);
         }
         const float selw = (i < kb ? Gx0 : 0.f) + (i == kb ? Gdx : 0.f);
         const float selh = (i < kb ? Gy0 : 0.f) + (i == kb ? Gdy : 0.f);

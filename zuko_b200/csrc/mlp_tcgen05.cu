@@ -611,13 +611,31 @@ colsum_planes_stage1(const __nv_bfloat16* planes, int64_t M, int Np, int N, int6
     const uint16_t* hi = reinterpret_cast<const uint16_t*>(planes);
     const uint16_t* lo = hi + M * (int64_t)Np;
     float a0 = 0.f, a1 = 0.f;
-    if (col < Np)
-        for (int64_t r = lo_r + ty; r < hi_r; r += 8) {
+    if (col < Np) {
+        // eight rows (16 independent 32-bit loads) in flight per thread: the kernel is bound by load latency, and
+        // the running sums keep the row order of the one-row-at-a-time loop (bit-identical results)
+        constexpr int U = 8;
+        int64_t r = lo_r + ty;
+        for (; r + 8 * (U - 1) < hi_r; r += 8 * U) {
+            uint32_t h[U], l[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                h[u] = *reinterpret_cast<const uint32_t*>(hi + (r + 8 * u) * Np + col);
+                l[u] = *reinterpret_cast<const uint32_t*>(lo + (r + 8 * u) * Np + col);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a0 += __uint_as_float(h[u] << 16) + __uint_as_float(l[u] << 16);
+                a1 += __uint_as_float(h[u] & 0xffff0000u) + __uint_as_float(l[u] & 0xffff0000u);
+            }
+        }
+        for (; r < hi_r; r += 8) {
             const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + r * Np + col);
             const uint32_t l = *reinterpret_cast<const uint32_t*>(lo + r * Np + col);
             a0 += __uint_as_float(h << 16) + __uint_as_float(l << 16);
             a1 += __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
         }
+    }
     sm[ty][2 * tx] = a0;
     sm[ty][2 * tx + 1] = a1;
     __syncthreads();

@@ -216,9 +216,13 @@ class NormalizingFlow(Distribution):
             fused = t._fused(first.shape[0])
             if fused is not None:
                 call, ctx = fused
+                kind = E.ZK_BASE_BOX_UNIFORM if box else E.ZK_BASE_DIAG_NORMAL
                 fc = (_ops.FlowCall(call._handles, call.D, call.C, first, second, sources=call._sources, keep=call._keep,
-                                    base_kind=E.ZK_BASE_BOX_UNIFORM if box else E.ZK_BASE_DIAG_NORMAL,
-                                    inverted=call._inverted), ctx)  # fmt: skip
+                                    base_kind=kind, inverted=call._inverted), ctx)  # fmt: skip
+                if call.folded is not None:  # permutations folded into the layers: forward-only sibling, same base
+                    f = call.folded
+                    fc[0].folded = _ops.FlowCall(f._handles, f.D, f.C, first.detach(), second.detach(), sources=None,
+                                                 keep=f._keep, base_kind=kind, inverted=f._inverted)  # fmt: skip
         self.__dict__["_fc"] = fc
         return fc
 
@@ -226,7 +230,7 @@ class NormalizingFlow(Distribution):
         fc = self._flow_call()
         if fc is not None and fc[0].usable(x, fc[1]):
             call, ctx = fc
-            lp = call.log_prob(x, ctx)
+            lp = call.best(x, ctx).log_prob(x, ctx)
             return lp.expand(torch.broadcast_shapes(lp.shape, self.batch_shape)) if self.batch_shape else lp
         z, ladj = self.transform.call_and_ladj(x)
         if self.reinterpreted:
@@ -246,14 +250,14 @@ class NormalizingFlow(Distribution):
                 total = sum_out
             return lp, total
         call, ctx = fc
-        return call.log_prob(x, ctx, with_sum=True, sum_out=sum_out)
+        return call.best(x, ctx).log_prob(x, ctx, with_sum=True, sum_out=sum_out)
 
     def rsample(self, shape: Size = ()) -> Tensor:
         z = self.base.rsample(shape) if self.base.has_rsample else self.base.sample(shape)
         fc = self._flow_call()
         if fc is not None and fc[0].usable(z, fc[1]):
             call, ctx = fc
-            return call.inverse(z, ctx)
+            return call.best(z, ctx).inverse(z, ctx)
         return self.transform.inv(z)
 
     def sample(self, shape: Size = ()) -> Tensor:
@@ -265,7 +269,7 @@ class NormalizingFlow(Distribution):
         fc = self._flow_call()
         if fc is not None and fc[0].usable(z, fc[1], inverse_log_prob=True):
             call, ctx = fc
-            return call.inverse(z, ctx, with_log_prob=True)
+            return call.best(z, ctx).inverse(z, ctx, with_log_prob=True)
         x, ladj = self.transform.inv.call_and_ladj(z)
         if self.reinterpreted:
             ladj = ladj.sum(dim=tuple(range(-self.reinterpreted, 0)))

@@ -165,6 +165,7 @@ class PackedLayerMixin:
 
     def _zk_release(self) -> None:
         self.__dict__.pop("_zk_cache", None)  # the handle is destroyed with its last reference
+        self.__dict__.pop("_zk_reindexed", None)
 
     def _grad_source(self) -> dict:
         """Tensors the engine's parameter gradients of this layer belong to (see _ops.FlowCall)."""
@@ -186,6 +187,7 @@ class PackedLayerMixin:
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_zk_cache", None)
+        state.pop("_zk_reindexed", None)
         return state
 
     def _base_desc(self, kind: int) -> E.LayerDesc:

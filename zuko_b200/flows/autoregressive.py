@@ -13,6 +13,8 @@ __all__ = ["MAF", "MaskedAutoregressiveTransform"]
 from collections.abc import Callable, Sequence
 from math import ceil
 
+from functools import partial
+
 import torch
 from torch import BoolTensor, LongTensor, Size, Tensor
 from torch.distributions import Transform
@@ -47,6 +49,35 @@ def dag_diameter(adjacency: BoolTensor) -> int:
         frontier = nxt
     assert resolved == n, "The graph contains cycles."
     return generations
+
+
+def reindex_conditioner(i: int, n: int, w: Tensor, b: Tensor | None, mask: Tensor | None, *, qi: Tensor, D: int, P: int):
+    """Tensors of linear layer ``i`` of ``n`` of an autoregressive conditioner re-indexed by the feature permutation
+    ``q`` (``qi`` as a LongTensor): the layer ``T~`` with ``T(P x) = P T~(x)`` for ``(P x)_j = x_{q[j]}`` reads
+    feature ``q[j]`` where ``T`` read its input ``j`` (first layer: ``W~[:, q[j]] = W[:, j]`` for the D x-columns, the
+    context columns stay) and emits the parameters of feature ``q[j]`` where ``T`` emitted those of ``j`` (last
+    layer: block ``q[j]`` of P rows = block ``j``)."""
+    if i == 0:
+        w2 = w.clone()
+        w2[:, qi] = w[:, :D]
+        w = w2
+        if mask is not None:
+            m2 = mask.clone()
+            m2[:, qi] = mask[:, :D]
+            mask = m2
+    if i == n - 1:
+        w2 = torch.empty_like(w)
+        w2.view(D, P, -1)[qi] = w.view(D, P, -1)
+        w = w2
+        if b is not None:
+            b2 = torch.empty_like(b)
+            b2.view(D, P)[qi] = b.view(D, P)
+            b = b2
+        if mask is not None:
+            m2 = torch.empty_like(mask)
+            m2.view(D, P, -1)[qi] = mask.view(D, P, -1)
+            mask = m2
+    return w, b, mask
 
 
 class MaskedAutoregressiveTransform(PackedLayerMixin, LazyTransform):
@@ -136,6 +167,53 @@ class MaskedAutoregressiveTransform(PackedLayerMixin, LazyTransform):
             desc.order = arr
             keep.append(arr)
         return desc, keep
+
+    def _zk_layer_ref_reindexed(self, q: tuple):
+        """The handle of this layer conjugated by a feature permutation: with ``(P x)_i = x_{q[i]}``,
+        ``T(P x) = P T~(x)`` where ``T~`` is the same layer with the conditioner's x-input columns and its per-dimension
+        output blocks re-indexed (``W0~[:, q] = W0[:, :D]``, block ``q[i]`` of the last layer = block ``i``, ``order~[q] =
+        order``) — a permutation in front of an autoregressive layer (zuko/transforms.py:1193-1214 feeding
+        flows/autoregressive.py:207-215) costs nothing but this re-packing.  Forward-only (no gradient sources);
+        cached per (layer signature, q)."""
+        from ._packed import OwnedLayer
+
+        sig = (self._layer_signature(), tuple(q))
+        cache = self.__dict__.setdefault("_zk_reindexed", {})
+        hit = cache.get(tuple(q))
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        import ctypes
+
+        D, P = self.features, self.total
+        dev = self.hyper._linears()[0].weight.device
+        qi = torch.as_tensor(list(q), dtype=torch.long, device=dev)
+
+        reindex = partial(reindex_conditioner, qi=qi, D=D, P=P)
+
+        hyper, keep = self.hyper.mlp_desc(reindex)
+        desc = self._base_desc(E.ZK_LAYER_AUTOREGRESSIVE)
+        desc.hyper = ctypes.pointer(hyper)
+        keep = [hyper, keep]
+        if self.order is not None:
+            host = self.order.detach().to("cpu", torch.int64)
+            ro = torch.empty_like(host)
+            ro[torch.as_tensor(list(q), dtype=torch.long)] = host
+            arr = (ctypes.c_int64 * D)(*ro.tolist())
+            desc.order = arr
+            keep.append(arr)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            E.lib().zk_set_pack_stream(E.stream_ptr(dev))
+            try:
+                E.check(E.lib().zk_layer_create(ctypes.byref(desc), ctypes.byref(h)))
+            finally:
+                E.lib().zk_set_pack_stream(None)
+        del keep
+        ref = OwnedLayer(h)
+        if len(cache) > 8:
+            cache.clear()
+        cache[tuple(q)] = (sig, ref)
+        return ref
 
     def forward(self, c: Tensor | None = None) -> Transform:
         return AutoregressiveTransform(self, c)

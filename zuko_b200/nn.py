@@ -158,8 +158,10 @@ class _EngineMLP(nn.Sequential):
                 sig.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
         return tuple(sig)
 
-    def mlp_desc(self) -> tuple[E.MlpDesc, list]:
-        """Builds the ``zk_mlp_desc`` for the current parameters. Returns (desc, keepalive)."""
+    def mlp_desc(self, reindex=None) -> tuple[E.MlpDesc, list]:
+        """Builds the ``zk_mlp_desc`` for the current parameters. Returns (desc, keepalive).
+        ``reindex(i, n, weight, bias, mask)`` may substitute the tensors of linear layer ``i`` of ``n`` (used to
+        re-index a conditioner's input columns / output rows when a permutation is folded into the layer)."""
         lins = self._linears()
         n = len(lins)
         keep: list = []
@@ -169,14 +171,16 @@ class _EngineMLP(nn.Sequential):
         M = (ctypes.c_void_p * n)()
         for i, m in enumerate(lins):
             E.require_cuda(m.weight, "conditioner weight")
-            w = m.weight.detach().contiguous()
+            w_src, b_src, mask = m.weight.detach(), (None if m.bias is None else m.bias.detach()), getattr(m, "mask", None)
+            if reindex is not None:
+                w_src, b_src, mask = reindex(i, n, w_src, b_src, mask)
+            w = w_src.contiguous()
             keep.append(w)
             W[i] = w.data_ptr()
-            if m.bias is not None:
-                b = m.bias.detach().contiguous()
+            if b_src is not None:
+                b = b_src.contiguous()
                 keep.append(b)
                 Bv[i] = b.data_ptr()
-            mask = getattr(m, "mask", None)
             if mask is not None:
                 mk = mask.detach().to(torch.uint8).contiguous()
                 keep.append(mk)

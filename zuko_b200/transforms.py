@@ -616,14 +616,62 @@ class ComposedTransform(EngineTransform):
         if ok:
             handles = [r.handle for r in refs]
             call = (_ops.FlowCall(handles, D, C, None, None, sources=sources, keep=refs, inverted=inverted), ctx)
+            call[0].folded = self._folded(D, C, refs, inverted)
         self.__dict__[key] = call
         return call
+
+    def _folded(self, D: int, C: int, refs: list, inverted: list):
+        """The same bijection with every ``PermutationTransform`` that feeds an autoregressive layer folded INTO that
+        layer (zuko/transforms.py:1193-1214): with ``(P x)_i = x_{q[i]}``, ``T(P x) = P T~(x)`` for the
+        layer ``T~`` re-indexed by ``q`` (``MaskedAutoregressiveTransform._zk_layer_ref_reindexed``), and a soft clip
+        commutes with ``P`` — so the permutation is carried along as a pending re-indexing ``q`` of the stored vector,
+        and a gather kernel runs only where a member that cannot be re-indexed (coupling, rotation, element-wise
+        tables) needs the true order, or at the end when ``q`` is not the identity (two reversals cancel).  A
+        forward-only ``FlowCall`` (no gradient sources), or ``None`` when nothing folds."""
+        from .flows.autoregressive import MaskedAutoregressiveTransform
+
+        members = []
+        for t in self.transforms:
+            members.append(t._t if isinstance(t, _InverseOf) and isinstance(t._t, AutoregressiveTransform) else t)
+        if not any(isinstance(t, PermutationTransform) for t in members):
+            return None
+        ident = tuple(range(D))
+        q = ident
+        out_refs, out_inv = [], []
+
+        def flush():
+            nonlocal q
+            if q != ident:
+                out_refs.append(_simple_layer_handle(PermutationTransform(torch.tensor(q, dtype=torch.long)), D))
+                out_inv.append(False)
+                q = ident
+
+        for t, ref, inv in zip(members, refs, inverted):
+            if isinstance(t, PermutationTransform):
+                sigma = t.order.detach().to("cpu", torch.int64).tolist()
+                if sorted(sigma) != list(ident):
+                    return None
+                q = tuple(q[j] for j in sigma)  # true'_i = true_{sigma[i]} = stored_{q[sigma[i]]}
+            elif isinstance(t, AutoregressiveTransform) and isinstance(t._owner, MaskedAutoregressiveTransform):
+                out_refs.append(ref if q == ident else t._owner._zk_layer_ref_reindexed(q))
+                out_inv.append(inv)
+            elif isinstance(t, SoftclipTransform):
+                out_refs.append(ref)  # element-wise with one bound: S(P x) = P S(x), the ladj sum does not see the order
+                out_inv.append(inv)
+            else:
+                flush()
+                out_refs.append(ref)
+                out_inv.append(inv)
+        flush()
+        if len(out_refs) >= len(refs):
+            return None  # no kernel saved
+        return _ops.FlowCall([r.handle for r in out_refs], D, C, None, None, sources=None, keep=out_refs, inverted=out_inv)
 
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
         fused = self._fused(x.shape[-1]) if x.dim() >= 1 else None
         if fused is not None and fused[0].usable(x, fused[1]):
             call, ctx = fused
-            return call.forward(x, ctx)
+            return call.best(x, ctx).forward(x, ctx)
         event_dim = self.domain_dim
         acc = 0
         for t in self.transforms:
@@ -636,7 +684,7 @@ class ComposedTransform(EngineTransform):
         fused = self._fused(y.shape[-1]) if y.dim() >= 1 else None
         if fused is not None and fused[0].usable(y, fused[1]):
             call, ctx = fused
-            return call.inverse(y, ctx)
+            return call.best(y, ctx).inverse(y, ctx)
         for t in reversed(self.transforms):
             y = t.inv(y)
         return y
