@@ -529,6 +529,22 @@ def _simple_layer_handle(t: Transform, D: int):
     return cache[key]
 
 
+_FOLD_PERMS: dict = {}
+
+
+def _fold_perm_handle(q: tuple):
+    """The gather layer that materialises a pending re-indexing ``q`` (ComposedTransform._folded): the composed
+    transform is rebuilt on every ``flow(c)`` call, so these handles are kept per (device, q) — no allocation per call."""
+    key = (torch.cuda.current_device() if torch.cuda.is_available() else -1, q)
+    ref = _FOLD_PERMS.get(key)
+    if ref is None:
+        if len(_FOLD_PERMS) >= 64:
+            _FOLD_PERMS.clear()
+        ref = _simple_layer_handle(PermutationTransform(torch.tensor(q, dtype=torch.long)), len(q))
+        _FOLD_PERMS[key] = ref
+    return ref
+
+
 class _OwnedLayer:
     def __init__(self, handle) -> None:  # noqa: ANN001
         self.handle = handle
@@ -642,13 +658,15 @@ class ComposedTransform(EngineTransform):
         def flush():
             nonlocal q
             if q != ident:
-                out_refs.append(_simple_layer_handle(PermutationTransform(torch.tensor(q, dtype=torch.long)), D))
+                out_refs.append(_fold_perm_handle(q))
                 out_inv.append(False)
                 q = ident
 
         for t, ref, inv in zip(members, refs, inverted):
             if isinstance(t, PermutationTransform):
-                sigma = t.order.detach().to("cpu", torch.int64).tolist()
+                sigma = t.__dict__.get("_order_host")  # the object is cached by its lazy module: one download, not one per call
+                if sigma is None:
+                    sigma = t.__dict__["_order_host"] = t.order.detach().to("cpu", torch.int64).tolist()
                 if sorted(sigma) != list(ident):
                     return None
                 q = tuple(q[j] for j in sigma)  # true'_i = true_{sigma[i]} = stored_{q[sigma[i]]}
