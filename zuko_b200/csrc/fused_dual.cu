@@ -354,15 +354,38 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                     tc_fence_after();
                     if (l < 4) W_STAMP(sbase + 8 + 8 * l + 2 * ch);
                     const int nbase = ch * 128 + s * 64;  // first output column of this thread = K index of the next layer
+                    // All 64 columns of the set are pulled first and the accumulator is released BEFORE the
+                    // arithmetic (ReLU only): the next chunk of this sub-tile waits for this arrive, and four
+                    // load / wait / convert rounds took ~1.4 k cycles (profiles/r02_dual_timeline_recapture.txt).
                     uint32_t ph[32], pl[32];
+                    if constexpr (!GACT) {
+                        uint32_t ra[64];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // four groups of 16 columns
-                        const float4* b4 = reinterpret_cast<const float4*>(bias + nbase + 16 * g);
-                        uint32_t ra[16];
-                        tmem_ld_x16(t_lane + d_col0 + (uint32_t)(s * 64 + 16 * g), ra);
+                        for (int g = 0; g < 4; ++g) tmem_ld_x16(t_lane + d_col0 + (uint32_t)(s * 64 + 16 * g), ra + 16 * g);
                         tmem_ld_wait();
-                        if constexpr (GACT) {  // any ZK_ACT_* (nn.py:264-265): one switch per 16 columns
-                            float v[16];
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(d_empty_r);  // this sub-tile's accumulator is drained
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + nbase + 16 * g);
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bb = b4[j >> 2];
+                                split2_bf16(fmaxf(__uint_as_float(ra[16 * g + j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[16 * g + j + 1]) + bb.y, 0.f),
+                                            ph[8 * g + (j >> 1)], pl[8 * g + (j >> 1)]);
+                                split2_bf16(fmaxf(__uint_as_float(ra[16 * g + j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[16 * g + j + 3]) + bb.w, 0.f),
+                                            ph[8 * g + (j >> 1) + 1], pl[8 * g + (j >> 1) + 1]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {  // four groups of 16 columns
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + nbase + 16 * g);
+                            uint32_t ra[16];
+                            tmem_ld_x16(t_lane + d_col0 + (uint32_t)(s * 64 + 16 * g), ra);
+                            tmem_ld_wait();
+                            float v[16];  // any ZK_ACT_* (nn.py:264-265): one switch per 16 columns
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 bb = b4[j >> 2];
@@ -372,20 +395,11 @@ fused_dual_kernel(const __grid_constant__ DualParams p) {
                             if constexpr (FAST) act_apply_n_fast<16>(v, p.act); else act_apply_n<16>(v, p.act);
 #pragma unroll
                             for (int j = 0; j < 16; j += 2) split2_bf16(v[j], v[j + 1], ph[8 * g + (j >> 1)], pl[8 * g + (j >> 1)]);
-                        } else {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = b4[j >> 2];
-                            split2_bf16(fmaxf(__uint_as_float(ra[j]) + bb.x, 0.f), fmaxf(__uint_as_float(ra[j + 1]) + bb.y, 0.f),
-                                        ph[8 * g + (j >> 1)], pl[8 * g + (j >> 1)]);
-                            split2_bf16(fmaxf(__uint_as_float(ra[j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(ra[j + 3]) + bb.w, 0.f),
-                                        ph[8 * g + (j >> 1) + 1], pl[8 * g + (j >> 1) + 1]);
                         }
-                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(d_empty_r);  // this sub-tile's accumulator is drained
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(d_empty_r);  // this sub-tile's accumulator is drained
                     if (l < 4) W_STAMP(sbase + 100 + 2 * l + ch);
                     for (int kb = 2 * ch; kb < 2 * ch + 2; ++kb)
                         if ((rd >> kb) & 1u) {
