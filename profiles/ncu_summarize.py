@@ -53,7 +53,7 @@ def section(title, name):
 
 
 t, _ = val("dual_cfg2", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
-section(f"`fused_dual_kernel<RQS,8>` — one layer of cfg2 (NSF(16, 8, K8, [256]³)), 2²⁰ rows: tensor pipe {t:.0f} % active (58 % before the all-zero MMA steps of diagonal K blocks stopped being issued — 4.7 % fewer MMAs in the same time; round 1: 47 % on `fused_layer_kernel`); DRAM 107 MB per launch against 172 MB algorithmic incl. the broadcast-free context", "dual_cfg2")
+section(f"`fused_dual_kernel<RQS,8>` — one layer of cfg2 (NSF(16, 8, K8, [256]³)), 2²⁰ rows: tensor pipe {t:.0f} % active (final kernel: accumulator released before the hidden-chunk arithmetic; 55 % without that, 58 % before the all-zero MMA steps of diagonal K blocks stopped being issued — 4.7 % fewer MMAs in the same time; round 1: 47 % on `fused_layer_kernel`); DRAM 107 MB per launch against 172 MB algorithmic incl. the broadcast-free context", "dual_cfg2")
 t, _ = val("wide_cfg3", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
 section(f"`fused_wide_kernel<AFFINE>` — one layer of cfg3 (MAF(32, [512]⁴)), 2²⁰ rows: tensor pipe {t:.0f} % active (82 % before the step trimming, 9 % fewer MMAs), DRAM 144 MB = the algorithmic x in / y, ladj out; weights stream from L2", "wide_cfg3")
 t, _ = val("wide_cfg5", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
