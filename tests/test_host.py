@@ -267,3 +267,60 @@ def test_folding_a_permutation_into_an_autoregressive_layer(rqs):
     # inverse: T^-1(P z) = P T~^-1(z)
     z = g.standard_normal((64, D)) * 0.5
     assert np.allclose(s1.inverse(z[:, qn], c), s2.inverse(z, c)[:, qn], rtol=1e-9, atol=1e-9)
+
+
+def test_permutation_fold_plan_is_the_same_bijection():
+    """transforms.plan_permutation_fold on random member sequences, simulated with numpy: "reindex" members are
+    order-dependent maps f_i (so that a wrong re-indexing shows), their re-indexed form is f~(s) = P^-1 f(P s);
+    "commute" members act element-wise, "fixed" members are order-dependent and may not be re-indexed.  The planned
+    sequence must give the sequential result, and never runs more members than the original."""
+    import numpy as np
+
+    from zuko_b200.transforms import plan_permutation_fold
+
+    rng = np.random.default_rng(0)
+    D = 7
+    n_plans = 0
+    for trial in range(300):
+        n = int(rng.integers(1, 9))
+        kinds = [str(rng.choice(["perm", "perm", "reindex", "reindex", "commute", "fixed"])) for _ in range(n)]
+        sigmas = [rng.permutation(D).tolist() if k == "perm" else None for k in kinds]
+        mats = [rng.standard_normal((D, D)) for _ in range(n)]  # an order-dependent map per member
+
+        def apply(i, v):
+            if kinds[i] == "perm":
+                return v[sigmas[i]]
+            if kinds[i] == "commute":
+                return np.tanh(v) + 0.1 * i
+            return np.tanh(mats[i] @ v) + np.arange(D) * 0.01  # "reindex" / "fixed": depends on the feature order
+
+        x = rng.standard_normal(D)
+        ref = x.copy()
+        for i in range(n):
+            ref = apply(i, ref)
+        plan = plan_permutation_fold(kinds, sigmas, D)
+        if plan is None:
+            continue
+        n_plans += 1
+        assert len(plan) < n
+        s = x.copy()
+        for act in plan:
+            if act[0] == "gather":
+                s = s[list(act[1])]
+                continue
+            _, i, q = act
+            assert kinds[i] != "perm" and (q is None or kinds[i] == "reindex")
+            if q is None:
+                s = apply(i, s)
+            else:  # T~(s) = P^-1 T(P s) with (P v)_j = v[q[j]]
+                qq = list(q)
+                out = np.empty(D)
+                out[qq] = apply(i, s[qq])
+                s = out
+        assert np.allclose(s, ref, rtol=0, atol=1e-12), (kinds, plan)
+    assert n_plans > 50
+    # two reversals around a layer cancel: no gather at all
+    rev = list(range(D))[::-1]
+    assert plan_permutation_fold(["perm", "reindex", "perm"], [rev, None, rev], D) == [("member", 1, tuple(rev))]
+    assert plan_permutation_fold(["perm", "fixed"], [rev, None], D) is None          # gather + member: nothing saved
+    assert plan_permutation_fold(["perm", "reindex"], [[0, 0, 1, 2, 3, 4, 5], None], D) is None  # not a permutation

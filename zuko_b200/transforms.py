@@ -34,6 +34,7 @@ __all__ = [
 
 import ctypes
 import math
+from collections.abc import Sequence
 from textwrap import indent
 
 import torch
@@ -556,6 +557,36 @@ class _OwnedLayer:
             pass
 
 
+def plan_permutation_fold(kinds: Sequence[str], sigmas: Sequence, D: int):
+    """Bookkeeping of ComposedTransform._folded, free of engine objects (CPU-tested).  ``kinds[i]`` says what member i
+    is: ``"perm"`` (``y = x[sigmas[i]]``), ``"reindex"`` (an autoregressive layer: ``T(P x) = P T~_q(x)``),
+    ``"commute"`` (``S(P x) = P S(x)``) or ``"fixed"`` (needs the true feature order).  The stored vector ``s`` and
+    the true one ``t`` are related by a pending re-indexing ``t[j] = s[q[j]]``.  Returns the list of actions
+    ``("member", i, q or None)`` (run member i, re-indexed by q unless None) / ``("gather", q)`` (``s <- s[q]``), or
+    ``None`` when a permutation is malformed or no kernel is saved."""
+    ident = tuple(range(D))
+    q = ident
+    plan: list[tuple] = []
+    for i, kind in enumerate(kinds):
+        if kind == "perm":
+            sigma = list(sigmas[i])
+            if sorted(sigma) != list(ident):
+                return None
+            q = tuple(q[j] for j in sigma)  # t'[j] = t[sigma[j]] = s[q[sigma[j]]]
+        elif kind == "reindex":
+            plan.append(("member", i, None if q == ident else q))
+        elif kind == "commute":
+            plan.append(("member", i, None))
+        else:
+            if q != ident:
+                plan.append(("gather", q))
+                q = ident
+            plan.append(("member", i, None))
+    if q != ident:
+        plan.append(("gather", q))
+    return plan if len(plan) < len(kinds) else None
+
+
 class ComposedTransform(EngineTransform):
     """``f = f_n ∘ ... ∘ f_0`` (zuko/transforms.py:59-160).
 
@@ -651,38 +682,34 @@ class ComposedTransform(EngineTransform):
             members.append(t._t if isinstance(t, _InverseOf) and isinstance(t._t, AutoregressiveTransform) else t)
         if not any(isinstance(t, PermutationTransform) for t in members):
             return None
-        ident = tuple(range(D))
-        q = ident
-        out_refs, out_inv = [], []
-
-        def flush():
-            nonlocal q
-            if q != ident:
-                out_refs.append(_fold_perm_handle(q))
-                out_inv.append(False)
-                q = ident
-
-        for t, ref, inv in zip(members, refs, inverted):
+        kinds, sigmas = [], []
+        for t in members:
+            sigma = None
             if isinstance(t, PermutationTransform):
+                kind = "perm"
                 sigma = t.__dict__.get("_order_host")  # the object is cached by its lazy module: one download, not one per call
                 if sigma is None:
                     sigma = t.__dict__["_order_host"] = t.order.detach().to("cpu", torch.int64).tolist()
-                if sorted(sigma) != list(ident):
-                    return None
-                q = tuple(q[j] for j in sigma)  # true'_i = true_{sigma[i]} = stored_{q[sigma[i]]}
             elif isinstance(t, AutoregressiveTransform) and isinstance(t._owner, MaskedAutoregressiveTransform):
-                out_refs.append(ref if q == ident else t._owner._zk_layer_ref_reindexed(q))
-                out_inv.append(inv)
+                kind = "reindex"
             elif isinstance(t, SoftclipTransform):
-                out_refs.append(ref)  # element-wise with one bound: S(P x) = P S(x), the ladj sum does not see the order
-                out_inv.append(inv)
+                kind = "commute"  # element-wise with one bound: S(P x) = P S(x), the ladj sum does not see the order
             else:
-                flush()
-                out_refs.append(ref)
-                out_inv.append(inv)
-        flush()
-        if len(out_refs) >= len(refs):
-            return None  # no kernel saved
+                kind = "fixed"
+            kinds.append(kind)
+            sigmas.append(sigma)
+        plan = plan_permutation_fold(kinds, sigmas, D)
+        if plan is None:
+            return None
+        out_refs, out_inv = [], []
+        for act in plan:
+            if act[0] == "gather":
+                out_refs.append(_fold_perm_handle(act[1]))
+                out_inv.append(False)
+            else:
+                _, i, q = act
+                out_refs.append(refs[i] if q is None else members[i]._owner._zk_layer_ref_reindexed(q))
+                out_inv.append(inverted[i])
         return _ops.FlowCall([r.handle for r in out_refs], D, C, None, None, sources=None, keep=out_refs, inverted=out_inv)
 
     def call_and_ladj(self, x: Tensor) -> tuple[Tensor, Tensor]:
