@@ -48,3 +48,18 @@ def test_clock_sampler_without_gpu_is_harmless():
         pass
     s = clk.summary()
     assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"} and isinstance(s["reasons"], list)
+
+
+def test_tensor_roofline_denominator_follows_the_clock():
+    """bench.tensor_peak: the cuBLAS burst figure when the run held >= 98 % of the maximum SM clock, else that figure
+    scaled to the clock actually held (a power-capped run is measured against the pipe's capacity at its clock, not
+    against a 'sustained' number taken at some other clock) — never a fraction that the kind string does not explain."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    peaks = {"bf16_tflops": 1640.0, "bf16_tflops_sustained": 1368.6}
+    assert bench.tensor_peak(peaks, {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}) == (1640.0, "burst")
+    assert bench.tensor_peak(peaks, {"sm_mhz": 1935.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"]}) == (1640.0, "burst")
+    peak, kind = bench.tensor_peak(peaks, {"sm_mhz": 1680.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"]})
+    assert abs(peak - 1640.0 * 1680.0 / 1965.0) < 1e-9 and "1680" in kind and "burst" in kind
+    assert bench.tensor_peak(peaks, {}) == (1640.0, "burst")  # no NVML: nothing to scale by
