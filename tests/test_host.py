@@ -324,3 +324,25 @@ def test_permutation_fold_plan_is_the_same_bijection():
     assert plan_permutation_fold(["perm", "reindex", "perm"], [rev, None, rev], D) == [("member", 1, tuple(rev))]
     assert plan_permutation_fold(["perm", "fixed"], [rev, None], D) is None          # gather + member: nothing saved
     assert plan_permutation_fold(["perm", "reindex"], [[0, 0, 1, 2, 3, 4, 5], None], D) is None  # not a permutation
+
+
+def test_flow_call_picks_the_folded_sibling_only_without_gradients():
+    """_ops.FlowCall.best: the permutation-folded (forward-only) sibling serves a call exactly when nothing has to be
+    differentiated — no grad mode, or no input / context / parameter / base tensor that requires grad."""
+    from zuko_b200 import _ops
+
+    w = torch.nn.Parameter(torch.zeros(3))
+    plain = _ops.FlowCall([1, 2, 3], 4, 2, None, None, sources=[{"weights": [w], "biases": [None]}, {}, {}])
+    folded = _ops.FlowCall([1, 3], 4, 2, None, None, sources=None)
+    x, c = torch.zeros(5, 4), torch.zeros(5, 2)
+    assert plain.best(x, c) is plain  # nothing folded yet
+    plain.folded = folded
+    with torch.no_grad():
+        assert plain.best(x, c) is folded
+        assert plain.best(x.clone().requires_grad_(), c) is folded
+    assert plain.best(x, c) is plain  # grad mode and a parameter that requires grad
+    w.requires_grad_(False)
+    assert plain.best(x, c) is folded
+    assert plain.best(x.clone().requires_grad_(), c) is plain
+    assert plain.best(x, c.clone().requires_grad_()) is plain
+    assert folded.best(x, c) is folded and folded.usable(x, c)
